@@ -1,0 +1,237 @@
+"""``Unet`` -- drop-in for ``flocoder.unet.Unet`` on the sampling path (inference).
+
+Same constructor arguments, same ``state_dict`` names/shapes/order and the same
+``forward(x, time, cond=None)`` contract as the reference (``flocoder/unet.py:164-377``),
+but the module tree only *holds parameters*: the forward pass is one call into the
+sm_100a C-ABI library (``include/flocoder_b200.h``), never PyTorch ops.  There is no CPU
+or eager fallback -- off-GPU, or without the built library, ``forward`` raises.
+
+Construction order of the parameterised leaves (Conv2d / Linear / Embedding) follows the
+reference's ``__init__`` (``unet.py:185-286``) so that the same ``torch.manual_seed`` yields
+bit-identical random-init weights; ``tests/test_unet_module.py`` checks this against the
+frozen fingerprints in ``tests/golden``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib
+
+HEADS, DIM_HEAD = 4, 32          # unet.py:100,126 defaults; Unet never overrides them
+
+
+def key_usable(d, key) -> bool:
+    """general.py:18-20."""
+    return (d is not None) and isinstance(d, dict) and (d.get(key) is not None)
+
+
+class _Holder(nn.Module):
+    """A parameter container whose children are registered under explicit names
+    (including numeric ones such as ``"1"``), so state_dict keys match the reference's
+    ``nn.Sequential`` / wrapper nesting without reproducing those classes."""
+
+    def __init__(self, **children):
+        super().__init__()
+        for k, v in children.items():
+            self.add_module(k.lstrip("_"), v)
+
+    def put(self, name: str, module: nn.Module) -> nn.Module:
+        self.add_module(str(name), module)
+        return module
+
+
+def _resnet_holder(dim_in: int, dim_out: int, time_dim: int, groups: int) -> _Holder:
+    """Parameters of ResnetBlock (unet.py:76-86): mlp.1, block{1,2}.{proj,norm}, [res_conv]."""
+    rb = _Holder()
+    rb.put("mlp", _Holder()).put("1", nn.Linear(time_dim, dim_out * 2))
+    for name, cin in (("block1", dim_in), ("block2", dim_out)):
+        blk = rb.put(name, _Holder())
+        blk.put("proj", nn.Conv2d(cin, dim_out, 3, padding=1))
+        blk.put("norm", nn.GroupNorm(groups, dim_out))
+    if dim_in != dim_out:
+        rb.put("res_conv", nn.Conv2d(dim_in, dim_out, 1))
+    return rb
+
+
+def _attn_holder(dim: int, linear: bool) -> _Holder:
+    """Residual(PreNorm(dim, [Linear]Attention(dim))) -> '<p>.fn.fn.*' then '<p>.fn.norm.*'
+    (unet.py:33-39,99-106,125-133,153-157)."""
+    hidden = HEADS * DIM_HEAD
+    core = _Holder()
+    core.put("to_qkv", nn.Conv2d(dim, hidden * 3, 1, bias=False))
+    if linear:
+        out = core.put("to_out", _Holder())
+        out.put("0", nn.Conv2d(hidden, dim, 1))
+        out.put("1", nn.GroupNorm(1, dim))
+    else:
+        core.put("to_out", nn.Conv2d(hidden, dim, 1))
+    prenorm = _Holder()
+    prenorm.put("fn", core)
+    prenorm.put("norm", nn.GroupNorm(1, dim))
+    res = _Holder()
+    res.put("fn", prenorm)
+    return res
+
+
+class Unet(nn.Module):
+    """Velocity-field U-Net whose forward runs on hand-written sm_100a kernels.
+
+    Extra (non-reference) keyword: ``compute_dtype`` -- ``None`` (follow the parameter
+    dtype: fp32 params -> fp32 kernels, bf16 params -> bf16 tensor-core kernels),
+    ``"fp32"`` or ``"bf16"`` (e.g. fp32 master parameters with bf16 tcgen05 convolutions).
+    Time embedding, MLPs, GroupNorm statistics, softmax and the integrator state are fp32
+    in every mode.
+    """
+
+    def __init__(self, dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=4,
+                 n_classes=10, mask_cond=False, use_checkpoint=False, compute_dtype: Optional[str] = None):
+        super().__init__()
+        if mask_cond:
+            raise NotImplementedError(
+                "mask_cond=True (inpainting U-Net) is outside the B200 sampling path (SURVEY.md 8f N3)")
+        self.use_checkpoint = use_checkpoint          # accepted for signature parity; inference only
+        self.dim = dim
+        self.dim_mults = tuple(int(m) for m in dim_mults)
+        self.channels = channels
+        self.out_dim = channels
+        self.groups = resnet_block_groups
+        self.n_classes = int(n_classes)
+        self.class_condition = n_classes > 0
+        self.compute_dtype = compute_dtype
+
+        dims = [dim] + [dim * m for m in self.dim_mults]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        time_dim = dim * 8
+        g = resnet_block_groups
+
+        self.init_conv = nn.Conv2d(channels, dim, 1, padding=0)
+        self.time_mlp = _Holder()
+        self.time_mlp.put("1", nn.Linear(dim, time_dim))
+        self.time_mlp.put("3", nn.Linear(time_dim, time_dim))
+        if self.class_condition:
+            self.class_cond_mlp = _Holder()
+            self.class_cond_mlp.put("0", nn.Embedding(n_classes, time_dim))
+            self.class_cond_mlp.put("1", nn.Linear(time_dim, time_dim))
+            self.class_cond_mlp.put("3", nn.Linear(time_dim, time_dim))
+
+        self.downs = nn.ModuleList()
+        n_res = len(in_out)
+        for i, (d_in, d_out) in enumerate(in_out):
+            last = i >= n_res - 1
+            stage = nn.ModuleList([
+                _resnet_holder(d_in, d_in, time_dim, g),
+                _resnet_holder(d_in, d_in, time_dim, g),
+                _attn_holder(d_in, linear=True),
+            ])
+            if last:
+                stage.append(nn.Conv2d(d_in, d_out, 3, padding=1))
+            else:
+                down = _Holder()
+                down.put("1", nn.Conv2d(d_in * 4, d_out, 1))
+                stage.append(down)
+            self.downs.append(stage)
+
+        mid = dims[-1]
+        self.mid_block1 = _resnet_holder(mid, mid, time_dim, g)
+        self.mid_attn = _attn_holder(mid, linear=False)
+        self.mid_block2 = _resnet_holder(mid, mid, time_dim, g)
+
+        self.ups = nn.ModuleList()
+        for i, (d_in, d_out) in enumerate(reversed(in_out)):
+            last = i == n_res - 1
+            stage = nn.ModuleList([
+                _resnet_holder(d_out + d_in, d_out, time_dim, g),
+                _resnet_holder(d_out + d_in, d_out, time_dim, g),
+                _attn_holder(d_out, linear=True),
+            ])
+            if last:
+                stage.append(nn.Conv2d(d_out, d_in, 3, padding=1))
+            else:
+                up = _Holder()
+                up.put("1", nn.Conv2d(d_out, d_in, 3, padding=1))
+                stage.append(up)
+            self.ups.append(stage)
+
+        self.final_res_block = _resnet_holder(dim * 2, dim, time_dim, g)
+        self.final_conv = nn.Conv2d(dim, channels, 1)
+
+        self._engine = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ engine
+    def _resolved_compute_dtype(self) -> str:
+        if self.compute_dtype is not None:
+            if self.compute_dtype not in ("fp32", "bf16"):
+                raise ValueError(f"compute_dtype must be None, 'fp32' or 'bf16', got {self.compute_dtype!r}")
+            return self.compute_dtype
+        p = next(self.parameters())
+        if p.dtype == torch.float32:
+            return "fp32"
+        if p.dtype == torch.bfloat16:
+            return "bf16"
+        raise TypeError(f"unsupported parameter dtype {p.dtype}: the B200 path computes in fp32 or bf16")
+
+    def _params_key(self, height: int, width: int):
+        ps = list(self.parameters())
+        return (ps[0].device, self._resolved_compute_dtype(), height, width,
+                tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps))
+
+    def engine(self, height: int, width: int) -> "_lib.Engine":
+        """The native handle for this module's current parameters (re-packed when they change)."""
+        key = self._params_key(height, width)
+        if self._engine is None or key != self._engine_key:
+            dev = key[0]
+            if dev.type != "cuda":
+                raise RuntimeError(
+                    "flocoder_b200.Unet runs only on a CUDA (sm_100a) device; there is no CPU fallback. "
+                    f"Parameters are on {dev}.")
+            if self._engine is not None:
+                self._engine.close()
+            sd = self.state_dict()
+            self._engine = _lib.Engine(
+                dim=self.dim, channels=self.channels, dim_mults=self.dim_mults, groups=self.groups,
+                n_classes=self.n_classes, height=height, width=width, compute_dtype=key[1],
+                device=dev, state_dict=sd)
+            self._engine_key = key
+        return self._engine
+
+    def invalidate(self):
+        if self._engine is not None:
+            self._engine.close()
+        self._engine, self._engine_key = None, None
+
+    @staticmethod
+    def split_cond(cond):
+        """Returns the class-id tensor (or None) exactly as unet.py:298,313-320 would consume ``cond``."""
+        if key_usable(cond, "mask_cond"):
+            raise NotImplementedError("cond['mask_cond'] needs the inpainting U-Net (mask_cond=True), "
+                                      "which is outside the B200 sampling path")
+        if cond is None:
+            return None
+        if not isinstance(cond, dict):
+            # the reference's non-dict branch dies on warnings.DeprecationWarning (unet.py:318)
+            raise TypeError("non-dict cond is not supported; use cond={'class_cond': LongTensor[B]}")
+        return cond.get("class_cond")
+
+    # ----------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, time: torch.Tensor, cond=None) -> torch.Tensor:
+        """x: [B,C,H,W]; time: [B] already scaled by 999 (sampling.py:63); returns v [B,C,H,W]."""
+        if x.dim() != 4 or x.shape[1] != self.channels:
+            raise ValueError(f"x must be [B,{self.channels},H,W], got {tuple(x.shape)}")
+        cls = self.split_cond(cond)
+        if cls is not None and not self.class_condition:
+            cls = None                                   # unet.py:315 hasattr(self,'class_cond_mlp')
+        b, _, h, w = x.shape
+        eng = self.engine(h, w)
+        if x.device != eng.device:
+            raise RuntimeError(f"x is on {x.device} but the model is on {eng.device}")
+        time = time.to(device=x.device, dtype=torch.float32).reshape(-1)
+        if time.numel() != b:
+            raise ValueError(f"time must have {b} elements, got {time.numel()}")
+        v = eng.forward(x.to(torch.float32).contiguous(), time.contiguous(), cls)
+        return v.to(x.dtype)

@@ -1,0 +1,138 @@
+/*
+ * flocoder_b200 -- C ABI of the B200 (sm_100a) latent flow-matching sampling path.
+ *
+ * This is the drop-in boundary for ONE hot path of drscotthawley/flocoder:
+ *   - the velocity field  Unet.forward(x, time, cond)          flocoder/unet.py:289-377
+ *   - the fixed-step ODE loop rk4_step / v_func_cfg /
+ *     generate_latents_rk4 / generate_latents                   flocoder/sampling.py:36-146
+ *   - the legacy Euler sampler                                   legacy/train_sd_flowers.py:50-67
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch); these entry points are
+ * what a ctypes/cffi binding for that path binds.  Plain pointers and
+ * sizes only -- no torch types.  Unless stated otherwise pointers are DEVICE pointers on the
+ * handle's device, calls are asynchronous on `stream` (a cudaStream_t passed as void*), do no
+ * host synchronisation, and return FLO_OK (0) or a negative flo_status; the message for the
+ * last failure on the calling thread is flo_last_error().  There is no CPU fallback.
+ *
+ * A handle is bound to one device and is not re-entrant (one in-flight call per handle).
+ */
+#ifndef FLOCODER_B200_H
+#define FLOCODER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLO_VERSION 100 /* 0.1.0 */
+
+typedef enum flo_status {
+    FLO_OK = 0,
+    FLO_ERR_INVALID = -1,     /* bad argument (ValueError in Python) */
+    FLO_ERR_UNSUPPORTED = -2, /* feature outside the built path, e.g. mask_cond (NotImplementedError) */
+    FLO_ERR_CUDA = -3,        /* CUDA runtime / driver failure (RuntimeError) */
+    FLO_ERR_NOMEM = -4
+} flo_status;
+
+typedef enum flo_dtype { FLO_F32 = 0, FLO_BF16 = 1 } flo_dtype;
+
+/* Integrators.  Stage times are formed in fp32 exactly as the reference forms them on 0-d
+ * tensors (sampling.py:44-47,117): dt = ts[i+1]-ts[i];  t, t+dt/2, t+dt;  time fed to the
+ * U-Net is fl32(t)*t_scale (sampling.py:63). */
+typedef enum flo_method {
+    FLO_RK4 = 0,          /* ts = time grid with n_ts points -> n_ts-1 classic RK4 intervals (sampling.py:37-48) */
+    FLO_EULER_LEGACY = 1, /* ts = the n_ts evaluation times t_i, fixed dt: x += v(x, t_i*t_scale)*dt
+                             (legacy/train_sd_flowers.py:58-64) */
+    FLO_EULER_GRID = 2    /* ts = time grid with n_ts points; forward Euler with dt_i = ts[i+1]-ts[i] */
+} flo_method;
+
+enum {
+    FLO_FLAG_NO_BUFFER_REUSE = 1, /* debug: every op output keeps its own buffer (flo_unet_read_activation) */
+    FLO_FLAG_NO_GRAPH = 2         /* debug: launch kernels directly instead of replaying a CUDA graph */
+};
+
+/* Constructor arguments of flocoder.unet.Unet (unet.py:165-175) + latent size + compute type. */
+typedef struct flo_unet_cfg {
+    int32_t dim;           /* Unet(dim=...)                         */
+    int32_t channels;      /* latent channels C                     */
+    int32_t n_mults;       /* len(dim_mults), 1..8                  */
+    int32_t mults[8];      /* dim_mults                             */
+    int32_t groups;        /* resnet_block_groups                   */
+    int32_t n_classes;     /* 0 = no class_cond_mlp                 */
+    int32_t height, width; /* latent H, W                           */
+    int32_t compute_dtype; /* flo_dtype: FLO_F32 = fp32 CUDA-core path (<=1e-5 parity),
+                              FLO_BF16 = bf16 tcgen05 convolutions, fp32 accumulate */
+    int32_t mask_cond;     /* must be 0 (inpainting U-Net is out of scope) */
+    int32_t flags;         /* FLO_FLAG_*                            */
+    int32_t device;        /* CUDA device ordinal                   */
+} flo_unet_cfg;
+
+typedef struct flo_unet flo_unet_t;
+
+int flo_version(void);
+const char* flo_last_error(void);
+
+/* Parameter manifest: the tensors of the reference state_dict, in state_dict order
+ * (e.g. "downs.0.2.fn.fn.to_qkv.weight").  Shapes are the reference's
+ * (OIHW conv weights, [out,in] linear weights). */
+int flo_param_count(const flo_unet_cfg* cfg);
+int flo_param_info(const flo_unet_cfg* cfg, int index, char* name, int name_cap, int64_t shape[4], int* ndim);
+
+/* Build a handle from fp32 device tensors given in manifest order; packs them into the
+ * kernels' layouts (replaces Unet.__init__ + load_state_dict, unet.py:165-286). */
+int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const* params, int n_params,
+                    void* stream);
+int flo_unet_destroy(flo_unet_t* h);
+
+/* Bytes of activation workspace the handle holds for batch size B. */
+size_t flo_workspace_bytes(flo_unet_t* h, int B);
+
+/* v = Unet.forward(x, time, cond)  (unet.py:374-377).
+ * x, v: [B,C,H,W] fp32 NCHW;  time: [B] fp32, already multiplied by t_scale;
+ * class_ids: [B] int64 or NULL (cond['class_cond'], unet.py:315-316). */
+int flo_unet_forward(flo_unet_t* h, const float* x, const float* time, const int64_t* class_ids, float* v,
+                     int B, void* stream);
+
+/* Whole trajectory on the device, no host synchronisation (replaces the loop of
+ * generate_latents_rk4, sampling.py:116-117, with v_func_cfg, sampling.py:51-76, inside).
+ * y: [B,C,H,W] fp32, in = start point, out = final latents.
+ * ts: HOST array of n_ts fp32 times (see flo_method).  dt: step for FLO_EULER_LEGACY, else ignored.
+ * class_ids: [B] int64 device or NULL.  cfg_strength: classifier-free guidance; if class_ids
+ *   != NULL and cfg_strength != 0 every evaluation is v_nc + cfg*(v_c - v_nc) (sampling.py:69-74).
+ * v_trace: optional [n_eval,B,C,H,W] fp32 device buffer receiving every stage velocity, or NULL. */
+int flo_integrate(flo_unet_t* h, float* y, const float* ts, int n_ts, int method, float dt, float t_scale,
+                  const int64_t* class_ids, float cfg_strength, float* v_trace, int B, void* stream);
+
+/* Same with HOST buffers: copies x0 (host, ideally pinned) to the device, integrates, copies the
+ * final latents back into x1 (host) and waits for completion.  class_ids is a HOST array here. */
+int flo_integrate_host(flo_unet_t* h, const float* x0, float* x1, const float* ts, int n_ts, int method,
+                       float dt, float t_scale, const int64_t* class_ids, float cfg_strength, int B,
+                       void* stream);
+
+/* Number of function evaluations flo_integrate performs for (method, n_ts) -- the honest count,
+ * not the reference's n_steps*4 over-count (sampling.py:121). */
+int flo_integrate_nfe(int method, int n_ts);
+
+/* ---- introspection (tests, bench) ---- */
+int flo_unet_num_ops(flo_unet_t* h);
+int flo_unet_op_name(flo_unet_t* h, int index, char* name, int name_cap);
+/* Kernel launches issued per forward pass (graph nodes) and total since creation. */
+int flo_unet_launches_per_forward(flo_unet_t* h, int B);
+int64_t flo_unet_launch_count(flo_unet_t* h);
+/* Copy a named intermediate of the LAST forward at batch B to a HOST fp32 NCHW buffer (needs
+ * FLO_FLAG_NO_BUFFER_REUSE).  shape receives [B,C,H,W]. */
+int flo_unet_read_activation(flo_unet_t* h, const char* name, int B, float* out, int64_t cap,
+                             int64_t shape[4], void* stream);
+
+/* ---- self tests of the sm_100a building blocks (GPU required) ---- */
+/* Runs tcgen05/TMEM/TMA micro-GEMMs with the exact descriptor forms the conv kernel uses and
+ * compares with a CPU result.  Returns the number of failing cases (0 = all good, <0 = error);
+ * a human-readable report is written to `report` (may be NULL). */
+int flo_selftest_umma(char* report, int report_cap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOCODER_B200_H */
