@@ -34,11 +34,6 @@ class _Holder(nn.Module):
     (including numeric ones such as ``"1"``), so state_dict keys match the reference's
     ``nn.Sequential`` / wrapper nesting without reproducing those classes."""
 
-    def __init__(self, **children):
-        super().__init__()
-        for k, v in children.items():
-            self.add_module(k.lstrip("_"), v)
-
     def put(self, name: str, module: nn.Module) -> nn.Module:
         self.add_module(str(name), module)
         return module
@@ -118,7 +113,10 @@ class Unet(nn.Module):
             self.class_cond_mlp.put("1", nn.Linear(time_dim, time_dim))
             self.class_cond_mlp.put("3", nn.Linear(time_dim, time_dim))
 
+        # registration order (downs, ups, mid, final) fixes the state_dict order; construction
+        # order (downs, mid, ups, final) fixes the RNG stream -- both as in unet.py:238-286
         self.downs = nn.ModuleList()
+        self.ups = nn.ModuleList()
         n_res = len(in_out)
         for i, (d_in, d_out) in enumerate(in_out):
             last = i >= n_res - 1
@@ -140,7 +138,6 @@ class Unet(nn.Module):
         self.mid_attn = _attn_holder(mid, linear=False)
         self.mid_block2 = _resnet_holder(mid, mid, time_dim, g)
 
-        self.ups = nn.ModuleList()
         for i, (d_in, d_out) in enumerate(reversed(in_out)):
             last = i == n_res - 1
             stage = nn.ModuleList([

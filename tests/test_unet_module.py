@@ -1,0 +1,64 @@
+"""Host-side checks of the drop-in ``Unet`` module (no GPU): parameter manifest, seeded-init
+parity with the reference (via frozen fingerprints), argument validation."""
+import hashlib
+
+import pytest
+import torch
+
+from conftest import CONFIGS, seeded_state_dict
+from flocoder_b200.unet import Unet
+
+
+def fingerprint(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().contiguous().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_seeded_init_matches_reference_fingerprint(goldens, name):
+    g = goldens[name]
+    model, sd = seeded_state_dict(g["n_classes"], g["model_seed"])
+    assert list(sd.keys()) == g["sd_names"]
+    assert sum(p.numel() for p in model.parameters()) == g["n_params"]
+    if torch.__version__ != g["torch_version"]:
+        pytest.skip("torch version differs from the one the goldens were frozen with")
+    assert fingerprint(sd) == g["sd_sha256"]
+
+
+def test_param_counts_match_survey():
+    # 2,619,172 / 2,573,092 / 2,607,396 parameters, 298 / 293 / 298 tensors
+    expect = {102: (2619172, 298), 0: (2573092, 293), 10: (2607396, 298)}
+    for n_cls, (n_par, n_tensors) in expect.items():
+        m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=n_cls)
+        assert sum(p.numel() for p in m.parameters()) == n_par
+        assert len(m.state_dict()) == n_tensors
+
+
+def test_mask_cond_is_an_explicit_error():
+    with pytest.raises(NotImplementedError):
+        Unet(dim=8, channels=4, mask_cond=True)
+    m = Unet(dim=16, channels=4, n_classes=0)
+    with pytest.raises(NotImplementedError):
+        Unet.split_cond({"mask_cond": torch.ones(1, 4, 16, 16)})
+    with pytest.raises(TypeError):
+        Unet.split_cond(torch.arange(4))
+    assert Unet.split_cond(None) is None
+    assert Unet.split_cond({"class_cond": None}) is None
+
+
+def test_no_cpu_fallback():
+    m = Unet(dim=16, channels=4, n_classes=0)
+    with pytest.raises((RuntimeError, ImportError)):
+        m(torch.zeros(1, 4, 16, 16), torch.zeros(1))
+
+
+def test_load_reference_state_dict_roundtrip():
+    a = Unet(dim=16, channels=4, n_classes=10)
+    b = Unet(dim=16, channels=4, n_classes=10)
+    missing = b.load_state_dict(a.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
