@@ -7,6 +7,7 @@ path never falls back to PyTorch or to the CPU oracle.
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_void_p, create_string_buffer)
@@ -24,7 +25,7 @@ FLO_FLAG_NO_BUFFER_REUSE, FLO_FLAG_NO_GRAPH = 1, 2
 # every symbol include/flocoder_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them)
 EXPORTS = (
     "flo_version", "flo_last_error", "flo_param_count", "flo_param_info", "flo_unet_create",
-    "flo_unet_destroy", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
+    "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
     "flo_integrate_nfe", "flo_unet_num_ops", "flo_unet_op_name", "flo_unet_launches_per_forward",
     "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma",
 )
@@ -58,6 +59,7 @@ def lib() -> ctypes.CDLL:
     L.flo_param_info.argtypes = [POINTER(FloUnetCfg), c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]
     L.flo_unet_create.argtypes = [POINTER(c_void_p), POINTER(FloUnetCfg), POINTER(c_void_p), c_int, c_void_p]
     L.flo_unet_destroy.argtypes = [c_void_p]
+    L.flo_unet_set_time_freqs.argtypes = [c_void_p, POINTER(c_float), c_int]
     L.flo_workspace_bytes.argtypes = [c_void_p, c_int]
     L.flo_workspace_bytes.restype = c_size_t
     L.flo_unet_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
@@ -157,6 +159,11 @@ class Engine:
             check(self.L.flo_unet_create(byref(self.handle), byref(self.cfg), ptrs, len(tensors),
                                          _stream_ptr(self.device)), "flo_unet_create")
             torch.cuda.current_stream(self.device).synchronize()   # packing reads `tensors`
+            # sinusoidal frequencies exactly as the reference forms them (unet.py:26-27): torch.exp in fp32
+            half = dim // 2
+            freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+            check(self.L.flo_unet_set_time_freqs(self.handle, (c_float * half)(*freqs.tolist()), half),
+                  "flo_unet_set_time_freqs")
         del tensors
 
     def close(self):

@@ -1,0 +1,410 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a.
+//
+// GEMM view of a 1x1 / 3x3 (pad 1) convolution over blocked bf16 activations:
+//     D[pixel, cout] = sum_{tap, cin} A_tap[pixel, cin] * W[tap, cin, cout]
+// * A operand: ONE TMA tensor-tile load per source brings the zero-padded image tile of `nb`
+//   samples -- box {8ch, W+2, H+2, nb, C/8} at coordinates (0,-1,-1,b0,0), out-of-bounds = 0 --
+//   into shared memory as [C/8][nb][H+2][W+2][8ch].  That is exactly the tcgen05 no-swizzle
+//   K-major operand layout (16-byte rows, 8-row core matrices): the A tile of a 3x3 tap is the
+//   SAME bytes at a start address shifted by (dh*(W+2)+dw)*16 B, so im2col costs no data
+//   movement at all -- nine descriptors instead of nine copies.  torch.cat of two sources is two
+//   TMA loads into consecutive planes (two K segments).
+// * M tile = 128 output pixels = 16 groups of 8 consecutive padded pixels.  At 16x16 a tile is a
+//   16-row x 8-column strip (group stride = padded row pitch, every row useful); at lower
+//   resolutions a tile is 128 consecutive padded pixels of `nb` stacked samples (halo rows compute
+//   junk that the epilogue discards).
+// * B operand: weights pre-packed on the host into the canonical K-major core-matrix layout, streamed
+//   through a ring of shared-memory stages by 1-D bulk TMA copies (cp.async.bulk, mbarrier tx).
+// * D: fp32 accumulators in TMEM (one 128 x n_tile block per M tile); tcgen05.mma issued by one thread;
+//   tcgen05.commit -> mbarrier hands stages back to the producer and the result to the epilogue.
+// * Epilogue: 4 warps tcgen05.ld their 32 TMEM lanes, add bias (+ fp32 residual), and write fp32
+//   and/or bf16 blocked outputs with 32-/16-byte vector stores.
+//
+// Warp roles (192 threads): warps 0-3 epilogue, warp 4 TMA producer, warp 5 TMEM owner + MMA issuer.
+#include "flo_internal.h"
+
+namespace flo {
+
+constexpr int UMMA_THREADS = 192;
+constexpr int MAX_WSTAGES = 4;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap (an error the host sees), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor, version 1):
+//   [0,14) start>>4 | [16,30) leading-dim byte offset>>4 (K direction: between the two 8-element
+//   K chunks) | [32,46) stride-dim byte offset>>4 (M/N direction: between 8-row groups) | [46,48) = 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry shared by the MMA issuer and the epilogue
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+    int Wp, PP;        // padded row pitch and padded pixels per sample (H*W for 1x1)
+};
+__device__ __forceinline__ int tile_row0(const ConvUmmaParams& p, int t) {
+    if (p.sbo_px != 8) {            // strip mode: tile = 16 image rows x 8 columns
+        const int tx_n = p.W >> 3;
+        const int ty = t / tx_n, tx = t % tx_n;
+        return (ty * 16 + 1) * (p.W + 2) + 1 + 8 * tx;
+    }
+    return p.row0 + t * p.tile_stride;
+}
+
+__global__ void __launch_bounds__(UMMA_THREADS) k_conv_umma(const __grid_constant__ CUtensorMap tmA0,
+                                                            const __grid_constant__ CUtensorMap tmA1,
+                                                            const ConvUmmaParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncbT = p.ncb0 + p.ncb1;
+    const int pad = p.ksize >> 1;
+    const int Wp = p.W + 2 * pad, Hp = p.H + 2 * pad, PP = Wp * Hp;
+    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
+    const uint32_t a_bytes = (uint32_t)ncbT * plane_bytes;
+    const uint32_t a_region = (a_bytes + (uint32_t)(128 + Wp + 2) * 16u + 127u) & ~127u;
+    const uint32_t stage_bytes = (uint32_t)p.slices_per_stage * (uint32_t)p.n_tile * 32u;
+    const uint32_t ring_off = a_region;
+    const uint32_t bar_off = ring_off + (uint32_t)p.n_wstages * stage_bytes;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_base + bar_off;                 // [MAX_WSTAGES]
+    const uint32_t bar_empty = bar_full + 8 * MAX_WSTAGES;         // [MAX_WSTAGES]
+    const uint32_t bar_a = bar_empty + 8 * MAX_WSTAGES;
+    const uint32_t bar_done = bar_a + 8;
+    const uint32_t tmem_slot = bar_done + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 16);
+
+    const int b0 = blockIdx.x * p.nb;
+    const int nt = blockIdx.y;
+    const int taps = p.ksize * p.ksize;
+    const int cpT = ncbT >> 1;                       // K16 slices per tap
+    const int total_slices = taps * cpT;
+    const int n_loads = total_slices / p.slices_per_stage;
+
+    if (warp == 4 && lane == 0) {
+        for (int i = 0; i < p.n_wstages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_a, 1);
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+        if (p.ncb1) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, a_bytes);
+            tma_load_5d(smem_base, &tmA0, bar_a, 0, -pad, -pad, b0, 0);
+            if (p.ncb1) tma_load_5d(smem_base + (uint32_t)p.ncb0 * plane_bytes, &tmA1, bar_a, 0, -pad, -pad, b0, 0);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)nt * total_slices * p.n_tile * 32;
+            for (int i = 0; i < n_loads; ++i) {
+                const int slot = i % p.n_wstages;
+                if (i >= p.n_wstages) mbar_wait(bar_empty + 8 * slot, ((i / p.n_wstages) - 1) & 1);
+                mbar_expect_tx(bar_full + 8 * slot, stage_bytes);
+                bulk_load_1d(smem_base + ring_off + slot * stage_bytes, wsrc + (size_t)i * stage_bytes, stage_bytes,
+                             bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.n_tile);
+            const uint32_t a_sbo = (uint32_t)p.sbo_px * 16u;
+            const uint32_t b_lbo = (uint32_t)p.n_tile * 16u;
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < n_loads; ++i) {
+                const int slot = i % p.n_wstages;
+                mbar_wait(bar_full + 8 * slot, (i / p.n_wstages) & 1);
+                tc_fence_after();
+                const uint32_t bstage = smem_base + ring_off + slot * stage_bytes;
+                for (int s = 0; s < p.slices_per_stage; ++s) {
+                    const int ks = i * p.slices_per_stage + s;
+                    const int tap = ks / cpT, cp = ks - tap * cpT;
+                    const int shift = pad ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
+                    const uint64_t bdesc = make_smem_desc(bstage + (uint32_t)s * (uint32_t)p.n_tile * 32u, b_lbo, 128u);
+                    for (int t = 0; t < p.n_mtiles; ++t) {
+                        const uint32_t a_addr =
+                            smem_base + (uint32_t)(2 * cp) * plane_bytes + (uint32_t)(tile_row0(p, t) + shift) * 16u;
+                        const uint64_t adesc = make_smem_desc(a_addr, plane_bytes, a_sbo);
+                        umma_bf16(tmem_base + (uint32_t)(t * p.n_tile), adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(bar_empty + 8 * slot);      // frees the weight stage when these MMAs retire
+            }
+            umma_commit(bar_done);                      // accumulators complete
+        }
+    } else {
+        // ===================== epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31) =====================
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const int HW = p.H * p.W;
+        const int r = warp * 32 + lane;
+        const int g = r >> 3, i8 = r & 7;
+        for (int t = 0; t < p.n_mtiles; ++t) {
+            const int pp = tile_row0(p, t) + g * p.sbo_px + i8;
+            const int s = pp / PP, rem = pp - s * PP;
+            bool valid;
+            int px;
+            if (pad) {
+                const int hh = rem / Wp, ww = rem - hh * Wp;
+                valid = (s < p.nb) && (hh >= 1) && (hh <= p.H) && (ww >= 1) && (ww <= p.W);
+                px = (hh - 1) * p.W + (ww - 1);
+            } else {
+                valid = (s < p.nb);
+                px = rem;
+            }
+            const int b = b0 + s;
+            valid = valid && (b < p.B);
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * p.n_tile);
+            for (int c16 = 0; c16 < p.n_tile; c16 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c16, v);
+                if (!valid) continue;
+                const int c = nt * p.n_tile + c16;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float* o = v + hb * 8;
+                    const int cc = c + hb * 8;
+                    if (p.bias) {
+                        const float4 b0v = *reinterpret_cast<const float4*>(p.bias + cc);
+                        const float4 b1v = *reinterpret_cast<const float4*>(p.bias + cc + 4);
+                        o[0] += b0v.x; o[1] += b0v.y; o[2] += b0v.z; o[3] += b0v.w;
+                        o[4] += b1v.x; o[5] += b1v.y; o[6] += b1v.z; o[7] += b1v.w;
+                    }
+                    const size_t off = ((size_t)((cc >> 3) * p.B + b) * HW + px) * 8;
+                    if (p.res) {
+                        const float4 r0 = *reinterpret_cast<const float4*>(p.res + off);
+                        const float4 r1 = *reinterpret_cast<const float4*>(p.res + off + 4);
+                        o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
+                        o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+                    }
+                    if (p.out_m) {
+                        *reinterpret_cast<float4*>(p.out_m + off) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(p.out_m + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                    if (p.out_o) {
+                        uint4 u;
+                        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) h2[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+                        *reinterpret_cast<uint4*>(p.out_o + off) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+cudaError_t conv_umma_configure() {
+    return cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_conv_umma(const ConvUmmaParams& p, const CUtensorMap& a0, const CUtensorMap& a1, cudaStream_t s) {
+    dim3 grid((p.B + p.nb - 1) / p.nb, p.cout / p.n_tile);
+    k_conv_umma<<<grid, UMMA_THREADS, p.smem_bytes, s>>>(a0, a1, p);
+    return cudaGetLastError();
+}
+
+// shared-memory bytes the kernel carves for a configuration (must mirror the kernel's arithmetic)
+int conv_umma_smem_bytes(const ConvUmmaParams& p) {
+    const int pad = p.ksize >> 1, Wp = p.W + 2 * pad;
+    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
+    const uint32_t a_bytes = (uint32_t)(p.ncb0 + p.ncb1) * plane_bytes;
+    const uint32_t a_region = (a_bytes + (uint32_t)(128 + Wp + 2) * 16u + 127u) & ~127u;
+    const uint32_t stage_bytes = (uint32_t)p.slices_per_stage * (uint32_t)p.n_tile * 32u;
+    return (int)(a_region + p.n_wstages * stage_bytes + 16 * MAX_WSTAGES + 16 + 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side weight packing: OIHW fp32 -> per n-tile stream of K16 slices in core-matrix order
+//   [n_tile index][slice = tap*(cin/16)+cp][k half][n/8][n%8][k%8]   (bf16)
+// ------------------------------------------------------------------------------------------------
+size_t pack_umma_weights(const float* w, int cout, int cin, int ksize, const int* perm, int n_tile,
+                         std::vector<__nv_bfloat16>& out) {
+    const int taps = ksize * ksize, cpT = cin / 16;
+    const size_t start = out.size();
+    out.resize(start + (size_t)cout * cin * taps);
+    __nv_bfloat16* dst = out.data() + start;
+    size_t idx = 0;
+    for (int nt = 0; nt < cout / n_tile; ++nt)
+        for (int tap = 0; tap < taps; ++tap)
+            for (int cp = 0; cp < cpT; ++cp)
+                for (int h = 0; h < 2; ++h)
+                    for (int n = 0; n < n_tile; ++n)
+                        for (int j = 0; j < 8; ++j) {
+                            const int ci_ours = (2 * cp + h) * 8 + j;
+                            const int ci = perm ? perm[ci_ours] : ci_ours;
+                            const int co = nt * n_tile + n;
+                            dst[idx++] = __float2bfloat16(w[((size_t)co * cin + ci) * taps + tap]);
+                        }
+    return idx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// descriptor micro-test: D[128 x N] = A[128 x K] * B[N x K]^T with A placed at arbitrary
+// (start shift, LBO, SBO) -- the exact descriptor forms the convolution relies on.
+// ------------------------------------------------------------------------------------------------
+struct MicroParams {
+    const __nv_bfloat16* a;   // [128][K] row-major
+    const __nv_bfloat16* b;   // [N][K] row-major
+    float* d;                 // [128][N]
+    int N, K;
+    int a_lbo, a_sbo, a_shift;   // bytes
+    int b_lbo, b_sbo;            // bytes
+};
+__global__ void __launch_bounds__(128) k_umma_micro(MicroParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t a_off = 0, b_off = 96 * 1024;
+    // place A: element (m, k) at a_shift + (k/8)%2... general: k16 slice s, half h, row m
+    for (int idx = tid; idx < 128 * p.K; idx += 128) {
+        const int m = idx / p.K, k = idx % p.K;
+        const int s = k / 16, h = (k / 8) & 1, j = k & 7;
+        const uint32_t o = a_off + (uint32_t)p.a_shift + (uint32_t)s * 2u * (uint32_t)p.a_lbo + (uint32_t)h * p.a_lbo +
+                           (uint32_t)(m / 8) * p.a_sbo + (uint32_t)(m % 8) * 16u + (uint32_t)j * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(smem + o) = p.a[idx];
+    }
+    for (int idx = tid; idx < p.N * p.K; idx += 128) {
+        const int n = idx / p.K, k = idx % p.K;
+        const int s = k / 16, h = (k / 8) & 1, j = k & 7;
+        const uint32_t o = b_off + (uint32_t)s * 2u * (uint32_t)p.b_lbo + (uint32_t)h * p.b_lbo +
+                           (uint32_t)(n / 8) * p.b_sbo + (uint32_t)(n % 8) * 16u + (uint32_t)j * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(smem + o) = p.b[idx];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int cols = 32;
+    while (cols < p.N) cols <<= 1;
+    if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(&tslot);
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, p.N);
+        const uint32_t base = smem_u32(smem);
+        for (int s = 0; s < p.K / 16; ++s) {
+            const uint64_t ad = make_smem_desc(base + a_off + p.a_shift + s * 2 * p.a_lbo, p.a_lbo, p.a_sbo);
+            const uint64_t bd = make_smem_desc(base + b_off + s * 2 * p.b_lbo, p.b_lbo, p.b_sbo);
+            umma_bf16(tbase, ad, bd, idesc, s > 0);
+        }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c = 0; c < p.N; c += 16) {
+        float v[16];
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+        for (int i = 0; i < 16; ++i) p.d[(size_t)(warp * 32 + lane) * p.N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, cols);
+}
+
+cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int N, int K, int a_lbo,
+                              int a_sbo, int a_shift, int b_lbo, int b_sbo, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_umma_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    MicroParams p{a, b, d, N, K, a_lbo, a_sbo, a_shift, b_lbo, b_sbo};
+    k_umma_micro<<<1, 128, 200 * 1024, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace flo

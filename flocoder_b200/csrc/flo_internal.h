@@ -1,0 +1,195 @@
+// Internal declarations shared by the flocoder_b200 translation units (not part of the C ABI).
+//
+// Activation layout ("blocked"): a tensor with C channels (C % 8 == 0) at H x W for B samples is
+// stored as [C/8][B][H][W][8] -- channel-blocks outermost, 8 channels innermost.  One 8-channel
+// pixel is 16 B in bf16 / 32 B in fp32, which is (a) the 16-byte row of a tcgen05 no-swizzle
+// K-major core matrix, so a TMA box of the padded image is directly a UMMA A operand whose 3x3
+// taps are shifted start addresses, and (b) a full vector load for the elementwise kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/flocoder_b200.h"
+
+namespace flo {
+
+// ---------------------------------------------------------------------------------------------
+// device-resident control block: everything that changes between replays of the forward graph
+// ---------------------------------------------------------------------------------------------
+enum StageKind : int {
+    ST_PLAIN = 0,     // write v to ctrl.vout                              (Unet.forward)
+    ST_RK1 = 1,       // acc = k;        xs = y + (dt*k)/2                 (sampling.py:43,45)
+    ST_RK2 = 2,       // acc += 2k;      xs = y + (dt*k)/2                 (sampling.py:45,46)
+    ST_RK3 = 3,       // acc += 2k;      xs = y + dt*k                     (sampling.py:46,47)
+    ST_RK4 = 4,       // acc += k;       y += (dt/6)*acc; xs = y           (sampling.py:48)
+    ST_EULER = 5,     // y = y + k*dt;   xs = y                            (legacy/train_sd_flowers.py:64)
+    ST_CFG_COND = 6   // vcond = k (conditional pass of classifier-free guidance, sampling.py:63)
+};
+enum StageFlags : int {
+    SF_CFG_COMBINE = 1   // this pass is the unconditional one: k = k + cfg*(vcond - k)  (sampling.py:74)
+};
+
+struct Stage {
+    float t_scaled;   // fl32(t) * t_scale, the value fed to the U-Net (sampling.py:63)
+    float dt;
+    float dt6;        // dt / 6 in fp32 (sampling.py:48)
+    int kind;
+    int film_row;     // row of the FiLM table for a batch-uniform time
+    int flags;
+    int eval_idx;     // index of this velocity evaluation in ctrl.vtrace, or -1
+    int pad;
+};
+
+struct Ctrl {
+    int step;             // index of the current stage; advanced by the last CTA of the final kernel
+    int done_ctr;
+    int film_per_sample;  // 1: FiLM row = sample index (per-sample time / class conditioning)
+    int n_stages;
+    float cfg;
+    int pad0;
+    float* y;             // [B,C,H,W] integrator state
+    float* acc;           // [B,C,H,W] running k1+2k2+2k3+k4
+    float* xs;            // [B,C,H,W] input of the current U-Net evaluation
+    float* vcond;         // [B,C,H,W] conditional velocity (CFG)
+    float* vout;          // ST_PLAIN destination
+    float* vtrace;        // optional [n_eval,B,C,H,W]
+    const float* film;    // FiLM table [rows][film_dim]
+    const Stage* stages;
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameter blocks
+// ---------------------------------------------------------------------------------------------
+struct InitConvParams {
+    const Ctrl* ctrl;
+    const float* w;       // [dim][cin]
+    const float* bias;    // [dim]
+    float* out_m;         // fp32 blocked or null
+    void* out_o;          // operand blocked (bf16 or fp32) or null
+    int B, HW, cin, dim, o_is_bf16;
+};
+
+struct ConvSimtParams {
+    const void* in0; const void* in1;   // blocked sources (operand dtype), in1 may be null
+    int ncb0, ncb1;                     // channel blocks per source
+    int in_is_bf16;
+    const float* w;                     // [taps][cin][cout]
+    const float* bias;                  // [cout] or null
+    const float* res;                   // fp32 blocked residual or null
+    float* out_m; void* out_o;          // fp32 blocked / operand blocked (either may be null)
+    int o_is_bf16;
+    int B, H, W, cout, ksize;
+};
+
+struct GnParams {
+    const Ctrl* ctrl;
+    const float* in;      // fp32 blocked [C/8][B][HW][8]
+    const float* res;     // fp32 blocked residual or null
+    const float* gamma; const float* beta;
+    float* out_m;         // fp32 blocked or null
+    void* out_o;          // operand blocked or null
+    void* out_unshuf;     // operand [4*C/8][B][H/2][W/2][8] or null  (pixel-unshuffle, unet.py:52)
+    void* out_up;         // operand [C/8][B][2H][2W][8] or null      (nearest x2, unet.py:44)
+    int o_is_bf16;
+    int B, C, H, W, groups;
+    int film_off;         // offset of this block's (scale|shift) in a FiLM row, or -1
+    int film_dim;
+    int silu;
+};
+
+struct AttnParams {
+    const void* qkv;      // operand blocked [48][B][n][8]   (q | k | v, 4 heads x 32)
+    void* out;            // operand blocked [16][B][n][8]
+    int is_bf16;
+    int B, n;
+};
+
+struct TembParams {
+    const float* t; int t_stride;        // time per row (already scaled); stride 0 = same for all rows
+    const int64_t* cls;                  // class id per row or null
+    int n_rows;
+    float* film;                         // [n_rows][film_dim]
+    int dim, time_dim, film_dim, n_classes;
+    const float* freqs;                  // [dim/2]
+    const float* w1t; const float* b1;   // [dim][time_dim]
+    const float* w2t; const float* b2;   // [time_dim][time_dim]
+    const float* emb;                    // [n_classes][time_dim]
+    const float* wc1t; const float* bc1;
+    const float* wc3t; const float* bc3;
+    const float* wft; const float* bf;   // [time_dim][film_dim]
+};
+
+struct FinalParams {
+    Ctrl* ctrl;
+    const float* in;      // fp32 blocked [dim/8][B][HW][8]
+    const float* w;       // [channels][dim]
+    const float* bias;
+    int B, HW, dim, channels;
+};
+
+// tcgen05 convolution (conv_umma.cu)
+struct ConvUmmaParams {
+    const __nv_bfloat16* w;      // packed weight stream for this layer (see pack_umma_weights)
+    const float* bias;           // [cout] or null
+    const float* res;            // fp32 blocked residual or null
+    float* out_m;                // fp32 blocked or null
+    __nv_bfloat16* out_o;        // bf16 blocked or null
+    int B, H, W;
+    int ncb0, ncb1;              // channel blocks of the two (concatenated) sources
+    int cout;                    // total output channels
+    int n_tile;                  // output channels per CTA (multiple of 16, <= 256)
+    int ksize;                   // 1 or 3
+    int nb;                      // samples per CTA
+    int n_mtiles;                // 128-row M tiles per CTA
+    int row0;                    // flattened (padded) pixel index of row 0 of M tile 0
+    int tile_stride;             // pixel distance between consecutive M tiles
+    int sbo_px;                  // pixel distance between consecutive 8-row groups (8 = flattened)
+    int plane_px;                // pixels per channel-block plane in shared memory (nb * Hp * Wp)
+    int slices_per_stage;        // K16 slices per weight pipeline stage
+    int n_wstages;               // ring depth
+    int smem_bytes;
+    int tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------------------
+// launchers (each returns cudaGetLastError())
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_setup_ctrl(Ctrl* ctrl_dev, const Ctrl& value, Stage* stage0_dev, const Stage* stage0_value,
+                              cudaStream_t s);
+cudaError_t launch_init_conv(const InitConvParams& p, cudaStream_t s);
+cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t s);
+cudaError_t launch_gn(const GnParams& p, cudaStream_t s);
+cudaError_t launch_linattn(const AttnParams& p, cudaStream_t s);
+cudaError_t launch_midattn(const AttnParams& p, cudaStream_t s);
+cudaError_t launch_temb(const TembParams& p, cudaStream_t s);
+cudaError_t launch_final(const FinalParams& p, cudaStream_t s);
+cudaError_t launch_conv_umma(const ConvUmmaParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
+                             cudaStream_t s);
+cudaError_t conv_umma_configure();   // one-time cudaFuncSetAttribute calls
+cudaError_t simt_configure();
+cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int N, int K, int a_lbo,
+                              int a_sbo, int a_shift, int b_lbo, int b_sbo, cudaStream_t s);
+
+// tiling of one convolution for the tcgen05 kernel, and the TMA map of a blocked bf16 tensor
+struct ConvShape { const char* name; int H, W, ksize, ncb0, ncb1, cout, n_tile; };
+int plan_umma(const ConvShape& shape, int B, ConvUmmaParams& p);
+int make_tmap(CUtensorMap* tm, void* base, int ncb, int B, int H, int W, int pad, int nb);
+
+// host-side packing of OIHW fp32 weights (with input-channel permutation `perm`, or null) into the
+// bf16 stream the tcgen05 kernel consumes; returns elements written.
+size_t pack_umma_weights(const float* w_oihw, int cout, int cin, int ksize, const int* perm, int n_tile,
+                         std::vector<__nv_bfloat16>& out);
+
+// TMA tensor-map encoder obtained through the runtime (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+void set_error(const char* fmt, ...);
+
+}  // namespace flo

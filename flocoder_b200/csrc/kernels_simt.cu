@@ -1,0 +1,618 @@
+// CUDA-core kernels of the flocoder_b200 sampling path (sm_100a).
+//
+//   k_init_conv   init_conv 1x1 (unet.py:295) reading the NCHW fp32 integrator state
+//   k_conv_simt   fp32 direct convolution on blocked tensors (the FLO_F32 path, <=1e-5 parity)
+//   k_gn          GroupNorm + timestep-FiLM + SiLU + residual in ONE pass (unet.py:64-73,96,133,157):
+//                 each value is read once into registers, reduced with warp shuffles, written once
+//   k_linattn     LinearAttention core (unet.py:142-149), one CTA per (sample, head)
+//   k_midattn     mid-block Attention core (unet.py:114-121), one CTA per (sample, head)
+//   k_temb        sinusoidal embedding + time/class MLPs + all ResnetBlock FiLM projections
+//                 (unet.py:23-30,199-212,79-82,90-92) -> one FiLM row per distinct time / sample
+//   k_final       final_conv 1x1 (unet.py:372) with the RK4 / Euler / CFG stage update fused as its
+//                 epilogue (sampling.py:43-48,69-74)
+//
+// All tensors other than the NCHW latents use the blocked layout of flo_internal.h.
+#include "flo_internal.h"
+
+namespace flo {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float* src, float v[8]) {
+    float4 a = *reinterpret_cast<const float4*>(src);
+    float4 b = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* src, float v[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(src);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8(float* dst, const float v[8]) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* dst, const float v[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void store4(float* dst, float4 v) { *reinterpret_cast<float4*>(dst) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, float4 v) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(v.x, v.y);
+    h[1] = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; every thread gets the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (nw == 1) return v;
+    __syncthreads();                 // protect `red` from the previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    return warp_sum(t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// control block setup (by-value launch arguments -> device memory; fully stream-ordered)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_setup_ctrl(Ctrl* dst, Ctrl value, Stage* stage0_dst, Stage stage0, int write_stage) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *dst = value;
+        if (write_stage) *stage0_dst = stage0;
+    }
+}
+cudaError_t launch_setup_ctrl(Ctrl* ctrl_dev, const Ctrl& value, Stage* stage0_dev, const Stage* stage0_value,
+                              cudaStream_t s) {
+    Stage st = {};
+    if (stage0_value) st = *stage0_value;
+    k_setup_ctrl<<<1, 32, 0, s>>>(ctrl_dev, value, stage0_dev, st, stage0_value != nullptr);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// init_conv: NCHW fp32 latents -> blocked activations (fp32 master and/or operand copy)
+// ------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(128) k_init_conv(InitConvParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.B * p.HW) return;
+    const int b = idx / p.HW, px = idx % p.HW;
+    const float* x = p.ctrl->xs;
+    float xin[16];
+#pragma unroll 4
+    for (int ci = 0; ci < p.cin; ++ci) xin[ci] = x[((size_t)b * p.cin + ci) * p.HW + px];
+    const int ncb = p.dim >> 3;
+    for (int cb = 0; cb < ncb; ++cb) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = cb * 8 + j;
+            float a = 0.f;
+            for (int ci = 0; ci < p.cin; ++ci) a = fmaf(xin[ci], p.w[co * p.cin + ci], a);
+            o[j] = a + p.bias[co];
+        }
+        const size_t off = ((size_t)(cb * p.B + b) * p.HW + px) * 8;
+        if (p.out_m) store8(p.out_m + off, o);
+        if (p.out_o) store8(reinterpret_cast<TO*>(p.out_o) + off, o);
+    }
+}
+cudaError_t launch_init_conv(const InitConvParams& p, cudaStream_t s) {
+    const int n = p.B * p.HW;
+    if (p.o_is_bf16) k_init_conv<__nv_bfloat16><<<(n + 127) / 128, 128, 0, s>>>(p);
+    else k_init_conv<float><<<(n + 127) / 128, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 direct convolution (1x1 or 3x3 pad 1, stride 1) over up to two concatenated sources
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) k_conv_simt(ConvSimtParams p) {
+    const int HW = p.H * p.W;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.B * HW) return;
+    const int b = idx / HW, px = idx % HW, h = px / p.W, w = px % p.W;
+    const int co0 = blockIdx.y * 8;
+    const int cin = (p.ncb0 + p.ncb1) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int taps = p.ksize * p.ksize, r = p.ksize >> 1;
+    for (int t = 0; t < taps; ++t) {
+        const int hh = h + t / p.ksize - r, ww = w + t % p.ksize - r;
+        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+        const int q = hh * p.W + ww;
+        const float* wt = p.w + (size_t)t * cin * p.cout + co0;
+        for (int src = 0; src < 2; ++src) {
+            const TI* in = reinterpret_cast<const TI*>(src ? p.in1 : p.in0);
+            const int ncb = src ? p.ncb1 : p.ncb0;
+            const int cbase = src ? p.ncb0 * 8 : 0;
+            for (int cb = 0; cb < ncb; ++cb) {
+                float xv[8];
+                load8(in + ((size_t)(cb * p.B + b) * HW + q) * 8, xv);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float wv[8];
+                    load8(wt + (size_t)(cbase + cb * 8 + c8) * p.cout, wv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[c8], wv[j], acc[j]);
+                }
+            }
+        }
+    }
+    const size_t off = ((size_t)(blockIdx.y * p.B + b) * HW + px) * 8;
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += p.bias[co0 + j];
+    }
+    if (p.res) {
+        float rv[8];
+        load8(p.res + off, rv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+    }
+    if (p.out_m) store8(p.out_m + off, acc);
+    if (p.out_o) store8(reinterpret_cast<TO*>(p.out_o) + off, acc);
+}
+cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t s) {
+    dim3 grid((p.B * p.H * p.W + 127) / 128, p.cout / 8);
+    if (p.in_is_bf16) {
+        if (p.o_is_bf16) k_conv_simt<__nv_bfloat16, __nv_bfloat16><<<grid, 128, 0, s>>>(p);
+        else k_conv_simt<__nv_bfloat16, float><<<grid, 128, 0, s>>>(p);
+    } else {
+        if (p.o_is_bf16) k_conv_simt<float, __nv_bfloat16><<<grid, 128, 0, s>>>(p);
+        else k_conv_simt<float, float><<<grid, 128, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm + FiLM + SiLU + residual, one pass.  One CTA per (sample, group).
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_VPT = 8;   // float4 vectors held per thread
+
+template <typename TO>
+__global__ void __launch_bounds__(256) k_gn(GnParams p) {
+    __shared__ float red[32];
+    const int G = p.groups, cpg = p.C / G, HW = p.H * p.W;
+    const int b = blockIdx.x / G, g = blockIdx.x % G;
+    const int nvec = cpg * HW / 4;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int ncb = p.C >> 3;
+
+    float4 v[GN_VPT];
+    size_t offs[GN_VPT];
+    int chan[GN_VPT], pix[GN_VPT];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+        const int i = tid + k * NT;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        offs[k] = 0; chan[k] = 0; pix[k] = 0;
+        if (i < nvec) {
+            int cb, sub, px;
+            if (cpg >= 8) {                 // the group spans whole channel blocks
+                const int per_cb = HW * 2;
+                cb = g * (cpg >> 3) + i / per_cb;
+                const int r = i % per_cb;
+                px = r >> 1; sub = (r & 1) * 4;
+            } else {                        // cpg == 4: half a channel block
+                cb = (g * 4) >> 3; sub = (g & 1) * 4; px = i;
+            }
+            offs[k] = ((size_t)(cb * p.B + b) * HW + px) * 8 + sub;
+            chan[k] = cb * 8 + sub; pix[k] = px;
+            v[k] = *reinterpret_cast<const float4*>(p.in + offs[k]);
+            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+    }
+    const float inv_n = 1.f / (float)(cpg * HW);
+    const float mean = block_sum(sum, red) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+        if (tid + k * NT < nvec) {
+            const float a = v[k].x - mean, b2 = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            sq += (a * a + b2 * b2) + (c * c + d * d);
+        }
+    }
+    const float var = block_sum(sq, red) * inv_n;          // biased variance (nn.GroupNorm)
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+
+    const float* film = nullptr;
+    if (p.film_off >= 0) {
+        const Ctrl* c = p.ctrl;
+        const int row = c->film_per_sample ? b : c->stages[c->step].film_row;
+        film = c->film + (size_t)row * p.film_dim + p.film_off;
+    }
+    TO* out_o = reinterpret_cast<TO*>(p.out_o);
+    TO* out_un = reinterpret_cast<TO*>(p.out_unshuf);
+    TO* out_up = reinterpret_cast<TO*>(p.out_up);
+#pragma unroll
+    for (int k = 0; k < GN_VPT; ++k) {
+        if (tid + k * NT >= nvec) continue;
+        const int c0 = chan[k];
+        float x[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
+        const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
+        const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y = (x[j] - mean) * rstd * gam[j] + bet[j];
+            if (film) y = y * (film[c0 + j] + 1.0f) + film[p.C + c0 + j];     // unet.py:70
+            if (p.silu) y = y / (1.0f + expf(-y));                            // x*sigmoid(x)
+            x[j] = y;
+        }
+        if (p.res) {
+            const float4 r = *reinterpret_cast<const float4*>(p.res + offs[k]);
+            x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+        }
+        const float4 o = make_float4(x[0], x[1], x[2], x[3]);
+        if (p.out_m) store4(p.out_m + offs[k], o);
+        if (out_o) store4(out_o + offs[k], o);
+        if (out_un || out_up) {
+            const int h = pix[k] / p.W, w = pix[k] % p.W, cb = c0 >> 3, sub = c0 & 7;
+            if (out_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)
+                const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
+                const int q = (h >> 1) * (p.W >> 1) + (w >> 1);
+                store4(out_un + ((size_t)(plane * p.B + b) * (HW >> 2) + q) * 8 + sub, o);
+            }
+            if (out_up) {   // nearest x2: dst(2h+dy, 2w+dx) = src(h, w)
+                const int W2 = p.W * 2;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int q = (2 * h + (d >> 1)) * W2 + 2 * w + (d & 1);
+                    store4(out_up + ((size_t)(cb * p.B + b) * (HW * 4) + q) * 8 + sub, o);
+                }
+            }
+        }
+    }
+}
+cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
+    const int nvec = (p.C / p.groups) * p.H * p.W / 4;
+    int nt = 32;
+    while (nt < 256 && nt * GN_VPT < nvec) nt <<= 1;
+    // prefer ~4 vectors per thread when the unit is big enough to fill more warps
+    while (nt < 256 && nvec / nt > 4) nt <<= 1;
+    if (nt * GN_VPT < nvec) return cudaErrorInvalidValue;
+    const int grid = p.B * p.groups;
+    if (p.o_is_bf16) k_gn<__nv_bfloat16><<<grid, nt, 0, s>>>(p);
+    else k_gn<float><<<grid, nt, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// LinearAttention core (unet.py:142-149).  One CTA (256 threads) per (sample, head); n <= 256.
+// q: softmax over the 32 head channels per pixel, then * 32^-0.5;  k: softmax over pixels per
+// channel;  ctx[d][e] = sum_n k[d,n] v[e,n];  out[e][n] = sum_d ctx[d][e] q[d,n].
+// ------------------------------------------------------------------------------------------------
+constexpr int LA_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(LA_THREADS) k_linattn(AttnParams p) {
+    extern __shared__ float sm[];
+    const int n = p.n, ld = n + 1;
+    float* sq = sm;                 // [32][ld]
+    float* sk = sq + 32 * ld;       // [32][ld]
+    float* sv = sk + 32 * ld;       // [32][ld]
+    float* ctx = sv + 32 * ld;      // [32][33]
+    const int b = blockIdx.x >> 2, head = blockIdx.x & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T* qkv = reinterpret_cast<const T*>(p.qkv);
+
+    // load q, k, v: 3 tensors x 4 channel blocks x n pixels, 8 channels per item
+    for (int it = tid; it < 12 * n; it += LA_THREADS) {
+        const int which = it / (4 * n), rem = it % (4 * n), cbl = rem / n, px = rem % n;
+        const int plane = which * 16 + head * 4 + cbl;
+        float x[8];
+        load8(qkv + ((size_t)(plane * p.B + b) * n + px) * 8, x);
+        float* dst = (which == 0 ? sq : which == 1 ? sk : sv) + (cbl * 8) * ld + px;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j * ld] = x[j];
+    }
+    __syncthreads();
+    // q: softmax over d for each pixel
+    for (int px = tid; px < n; px += LA_THREADS) {
+        float m = -INFINITY;
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) m = fmaxf(m, sq[d * ld + px]);
+        float s = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) { const float e = expf(sq[d * ld + px] - m); sq[d * ld + px] = e; s += e; }
+        const float scale = 0.17677669529663687f;      // 32^-0.5
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) sq[d * ld + px] = (sq[d * ld + px] / s) * scale;
+    }
+    // k: softmax over pixels for each channel (one warp per channel)
+    for (int d = warp; d < 32; d += LA_THREADS / 32) {
+        float m = -INFINITY;
+        for (int px = lane; px < n; px += 32) m = fmaxf(m, sk[d * ld + px]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int px = lane; px < n; px += 32) { const float e = expf(sk[d * ld + px] - m); sk[d * ld + px] = e; s += e; }
+        s = warp_sum(s);
+        for (int px = lane; px < n; px += 32) sk[d * ld + px] = sk[d * ld + px] / s;
+    }
+    __syncthreads();
+    // ctx[d][e]: warp w owns d = 4w..4w+3, lane = e
+    {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* k0 = sk + (warp * 4) * ld;
+        const float* vv = sv + lane * ld;
+        for (int px = 0; px < n; ++px) {
+            const float x = vv[px];
+            a0 = fmaf(k0[px], x, a0);
+            a1 = fmaf(k0[ld + px], x, a1);
+            a2 = fmaf(k0[2 * ld + px], x, a2);
+            a3 = fmaf(k0[3 * ld + px], x, a3);
+        }
+        ctx[(warp * 4 + 0) * 33 + lane] = a0;
+        ctx[(warp * 4 + 1) * 33 + lane] = a1;
+        ctx[(warp * 4 + 2) * 33 + lane] = a2;
+        ctx[(warp * 4 + 3) * 33 + lane] = a3;
+    }
+    __syncthreads();
+    // out[e][px] = sum_d ctx[d][e] q[d][px]; thread = pixel
+    T* out = reinterpret_cast<T*>(p.out);
+    for (int px = tid; px < n; px += LA_THREADS) {
+        float qv[32];
+#pragma unroll
+        for (int d = 0; d < 32; ++d) qv[d] = sq[d * ld + px];
+#pragma unroll 1
+        for (int cbl = 0; cbl < 4; ++cbl) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = cbl * 8 + j;
+                float a = 0.f;
+#pragma unroll
+                for (int d = 0; d < 32; ++d) a = fmaf(ctx[d * 33 + e], qv[d], a);
+                o[j] = a;
+            }
+            store8(out + ((size_t)((head * 4 + cbl) * p.B + b) * n + px) * 8, o);
+        }
+    }
+}
+static size_t linattn_smem(int n) { return (size_t)(3 * 32 * (n + 1) + 32 * 33) * sizeof(float); }
+cudaError_t simt_configure() {
+    cudaError_t e = cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)linattn_smem(256));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_linattn<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)linattn_smem(256));
+}
+cudaError_t launch_linattn(const AttnParams& p, cudaStream_t s) {
+    const size_t smem = linattn_smem(p.n);
+    if (p.n > 256) return cudaErrorInvalidValue;
+    if (p.is_bf16) k_linattn<__nv_bfloat16><<<p.B * 4, LA_THREADS, smem, s>>>(p);
+    else k_linattn<float><<<p.B * 4, LA_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// mid-block Attention core (unet.py:114-121), n = H*W <= 64.  One CTA (64 threads) per (sample, head).
+// ------------------------------------------------------------------------------------------------
+constexpr int MA_MAXN = 64;
+template <typename T>
+__global__ void __launch_bounds__(64) k_midattn(AttnParams p) {
+    __shared__ float sq[32][MA_MAXN + 1], sk[32][MA_MAXN + 1], sv[32][MA_MAXN + 1];
+    __shared__ float sim[MA_MAXN][MA_MAXN + 1];
+    const int n = p.n;
+    const int b = blockIdx.x >> 2, head = blockIdx.x & 3, tid = threadIdx.x;
+    const T* qkv = reinterpret_cast<const T*>(p.qkv);
+    for (int it = tid; it < 12 * n; it += 64) {
+        const int which = it / (4 * n), rem = it % (4 * n), cbl = rem / n, px = rem % n;
+        const int plane = which * 16 + head * 4 + cbl;
+        float x[8];
+        load8(qkv + ((size_t)(plane * p.B + b) * n + px) * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (which == 0) sq[cbl * 8 + j][px] = x[j] * 0.17677669529663687f;   // q * scale (unet.py:114)
+            else if (which == 1) sk[cbl * 8 + j][px] = x[j];
+            else sv[cbl * 8 + j][px] = x[j];
+        }
+    }
+    __syncthreads();
+    for (int ij = tid; ij < n * n; ij += 64) {
+        const int i = ij / n, j = ij % n;
+        float a = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < 32; ++d) a = fmaf(sq[d][i], sk[d][j], a);
+        sim[i][j] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 64) {          // softmax over j (the amax subtraction of unet.py:117 included)
+        float m = -INFINITY;
+        for (int j = 0; j < n; ++j) m = fmaxf(m, sim[i][j]);
+        float s = 0.f;
+        for (int j = 0; j < n; ++j) { const float e = expf(sim[i][j] - m); sim[i][j] = e; s += e; }
+        for (int j = 0; j < n; ++j) sim[i][j] = sim[i][j] / s;
+    }
+    __syncthreads();
+    // out[i][d] = sum_j attn[i][j] v[d][j] -> channel head*32+d at pixel i  ('b h (x y) d -> b (h d) x y')
+    T* out = reinterpret_cast<T*>(p.out);
+    for (int it = tid; it < 4 * n; it += 64) {
+        const int cbl = it / n, i = it % n;
+        float o[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int d = cbl * 8 + jj;
+            float a = 0.f;
+            for (int j = 0; j < n; ++j) a = fmaf(sim[i][j], sv[d][j], a);
+            o[jj] = a;
+        }
+        store8(out + ((size_t)((head * 4 + cbl) * p.B + b) * n + i) * 8, o);
+    }
+}
+cudaError_t launch_midattn(const AttnParams& p, cudaStream_t s) {
+    if (p.n > MA_MAXN) return cudaErrorInvalidValue;
+    if (p.is_bf16) k_midattn<__nv_bfloat16><<<p.B * 4, 64, 0, s>>>(p);
+    else k_midattn<float><<<p.B * 4, 64, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding -> FiLM rows.  grid (n_rows, splits); each CTA recomputes the small MLP and
+// produces a slice of the row's film_dim outputs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(128) k_temb(TembParams p) {
+    extern __shared__ float sm[];
+    float* e = sm;                       // [dim]
+    float* h = e + p.dim;                // [time_dim]
+    float* t = h + p.time_dim;           // [time_dim]
+    float* c = t + p.time_dim;           // [time_dim]
+    const int row = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const float tv = p.t[(size_t)row * p.t_stride];
+    const int half = p.dim >> 1;
+    for (int j = tid; j < half; j += NT) {           // unet.py:28-29: [sin | cos]
+        const float a = tv * p.freqs[j];
+        e[j] = sinf(a);
+        e[half + j] = cosf(a);
+    }
+    __syncthreads();
+    for (int j = tid; j < p.time_dim; j += NT) {     // Linear(dim, time_dim) -> GELU
+        float a = p.b1[j];
+        for (int i = 0; i < p.dim; ++i) a = fmaf(e[i], p.w1t[i * p.time_dim + j], a);
+        h[j] = gelu_erf(a);
+    }
+    __syncthreads();
+    for (int j = tid; j < p.time_dim; j += NT) {     // Linear(time_dim, time_dim)
+        float a = p.b2[j];
+        for (int i = 0; i < p.time_dim; ++i) a = fmaf(h[i], p.w2t[i * p.time_dim + j], a);
+        t[j] = a;
+    }
+    if (p.cls != nullptr && p.n_classes > 0) {       // class_cond_mlp (unet.py:207-212,316)
+        __syncthreads();
+        long long id = p.cls[row];
+        if (id < 0) id = 0;
+        if (id >= p.n_classes) id = p.n_classes - 1;
+        const float* emb = p.emb + (size_t)id * p.time_dim;
+        for (int j = tid; j < p.time_dim; j += NT) {
+            float a = p.bc1[j];
+            for (int i = 0; i < p.time_dim; ++i) a = fmaf(emb[i], p.wc1t[i * p.time_dim + j], a);
+            c[j] = gelu_erf(a);
+        }
+        __syncthreads();
+        for (int j = tid; j < p.time_dim; j += NT) {
+            float a = p.bc3[j];
+            for (int i = 0; i < p.time_dim; ++i) a = fmaf(c[i], p.wc3t[i * p.time_dim + j], a);
+            t[j] += a;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < p.time_dim; j += NT) {     // ResnetBlock.mlp[0] = SiLU (unet.py:80)
+        const float x = t[j];
+        h[j] = x / (1.0f + expf(-x));
+    }
+    __syncthreads();
+    const int per = (p.film_dim + gridDim.y - 1) / gridDim.y;
+    const int o0 = blockIdx.y * per, o1 = min(p.film_dim, o0 + per);
+    for (int o = o0 + tid; o < o1; o += NT) {        // all ResnetBlock Linear(time_dim, 2*dim_out) at once
+        float a = p.bf[o];
+        for (int i = 0; i < p.time_dim; ++i) a = fmaf(h[i], p.wft[(size_t)i * p.film_dim + o], a);
+        p.film[(size_t)row * p.film_dim + o] = a;
+    }
+}
+cudaError_t launch_temb(const TembParams& p, cudaStream_t s) {
+    if (p.n_rows <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(p.dim + 3 * p.time_dim) * sizeof(float);
+    int splits = p.n_rows >= 256 ? 2 : 16;
+    dim3 grid(p.n_rows, splits);
+    k_temb<<<grid, 128, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// final_conv 1x1 + integrator stage epilogue
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_final(FinalParams p) {
+    Ctrl* c = p.ctrl;
+    const int step = c->step;
+    const Stage st = c->stages[step];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < p.B * p.HW) {
+        const int b = idx / p.HW, px = idx % p.HW;
+        float x[64];
+        const int ncb = p.dim >> 3;
+        for (int cb = 0; cb < ncb; ++cb) load8(p.in + ((size_t)(cb * p.B + b) * p.HW + px) * 8, x + cb * 8);
+        const size_t plane = (size_t)p.B * p.channels * p.HW;
+        for (int co = 0; co < p.channels; ++co) {
+            float k = 0.f;
+            for (int i = 0; i < p.dim; ++i) k = fmaf(x[i], p.w[co * p.dim + i], k);
+            k += p.bias[co];
+            const size_t o = ((size_t)b * p.channels + co) * p.HW + px;
+            if (st.flags & SF_CFG_COMBINE) {        // v = v_nc + cfg*(v_c - v_nc)   (sampling.py:74)
+                const float vc = c->vcond[o];
+                k = __fadd_rn(k, __fmul_rn(c->cfg, __fsub_rn(vc, k)));
+            }
+            if (c->vtrace && st.eval_idx >= 0) c->vtrace[(size_t)st.eval_idx * plane + o] = k;
+            switch (st.kind) {
+                case ST_PLAIN: c->vout[o] = k; break;
+                case ST_CFG_COND: c->vcond[o] = k; break;
+                case ST_RK1: {
+                    c->acc[o] = k;
+                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(__fmul_rn(st.dt, k), 0.5f));
+                } break;
+                case ST_RK2: {
+                    c->acc[o] = __fadd_rn(c->acc[o], __fmul_rn(2.0f, k));
+                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(__fmul_rn(st.dt, k), 0.5f));
+                } break;
+                case ST_RK3: {
+                    c->acc[o] = __fadd_rn(c->acc[o], __fmul_rn(2.0f, k));
+                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(st.dt, k));
+                } break;
+                case ST_RK4: {
+                    const float a = __fadd_rn(c->acc[o], k);
+                    const float yn = __fadd_rn(c->y[o], __fmul_rn(st.dt6, a));
+                    c->y[o] = yn; c->xs[o] = yn;
+                } break;
+                case ST_EULER: {
+                    const float yn = __fadd_rn(c->y[o], __fmul_rn(k, st.dt));
+                    c->y[o] = yn; c->xs[o] = yn;
+                } break;
+                default: break;
+            }
+        }
+    }
+    // the last CTA to finish advances the stage counter: every CTA has read `step` before it arrives here
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(&c->done_ctr, 1);
+        if (done == (int)gridDim.x - 1) {
+            c->done_ctr = 0;
+            c->step = step + 1;
+            __threadfence();
+        }
+    }
+}
+cudaError_t launch_final(const FinalParams& p, cudaStream_t s) {
+    const int n = p.B * p.HW;
+    k_final<<<(n + 127) / 128, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace flo

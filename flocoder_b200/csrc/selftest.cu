@@ -1,0 +1,204 @@
+// flo_selftest_umma: on-device checks of the tcgen05/TMEM/TMA building blocks.
+//   1. descriptor micro-GEMMs: canonical no-swizzle K-major operands, shifted start addresses and
+//      non-128-byte group strides (the forms the implicit-GEMM convolution relies on) vs a host GEMM;
+//   2. the full tcgen05 convolution kernel vs the CUDA-core convolution on identical bf16 inputs,
+//      for every layer shape class of the U-Net (strip / flattened tiles, concat, n-tiling, batch tail).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "flo_internal.h"
+
+namespace flo {
+
+struct Report {
+    std::string text;
+    int fails = 0;
+    void line(bool ok, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        text += ok ? "PASS " : "FAIL ";
+        text += buf;
+        text += "\n";
+        if (!ok) ++fails;
+    }
+};
+
+static uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s; }
+static float rnd(uint32_t& s) { return ((lcg(s) >> 8) & 0xFFFF) / 32768.0f - 1.0f; }   // [-1, 1)
+
+#define ST_CUDA(expr)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            set_error("selftest: %s failed: %s", #expr, cudaGetErrorString(_e));           \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+static int micro_case(Report& rep, cudaStream_t st, int N, int K, int a_lbo, int a_sbo, int a_shift) {
+    uint32_t seed = 1234u + N * 7 + K;
+    std::vector<__nv_bfloat16> a((size_t)128 * K), b((size_t)N * K);
+    for (auto& v : a) v = __float2bfloat16(rnd(seed));
+    for (auto& v : b) v = __float2bfloat16(rnd(seed));
+    __nv_bfloat16 *da, *db;
+    float* dd;
+    ST_CUDA(cudaMalloc(&da, a.size() * 2));
+    ST_CUDA(cudaMalloc(&db, b.size() * 2));
+    ST_CUDA(cudaMalloc(&dd, (size_t)128 * N * 4));
+    ST_CUDA(cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemset(dd, 0, (size_t)128 * N * 4));
+    ST_CUDA(launch_umma_micro(da, db, dd, N, K, a_lbo, a_sbo, a_shift, N * 16, 128, st));
+    ST_CUDA(cudaStreamSynchronize(st));
+    std::vector<float> d((size_t)128 * N);
+    ST_CUDA(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double r = 0;
+            for (int k = 0; k < K; ++k) r += (double)__bfloat162float(a[(size_t)m * K + k]) * __bfloat162float(b[(size_t)n * K + k]);
+            maxerr = fmax(maxerr, fabs(r - d[(size_t)m * N + n]));
+            maxref = fmax(maxref, fabs(r));
+        }
+    rep.line(maxerr <= 1e-3 * fmax(1.0, maxref), "umma_micro N=%d K=%d a_lbo=%d a_sbo=%d a_shift=%d  max|err|=%.3g max|ref|=%.3g", N, K,
+             a_lbo, a_sbo, a_shift, maxerr, maxref);
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return 0;
+}
+
+static int conv_case(Report& rep, cudaStream_t st, const char* name, int B, int H, int W, int C0, int C1, int cout,
+                     int ksize, int n_tile, bool with_res) {
+    const int cin = C0 + C1, taps = ksize * ksize, HW = H * W;
+    uint32_t seed = 99u + H * 131 + cin * 7 + cout;
+    std::vector<float> w((size_t)cout * cin * taps), bias(cout);
+    const float wscale = 1.0f / sqrtf((float)(cin * taps));
+    for (auto& v : w) v = __bfloat162float(__float2bfloat16(rnd(seed) * wscale));
+    for (auto& v : bias) v = rnd(seed);
+    auto make_in = [&](int C, std::vector<__nv_bfloat16>& v) {
+        v.resize((size_t)C * B * HW);
+        for (auto& x : v) x = __float2bfloat16(rnd(seed));
+    };
+    std::vector<__nv_bfloat16> in0, in1;
+    make_in(C0, in0);
+    if (C1) make_in(C1, in1);
+    std::vector<float> res((size_t)cout * B * HW);
+    for (auto& v : res) v = rnd(seed);
+    // weights: SIMT [tap][cin][cout] fp32, UMMA packed stream
+    std::vector<float> wsimt((size_t)taps * cin * cout);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < taps; ++t) wsimt[((size_t)t * cin + ci) * cout + co] = w[((size_t)co * cin + ci) * taps + t];
+    std::vector<__nv_bfloat16> wumma;
+    pack_umma_weights(w.data(), cout, cin, ksize, nullptr, n_tile, wumma);
+
+    __nv_bfloat16 *d_in0 = nullptr, *d_in1 = nullptr, *d_wu = nullptr, *d_oo = nullptr;
+    float *d_ws = nullptr, *d_bias = nullptr, *d_res = nullptr, *d_ref = nullptr, *d_om = nullptr;
+    const size_t out_n = (size_t)cout * B * HW;
+    ST_CUDA(cudaMalloc(&d_in0, in0.size() * 2));
+    ST_CUDA(cudaMemcpy(d_in0, in0.data(), in0.size() * 2, cudaMemcpyHostToDevice));
+    if (C1) {
+        ST_CUDA(cudaMalloc(&d_in1, in1.size() * 2));
+        ST_CUDA(cudaMemcpy(d_in1, in1.data(), in1.size() * 2, cudaMemcpyHostToDevice));
+    }
+    ST_CUDA(cudaMalloc(&d_wu, wumma.size() * 2));
+    ST_CUDA(cudaMemcpy(d_wu, wumma.data(), wumma.size() * 2, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMalloc(&d_ws, wsimt.size() * 4));
+    ST_CUDA(cudaMemcpy(d_ws, wsimt.data(), wsimt.size() * 4, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMalloc(&d_bias, bias.size() * 4));
+    ST_CUDA(cudaMemcpy(d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMalloc(&d_res, res.size() * 4));
+    ST_CUDA(cudaMemcpy(d_res, res.data(), res.size() * 4, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMalloc(&d_ref, out_n * 4));
+    ST_CUDA(cudaMalloc(&d_om, out_n * 4));
+    ST_CUDA(cudaMalloc(&d_oo, out_n * 2));
+    ST_CUDA(cudaMemset(d_om, 0xFF, out_n * 4));   // NaN pattern: unwritten outputs are caught
+    ST_CUDA(cudaMemset(d_oo, 0xFF, out_n * 2));
+
+    ConvSimtParams sp{};
+    sp.in0 = d_in0; sp.in1 = d_in1; sp.ncb0 = C0 / 8; sp.ncb1 = C1 / 8; sp.in_is_bf16 = 1; sp.w = d_ws; sp.bias = d_bias;
+    sp.res = with_res ? d_res : nullptr; sp.out_m = d_ref; sp.out_o = nullptr; sp.o_is_bf16 = 0;
+    sp.B = B; sp.H = H; sp.W = W; sp.cout = cout; sp.ksize = ksize;
+    ST_CUDA(launch_conv_simt(sp, st));
+
+    ConvUmmaParams up{};
+    ConvShape cs{name, H, W, ksize, C0 / 8, C1 / 8, cout, n_tile};
+    if (plan_umma(cs, B, up)) return -1;
+    CUtensorMap t0, t1;
+    if (make_tmap(&t0, d_in0, C0 / 8, B, H, W, ksize / 2, up.nb)) return -1;
+    t1 = t0;
+    if (C1 && make_tmap(&t1, d_in1, C1 / 8, B, H, W, ksize / 2, up.nb)) return -1;
+    up.w = d_wu; up.bias = d_bias; up.res = with_res ? d_res : nullptr; up.out_m = d_om; up.out_o = d_oo;
+    ST_CUDA(conv_umma_configure());
+    ST_CUDA(launch_conv_umma(up, t0, t1, st));
+    ST_CUDA(cudaStreamSynchronize(st));
+
+    std::vector<float> ref(out_n), om(out_n);
+    std::vector<__nv_bfloat16> oo(out_n);
+    ST_CUDA(cudaMemcpy(ref.data(), d_ref, out_n * 4, cudaMemcpyDeviceToHost));
+    ST_CUDA(cudaMemcpy(om.data(), d_om, out_n * 4, cudaMemcpyDeviceToHost));
+    ST_CUDA(cudaMemcpy(oo.data(), d_oo, out_n * 2, cudaMemcpyDeviceToHost));
+    double e_m = 0, e_o = 0, mref = 0;
+    size_t bad = 0;
+    for (size_t i = 0; i < out_n; ++i) {
+        const double r = ref[i];
+        mref = fmax(mref, fabs(r));
+        const double dm = fabs(om[i] - r), dob = fabs(__bfloat162float(oo[i]) - r);
+        if (!(dm == dm) || !(dob == dob)) { ++bad; continue; }
+        e_m = fmax(e_m, dm);
+        e_o = fmax(e_o, dob);
+    }
+    const bool ok = bad == 0 && e_m <= 2e-4 * fmax(1.0, mref) && e_o <= 1e-2 * fmax(1.0, mref);
+    rep.line(ok, "conv %-22s B=%d %dx%d cin=%d+%d cout=%d k=%d | nb=%d mt=%d n_tile=%d S=%d stages=%d smem=%d tmem=%d | "
+                 "max|f32 err|=%.3g max|bf16 err|=%.3g max|ref|=%.3g nan=%zu",
+             name, B, H, W, C0, C1, cout, ksize, up.nb, up.n_mtiles, up.n_tile, up.slices_per_stage, up.n_wstages, up.smem_bytes,
+             up.tmem_cols, e_m, e_o, mref, bad);
+    cudaFree(d_in0); if (d_in1) cudaFree(d_in1);
+    cudaFree(d_wu); cudaFree(d_ws); cudaFree(d_bias); cudaFree(d_res); cudaFree(d_ref); cudaFree(d_om); cudaFree(d_oo);
+    return 0;
+}
+
+}  // namespace flo
+
+using namespace flo;
+
+extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Report rep;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device"); return -1; }
+    int rc = 0;
+    // ---- descriptor micro-GEMMs
+    rc |= micro_case(rep, st, 16, 16, 2048, 128, 0);
+    rc |= micro_case(rep, st, 64, 64, 2048, 128, 0);
+    rc |= micro_case(rep, st, 128, 144, 2048, 128, 0);
+    rc |= micro_case(rep, st, 256, 32, 2048, 128, 0);
+    rc |= micro_case(rep, st, 32, 32, 2560, 128, 16 * 19);        // odd-pixel start shift
+    rc |= micro_case(rep, st, 16, 32, 5184, 288, 304);            // strip mode: group stride = padded row pitch
+    rc |= micro_case(rep, st, 48, 16, 2048, 128, 0);              // N multiple of 16 but not a power of two
+    auto flush = [&]() { if (report && report_cap > 0) snprintf(report, report_cap, "%s", rep.text.c_str()); };
+    if (rc) { flush(); return -1; }
+    // ---- tcgen05 convolution vs CUDA-core convolution
+    rc |= conv_case(rep, st, "3x3 16->16 @16 strip", 5, 16, 16, 16, 0, 16, 3, 16, false);
+    rc |= conv_case(rep, st, "3x3 16+16->16 @16", 5, 16, 16, 16, 16, 16, 3, 16, true);
+    rc |= conv_case(rep, st, "1x1 16->384 @16 qkv", 3, 16, 16, 16, 0, 384, 1, 128, false);
+    rc |= conv_case(rep, st, "1x1 128->16 @16", 3, 16, 16, 128, 0, 16, 1, 16, true);
+    rc |= conv_case(rep, st, "3x3 16->16 @8 flat", 7, 8, 8, 16, 0, 16, 3, 16, false);
+    rc |= conv_case(rep, st, "1x1 64->16 @8 down", 7, 8, 8, 64, 0, 16, 1, 16, false);
+    rc |= conv_case(rep, st, "3x3 32->32 @4", 37, 4, 4, 32, 0, 32, 3, 32, true);
+    rc |= conv_case(rep, st, "3x3 64+32->64 @4", 37, 4, 4, 64, 32, 64, 3, 64, false);
+    rc |= conv_case(rep, st, "3x3 64->128 @2", 70, 2, 2, 64, 0, 128, 3, 128, false);
+    rc |= conv_case(rep, st, "3x3 128+64->128 @2", 70, 2, 2, 128, 64, 128, 3, 128, true);
+    rc |= conv_case(rep, st, "1x1 128->384 @2 qkv", 70, 2, 2, 128, 0, 384, 1, 128, false);
+    rc |= conv_case(rep, st, "3x3 32->16 @16 up", 300, 16, 16, 32, 0, 16, 3, 16, false);
+    flush();
+    if (rc) return -1;
+    return rep.fails;
+}

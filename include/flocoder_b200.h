@@ -28,6 +28,12 @@ extern "C" {
 
 #define FLO_VERSION 100 /* 0.1.0 */
 
+#if defined(__GNUC__)
+#define FLO_API __attribute__((visibility("default")))
+#else
+#define FLO_API
+#endif
+
 typedef enum flo_status {
     FLO_OK = 0,
     FLO_ERR_INVALID = -1,     /* bad argument (ValueError in Python) */
@@ -71,28 +77,33 @@ typedef struct flo_unet_cfg {
 
 typedef struct flo_unet flo_unet_t;
 
-int flo_version(void);
-const char* flo_last_error(void);
+FLO_API int flo_version(void);
+FLO_API const char* flo_last_error(void);
 
 /* Parameter manifest: the tensors of the reference state_dict, in state_dict order
  * (e.g. "downs.0.2.fn.fn.to_qkv.weight").  Shapes are the reference's
  * (OIHW conv weights, [out,in] linear weights). */
-int flo_param_count(const flo_unet_cfg* cfg);
-int flo_param_info(const flo_unet_cfg* cfg, int index, char* name, int name_cap, int64_t shape[4], int* ndim);
+FLO_API int flo_param_count(const flo_unet_cfg* cfg);
+FLO_API int flo_param_info(const flo_unet_cfg* cfg, int index, char* name, int name_cap, int64_t shape[4], int* ndim);
 
 /* Build a handle from fp32 device tensors given in manifest order; packs them into the
  * kernels' layouts (replaces Unet.__init__ + load_state_dict, unet.py:165-286). */
-int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const* params, int n_params,
+FLO_API int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const* params, int n_params,
                     void* stream);
-int flo_unet_destroy(flo_unet_t* h);
+FLO_API int flo_unet_destroy(flo_unet_t* h);
+
+/* Optional: overwrite the dim/2 sinusoidal-embedding frequencies exp(-j*ln(1e4)/(dim/2-1))
+ * (unet.py:26-27) with host values computed by the caller's own exp(), so the table is bit-identical
+ * to the reference's torch.exp; the built-in default is the correctly rounded value. */
+FLO_API int flo_unet_set_time_freqs(flo_unet_t* h, const float* freqs_host, int n);
 
 /* Bytes of activation workspace the handle holds for batch size B. */
-size_t flo_workspace_bytes(flo_unet_t* h, int B);
+FLO_API size_t flo_workspace_bytes(flo_unet_t* h, int B);
 
 /* v = Unet.forward(x, time, cond)  (unet.py:374-377).
  * x, v: [B,C,H,W] fp32 NCHW;  time: [B] fp32, already multiplied by t_scale;
  * class_ids: [B] int64 or NULL (cond['class_cond'], unet.py:315-316). */
-int flo_unet_forward(flo_unet_t* h, const float* x, const float* time, const int64_t* class_ids, float* v,
+FLO_API int flo_unet_forward(flo_unet_t* h, const float* x, const float* time, const int64_t* class_ids, float* v,
                      int B, void* stream);
 
 /* Whole trajectory on the device, no host synchronisation (replaces the loop of
@@ -102,35 +113,35 @@ int flo_unet_forward(flo_unet_t* h, const float* x, const float* time, const int
  * class_ids: [B] int64 device or NULL.  cfg_strength: classifier-free guidance; if class_ids
  *   != NULL and cfg_strength != 0 every evaluation is v_nc + cfg*(v_c - v_nc) (sampling.py:69-74).
  * v_trace: optional [n_eval,B,C,H,W] fp32 device buffer receiving every stage velocity, or NULL. */
-int flo_integrate(flo_unet_t* h, float* y, const float* ts, int n_ts, int method, float dt, float t_scale,
+FLO_API int flo_integrate(flo_unet_t* h, float* y, const float* ts, int n_ts, int method, float dt, float t_scale,
                   const int64_t* class_ids, float cfg_strength, float* v_trace, int B, void* stream);
 
 /* Same with HOST buffers: copies x0 (host, ideally pinned) to the device, integrates, copies the
  * final latents back into x1 (host) and waits for completion.  class_ids is a HOST array here. */
-int flo_integrate_host(flo_unet_t* h, const float* x0, float* x1, const float* ts, int n_ts, int method,
+FLO_API int flo_integrate_host(flo_unet_t* h, const float* x0, float* x1, const float* ts, int n_ts, int method,
                        float dt, float t_scale, const int64_t* class_ids, float cfg_strength, int B,
                        void* stream);
 
 /* Number of function evaluations flo_integrate performs for (method, n_ts) -- the honest count,
  * not the reference's n_steps*4 over-count (sampling.py:121). */
-int flo_integrate_nfe(int method, int n_ts);
+FLO_API int flo_integrate_nfe(int method, int n_ts);
 
 /* ---- introspection (tests, bench) ---- */
-int flo_unet_num_ops(flo_unet_t* h);
-int flo_unet_op_name(flo_unet_t* h, int index, char* name, int name_cap);
+FLO_API int flo_unet_num_ops(flo_unet_t* h);
+FLO_API int flo_unet_op_name(flo_unet_t* h, int index, char* name, int name_cap);
 /* Kernel launches issued per forward pass (graph nodes) and total since creation. */
-int flo_unet_launches_per_forward(flo_unet_t* h, int B);
-int64_t flo_unet_launch_count(flo_unet_t* h);
+FLO_API int flo_unet_launches_per_forward(flo_unet_t* h, int B);
+FLO_API int64_t flo_unet_launch_count(flo_unet_t* h);
 /* Copy a named intermediate of the LAST forward at batch B to a HOST fp32 NCHW buffer (needs
  * FLO_FLAG_NO_BUFFER_REUSE).  shape receives [B,C,H,W]. */
-int flo_unet_read_activation(flo_unet_t* h, const char* name, int B, float* out, int64_t cap,
+FLO_API int flo_unet_read_activation(flo_unet_t* h, const char* name, int B, float* out, int64_t cap,
                              int64_t shape[4], void* stream);
 
 /* ---- self tests of the sm_100a building blocks (GPU required) ---- */
 /* Runs tcgen05/TMEM/TMA micro-GEMMs with the exact descriptor forms the conv kernel uses and
  * compares with a CPU result.  Returns the number of failing cases (0 = all good, <0 = error);
  * a human-readable report is written to `report` (may be NULL). */
-int flo_selftest_umma(char* report, int report_cap, void* stream);
+FLO_API int flo_selftest_umma(char* report, int report_cap, void* stream);
 
 #ifdef __cplusplus
 }

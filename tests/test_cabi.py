@@ -1,0 +1,87 @@
+"""The C-ABI library: loads without a GPU, exports every symbol include/flocoder_b200.h declares,
+and its host-side logic (manifest, validation, error mapping) behaves.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import CONFIGS, ROOT
+from flocoder_b200 import _lib
+from flocoder_b200.unet import Unet
+
+HEADER = os.path.join(ROOT, "include", "flocoder_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"FLO_API\s+[\w\s\*]+?\b(flo_\w+)\s*\(", text)))
+
+
+def test_library_is_built_and_loads():
+    assert os.path.isfile(_lib.LIB_PATH), "run `python -m flocoder_b200.build`"
+    L = _lib.lib()
+    assert L.flo_version() == 100
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_manifest_matches_module_state_dict(name):
+    n_classes = CONFIGS[name]
+    m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=n_classes)
+    cfg = _lib.make_cfg(16, 4, (1, 2, 4, 8), 4, n_classes, 16, 16, "fp32", 0)
+    manifest = _lib.param_manifest(cfg)
+    sd = m.state_dict()
+    assert [n for n, _ in manifest] == list(sd.keys())
+    for n, shape in manifest:
+        assert tuple(sd[n].shape) == shape, n
+
+
+def test_manifest_generic_dims():
+    m = Unet(dim=32, channels=3, dim_mults=[1, 2, 2], resnet_block_groups=8, n_classes=5)
+    cfg = _lib.make_cfg(32, 3, (1, 2, 2), 8, 5, 8, 8, "bf16", 0)
+    manifest = _lib.param_manifest(cfg)
+    assert [n for n, _ in manifest] == list(m.state_dict().keys())
+
+
+def test_unsupported_configs_are_explicit_errors():
+    L = _lib.lib()
+    cfg = _lib.make_cfg(16, 4, (1, 2, 4, 8), 4, 0, 16, 16, "fp32", 0)
+    cfg.mask_cond = 1
+    with pytest.raises(NotImplementedError):
+        _lib.check(L.flo_param_count(ctypes.byref(cfg)))
+    assert b"mask_cond" in L.flo_last_error()
+    cfg = _lib.make_cfg(12, 4, (1, 2), 4, 0, 16, 16, "fp32", 0)       # dim not a multiple of 8
+    with pytest.raises(NotImplementedError):
+        _lib.check(L.flo_param_count(ctypes.byref(cfg)))
+    cfg = _lib.make_cfg(16, 4, (1, 2, 4, 8), 4, 0, 12, 12, "fp32", 0)  # 12 not divisible by 8
+    with pytest.raises(ValueError):
+        _lib.check(L.flo_param_count(ctypes.byref(cfg)))
+    cfg = _lib.make_cfg(24, 4, (1, 2), 4, 0, 16, 16, "bf16", 0)       # bf16 path needs dim % 16 == 0
+    with pytest.raises(NotImplementedError):
+        _lib.check(L.flo_param_count(ctypes.byref(cfg)))
+
+
+def test_nfe_counts():
+    L = _lib.lib()
+    assert L.flo_integrate_nfe(_lib.FLO_RK4, 50) == 196          # 49 intervals x 4 (SURVEY TL;DR)
+    assert L.flo_integrate_nfe(_lib.FLO_EULER_LEGACY, 10) == 10
+    assert L.flo_integrate_nfe(_lib.FLO_EULER_GRID, 10) == 9
+    assert L.flo_integrate_nfe(99, 10) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_create_without_gpu_fails_loudly():
+    m = Unet(dim=16, channels=4, n_classes=0)
+    with pytest.raises(RuntimeError):
+        _lib.Engine(dim=16, channels=4, dim_mults=(1, 2, 4, 8), groups=4, n_classes=0, height=16, width=16,
+                    compute_dtype="fp32", device="cpu", state_dict=m.state_dict())

@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / the frozen reference outputs.
+
+Bars (BASELINE.json north_star):
+  fp32 : per-step velocity and final latent rel-L2 <= 1e-5 vs the reference (fp32 CPU)
+  bf16 : per-step velocity rel-L2 <= 2e-3 vs the precision-matched oracle (bf16 GEMM operands,
+         fp32 elsewhere), final latent rel-L2 <= 1e-2 vs the fp32 reference
+"""
+import pytest
+import torch
+
+import oracle
+from oracle.unet_oracle import BF16_MATCHED, FP32, OracleModel, UnetSpec, unet_forward
+from conftest import CONFIGS, rel_l2, seeded_state_dict
+
+pytestmark = pytest.mark.gpu
+
+SHAPE = (8, 4, 16, 16)
+FP32_STEP_TOL = 1e-5
+FP32_FINAL_TOL = 1e-5
+BF16_STEP_TOL = 2e-3
+BF16_FINAL_TOL = 1e-2
+
+
+def spec_for(n_classes):
+    return UnetSpec(dim=16, dim_mults=(1, 2, 4, 8), channels=4, groups=4, n_classes=n_classes)
+
+
+_models = {}
+
+
+def gpu_model(n_classes, compute_dtype):
+    key = (n_classes, compute_dtype)
+    if key not in _models:
+        from flocoder_b200.unet import Unet
+        torch.manual_seed(1234)
+        m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=n_classes, compute_dtype=compute_dtype)
+        _models[key] = m.cuda().eval()
+    return _models[key]
+
+
+def test_selftest_tcgen05_building_blocks():
+    from flocoder_b200 import _lib
+    rc, report = _lib.selftest_umma()
+    print(report)
+    assert rc == 0, f"flo_selftest_umma reported {rc} failing case(s):\n{report}"
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_fp32_forward_matches_reference_golden(goldens, name):
+    g = goldens[name]
+    m = gpu_model(g["n_classes"], "fp32")
+    v = m(g["x0"].cuda(), g["fwd_t"].cuda())
+    assert rel_l2(v, g["fwd_v"]) <= FP32_STEP_TOL
+    v = m(g["x0"].cuda(), g["fwd_tvec"].cuda())                       # per-sample times
+    assert rel_l2(v, g["fwd_v_tvec"]) <= FP32_STEP_TOL
+    if g["n_classes"] > 0:
+        v = m(g["x0"].cuda(), g["fwd_t"].cuda(), cond={"class_cond": g["cls"].cuda()})
+        assert rel_l2(v, g["fwd_v_cls"]) <= FP32_STEP_TOL
+        v = m(g["x0"].cuda(), g["fwd_t"].cuda(), cond={"class_cond": None})
+        assert rel_l2(v, g["fwd_v"]) <= FP32_STEP_TOL
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_fp32_integrators_match_reference_golden(goldens, name):
+    from flocoder_b200 import sampling
+    g = goldens[name]
+    m = gpu_model(g["n_classes"], "fp32")
+    x0 = g["x0"].cuda()
+    x1, nfe = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, source=x0)
+    assert nfe == g["rk4_10_nfe"]
+    assert rel_l2(x1, g["rk4_10"]) <= FP32_FINAL_TOL
+    assert torch.equal(x0.cpu(), g["x0"]), "the caller's source tensor must not be modified"
+    x1, nfe = sampling.euler_sampler(m, SHAPE, 10, source=x0)
+    assert nfe == 10 and x1.device.type == "cpu"
+    assert rel_l2(x1, g["euler_10"]) <= FP32_FINAL_TOL
+    x1, nfe = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, source=x0, init_latents=g["init_latents"].cuda(),
+                                            init_strength=0.3)
+    assert nfe == g["rk4_10_init03_nfe"] and rel_l2(x1, g["rk4_10_init03"]) <= FP32_FINAL_TOL
+    if g["n_classes"] > 0:
+        cond = {"class_cond": g["cls"].cuda()}
+        x1, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, cond=cond, cfg_strength=3.0, source=x0)
+        assert rel_l2(x1, g["rk4_10_cfg3"]) <= FP32_FINAL_TOL
+        x1, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, cond=cond, cfg_strength=0, source=x0)
+        assert rel_l2(x1, g["rk4_10_cls_nocfg"]) <= FP32_FINAL_TOL
+
+
+def test_fp32_rk4_50_final_latent(goldens):
+    """BASELINE config shape (RK4, n_steps=50 -> 49 intervals, 196 evaluations) at B=8."""
+    from flocoder_b200 import sampling
+    g = goldens["flowers_sd"]
+    m = gpu_model(102, "fp32")
+    x1, nfe = sampling.generate_latents(m, SHAPE, method="rk4", n_steps=50, source=g["x0"].cuda())
+    assert nfe == 200
+    assert rel_l2(x1, g["rk4_50"]) <= FP32_FINAL_TOL
+
+
+def _layer_report(m, sd, spec, x, t, prec, names=None):
+    """Per-op rel-L2 of the CUDA activations vs the oracle trace (needs FLO_FLAG_NO_BUFFER_REUSE)."""
+    from flocoder_b200 import _lib
+    eng = _lib.Engine(dim=m.dim, channels=m.channels, dim_mults=m.dim_mults, groups=m.groups, n_classes=m.n_classes,
+                      height=x.shape[2], width=x.shape[3], compute_dtype=m._resolved_compute_dtype(),
+                      device=x.device, state_dict=m.state_dict(), flags=_lib.FLO_FLAG_NO_BUFFER_REUSE)
+    eng.forward(x.float().contiguous(), t.float().contiguous(), None)
+    torch.cuda.synchronize()
+    trace = {}
+    with torch.no_grad():
+        unet_forward(sd, spec, x.cpu(), t.cpu(), None, prec, trace)
+    rows = []
+    for name in eng.op_names():
+        if name in trace:
+            try:
+                a = eng.read_activation(name, x.shape[0])
+            except ValueError:
+                continue
+            rows.append((name, rel_l2(a, trace[name])))
+    eng.close()
+    return rows
+
+
+def test_fp32_per_layer_activations(goldens):
+    g = goldens["midi_vqgan"]
+    m = gpu_model(0, "fp32")
+    _, sd = seeded_state_dict(0)
+    rows = _layer_report(m, sd, spec_for(0), g["x0"].cuda(), g["fwd_t"].cuda(), FP32)
+    assert len(rows) > 60
+    worst = max(rows, key=lambda r: r[1])
+    for name, e in rows:
+        print(f"{name:40s} {e:.3e}")
+    assert worst[1] <= 1e-5, worst
+
+
+@pytest.mark.parametrize("n_classes", [102, 0])
+def test_bf16_teacher_forced_velocity_vs_matched_oracle(goldens, n_classes):
+    """Per-step velocity: feed every oracle stage input (y_stage, t_stage) of an RK4 trajectory to the
+    CUDA forward (isolates per-forward error from trajectory drift)."""
+    g = goldens["flowers_sd" if n_classes else "midi_vqgan"]
+    m = gpu_model(n_classes, "bf16")
+    _, sd = seeded_state_dict(n_classes)
+    matched = OracleModel(sd, spec_for(n_classes), BF16_MATCHED)
+    trace = []
+    oracle.generate_latents_rk4(matched, SHAPE, n_steps=6, source=g["x0"].clone(), trace=trace)
+    assert len(trace) == 20
+    worst = 0.0
+    for x_stage, t_stage, v_ref in trace:
+        t_vec = torch.full((SHAPE[0],), float(t_stage)) * 999
+        v = m(x_stage.cuda(), t_vec.cuda())
+        worst = max(worst, rel_l2(v, v_ref))
+    print("worst per-step velocity rel-L2 vs matched oracle:", worst)
+    assert worst <= BF16_STEP_TOL
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_bf16_final_latent_vs_fp32_reference(goldens, name):
+    from flocoder_b200 import sampling
+    g = goldens[name]
+    m = gpu_model(g["n_classes"], "bf16")
+    x1, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=50, source=g["x0"].cuda())
+    e = rel_l2(x1, g["rk4_50"])
+    print(name, "bf16 RK4-50 final latent rel-L2 vs fp32 reference:", e)
+    assert e <= BF16_FINAL_TOL
+    x1, _ = sampling.euler_sampler(m, SHAPE, 10, source=g["x0"].cuda())
+    assert rel_l2(x1, g["euler_10"]) <= BF16_FINAL_TOL
+
+
+def test_bf16_per_layer_activations_vs_matched_oracle(goldens):
+    g = goldens["midi_vqgan"]
+    m = gpu_model(0, "bf16")
+    _, sd = seeded_state_dict(0)
+    rows = _layer_report(m, sd, spec_for(0), g["x0"].cuda(), g["fwd_t"].cuda(), BF16_MATCHED)
+    for name, e in rows:
+        print(f"{name:40s} {e:.3e}")
+    worst = max(rows, key=lambda r: r[1])
+    assert worst[1] <= 1e-2, worst       # bf16 storage of the compared tensor itself is ~4e-3
+
+
+@pytest.mark.parametrize("compute_dtype", ["fp32", "bf16"])
+def test_batch_slices_are_independent_and_deterministic(compute_dtype):
+    """Size-independent properties at a BASELINE-sized batch: a B=256 trajectory equals the trajectories of
+    its slices (what batch sharding across GPUs relies on) and repeats bit-for-bit."""
+    from flocoder_b200 import sampling
+    m = gpu_model(0, compute_dtype)
+    B = 256
+    x0 = torch.randn(B, 4, 16, 16, generator=torch.Generator().manual_seed(5678)).cuda()
+    full, _ = sampling.generate_latents_rk4(m, (B, 4, 16, 16), n_steps=5, source=x0)
+    again, _ = sampling.generate_latents_rk4(m, (B, 4, 16, 16), n_steps=5, source=x0)
+    assert torch.equal(full, again)
+    assert torch.isfinite(full).all()
+    for lo, hi in ((0, 8), (100, 131), (248, 256)):
+        part, _ = sampling.generate_latents_rk4(m, (hi - lo, 4, 16, 16), n_steps=5, source=x0[lo:hi])
+        assert rel_l2(part, full[lo:hi]) <= (1e-6 if compute_dtype == "fp32" else 1e-6)
+
+
+def test_generic_rk4_step_composes_with_our_forward(goldens):
+    """rk4_step / v_func_cfg keep the reference semantics for an arbitrary f: composing them over
+    Unet.forward must agree with the fused flo_integrate trajectory."""
+    from flocoder_b200 import sampling
+    g = goldens["stl_sd"]
+    m = gpu_model(10, "fp32")
+    x0 = g["x0"].cuda()
+    ts = sampling.time_grid(6, device="cuda")
+    t_vec = torch.zeros(8, device="cuda")
+    cond = {"class_cond": g["cls"].cuda()}
+    y = x0.clone()
+    for i in range(len(ts) - 1):
+        y = sampling.rk4_step(lambda x, t: sampling.v_func_cfg(m, cond, 2.0, t_vec, x, t), y, ts[i], ts[i + 1] - ts[i])
+    fused, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=6, cond=cond, cfg_strength=2.0, source=x0)
+    assert rel_l2(fused, y) <= 2e-6
+
+
+def test_host_buffer_entry_point(goldens):
+    from flocoder_b200 import _lib, sampling
+    g = goldens["midi_vqgan"]
+    m = gpu_model(0, "fp32")
+    eng = m.engine(16, 16)
+    x0 = g["x0"].clone().pin_memory()
+    x1 = torch.empty_like(x0).pin_memory()
+    ts = sampling.time_grid(10).tolist()
+    eng.integrate_host(x0, x1, ts, _lib.FLO_RK4)
+    assert rel_l2(x1, g["rk4_10"]) <= FP32_FINAL_TOL
+
+
+def test_bf16_param_dtype_follows_module(goldens):
+    """model.to(bfloat16): bf16 parameters -> bf16 compute path, bf16 in / bf16 out at the boundary."""
+    from flocoder_b200.unet import Unet
+    g = goldens["midi_vqgan"]
+    torch.manual_seed(1234)
+    m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0).cuda().to(torch.bfloat16)
+    v = m(g["x0"].cuda().to(torch.bfloat16), g["fwd_t"].cuda())
+    assert v.dtype == torch.bfloat16
+    assert rel_l2(v.float(), g["fwd_v"]) <= 3e-2          # weights themselves are bf16-rounded here
