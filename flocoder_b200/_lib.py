@@ -27,7 +27,7 @@ EXPORTS = (
     "flo_version", "flo_last_error", "flo_param_count", "flo_param_info", "flo_unet_create",
     "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
     "flo_integrate_nfe", "flo_unet_num_ops", "flo_unet_op_name", "flo_unet_launches_per_forward",
-    "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma",
+    "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma", "flo_describe_plan",
 )
 
 
@@ -76,6 +76,7 @@ def lib() -> ctypes.CDLL:
     L.flo_unet_read_activation.argtypes = [c_void_p, c_char_p, c_int, c_void_p, c_int64, POINTER(c_int64),
                                            c_void_p]
     L.flo_selftest_umma.argtypes = [c_char_p, c_int, c_void_p]
+    L.flo_describe_plan.argtypes = [POINTER(FloUnetCfg), c_int, c_char_p, c_int]
     _lib_handle = L
     return L
 
@@ -259,6 +260,13 @@ class Engine:
         shp = tuple(shape[i] for i in range(4))
         n = shp[0] * shp[1] * shp[2] * shp[3]
         return out[:n].reshape(shp).clone()
+
+
+def describe_plan(cfg: FloUnetCfg, b: int) -> str:
+    """Host-only description of the op program / buffers / tcgen05 tilings (no GPU needed)."""
+    buf = create_string_buffer(1 << 20)
+    check(lib().flo_describe_plan(byref(cfg), b, buf, len(buf)), "flo_describe_plan")
+    return buf.value.decode()
 
 
 def selftest_umma() -> tuple:

@@ -564,7 +564,7 @@ int plan_umma(const ConvShape& op, int B, ConvUmmaParams& p) {
         p.nb = 1; p.n_mtiles = (H / 16) * (W / 8); p.sbo_px = Wp; p.row0 = 0; p.tile_stride = 0;
     } else {
         // flattened padded pixels; choose samples per CTA: enough CTAs to fill the GPU, then fewer junk rows
-        const int max_mt = std::max(1, std::min(4, 512 / op.n_tile));
+        const int max_mt = std::max(1, std::min(4, 256 / op.n_tile));   // <= 256 TMEM columns: two CTAs per SM
         int best_nb = 1; double best_cost = 1e30;
         for (int nb = 1; nb <= 64; ++nb) {
             const int rows = nb * PP - 2 * (pad ? Wp + 1 : 0);
@@ -1067,6 +1067,163 @@ int flo_unet_set_time_freqs(flo_unet_t* hh, const float* freqs, int n) {
     CUDA_TRY(cudaSetDevice(h->spec.device));
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(h->d_f32 + h->o_freqs, freqs, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    return FLO_OK;
+}
+
+// Host-only: build the op program for `cfg` (zero weights) and describe ops, buffers and tcgen05 tilings.
+int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap) {
+    Handle h;
+    int rc = make_spec(cfg, h.spec);
+    if (rc) return rc;
+    h.params = manifest(h.spec);
+    for (auto& pi : h.params) h.host[pi.name].assign((size_t)pi.numel(), 0.f);
+    Builder b(h);
+    rc = b.build();
+    if (rc) return rc;
+    allocate_arena(h);
+    std::string t;
+    char line[512];
+    snprintf(line, sizeof(line), "ops=%d bufs=%d film_dim=%d arena_bytes_per_sample=%zu f32_blob=%zu bf16_blob=%zu\n",
+             (int)h.ops.size(), (int)h.bufs.size(), h.film_dim, h.arena_ps, h.blob_f32.size(), h.blob_bf16.size());
+    t += line;
+    static const char* kinds[] = {"init", "conv", "gn", "linattn", "midattn", "final"};
+    auto bn = [&](int id) { return id >= 0 ? h.bufs[id].name.c_str() : "-"; };
+    for (size_t i = 0; i < h.ops.size(); ++i) {
+        const Op& op = h.ops[i];
+        if (op.kind == OP_CONV) {
+            snprintf(line, sizeof(line), "%3zu conv    %-28s %dx%d k=%d cin=%d+%d cout=%d in0=%s in1=%s res=%s out_m=%s out_o=%s", i,
+                     op.name.c_str(), op.H, op.W, op.ksize, op.ncb0 * 8, op.ncb1 * 8, op.cout, bn(op.in0), bn(op.in1), bn(op.res),
+                     bn(op.out_m), bn(op.out_o));
+            t += line;
+            if (h.spec.bf16) {
+                ConvUmmaParams up;
+                ConvShape cs{op.name.c_str(), op.H, op.W, op.ksize, op.ncb0, op.ncb1, op.cout, op.n_tile};
+                if (plan_umma(cs, B, up) == FLO_OK) {
+                    snprintf(line, sizeof(line), " | nb=%d mt=%d n_tile=%d sbo=%d S=%d stages=%d smem=%d tmem=%d ctas=%d", up.nb,
+                             up.n_mtiles, up.n_tile, up.sbo_px, up.slices_per_stage, up.n_wstages, up.smem_bytes, up.tmem_cols,
+                             ((B + up.nb - 1) / up.nb) * (op.cout / up.n_tile));
+                    t += line;
+                } else {
+                    t += " | UNSUPPORTED: " + g_last_error;
+                }
+            }
+            t += "\n";
+        } else if (op.kind == OP_GN) {
+            snprintf(line, sizeof(line), "%3zu gn      %-28s C=%d %dx%d groups=%d film=%d silu=%d in=%s res=%s out_m=%s out_o=%s un=%s up=%s\n", i,
+                     op.name.c_str(), op.C, op.H, op.W, op.groups, op.film_off, op.silu, bn(op.gn_in), bn(op.res), bn(op.out_m),
+                     bn(op.out_o), bn(op.out_un), bn(op.out_up));
+            t += line;
+        } else if (op.kind == OP_LINATTN || op.kind == OP_MIDATTN) {
+            snprintf(line, sizeof(line), "%3zu %-7s %-28s n=%d qkv=%s out=%s\n", i, kinds[op.kind], op.name.c_str(), op.n, bn(op.qkv),
+                     bn(op.attn_out));
+            t += line;
+        } else {
+            snprintf(line, sizeof(line), "%3zu %-7s %-28s in=%s out_m=%s out_o=%s\n", i, kinds[op.kind], op.name.c_str(), bn(op.gn_in),
+                     bn(op.out_m), bn(op.out_o));
+            t += line;
+        }
+    }
+    for (size_t i = 0; i < h.bufs.size(); ++i) {
+        const Buf& bf = h.bufs[i];
+        snprintf(line, sizeof(line), "buf %3zu %-34s C=%d %dx%d %s bytes_ps=%zu live=[%d,%d] off_ps=%zu\n", i, bf.name.c_str(), bf.C, bf.H,
+                 bf.W, bf.bf16 ? "bf16" : "f32 ", bf.bytes_ps, bf.def, bf.last, bf.off_ps);
+        t += line;
+    }
+    if (out && cap > 0) snprintf(out, cap, "%s", t.c_str());
+    return (int)t.size();
+}
+
+int flo_unet_op_info(flo_unet_t* hh, int index, int* kind, double* flops_per_sample, double* bytes_per_sample) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || index < 0 || index >= (int)h->ops.size()) { set_error("op index out of range"); return FLO_ERR_INVALID; }
+    const Op& op = h->ops[index];
+    const Spec& s = h->spec;
+    const double ob = s.bf16 ? 2.0 : 4.0;      // operand bytes
+    double fl = 0, by = 0;
+    const double hw = (double)op.H * op.W;
+    switch (op.kind) {
+        case OP_INIT:
+            fl = 2.0 * hw * s.dim * s.channels;
+            by = hw * (s.channels * 4.0 + s.dim * (ob + (s.bf16 ? 4.0 : 0.0)));
+            break;
+        case OP_CONV: {
+            const double cin = (op.ncb0 + op.ncb1) * 8.0;
+            fl = 2.0 * hw * op.cout * cin * op.ksize * op.ksize;
+            by = hw * cin * ob + hw * op.cout * ((op.out_m >= 0 ? 4.0 : 0.0) + (op.out_o >= 0 ? ob : 0.0) + (op.res >= 0 ? 4.0 : 0.0));
+        } break;
+        case OP_GN:
+            by = hw * op.C * (4.0 + (op.res >= 0 ? 4.0 : 0.0) + (op.out_m >= 0 ? 4.0 : 0.0) + (op.out_o >= 0 ? ob : 0.0) +
+                              (op.out_un >= 0 ? ob : 0.0) + (op.out_up >= 0 ? 4.0 * ob : 0.0));
+            fl = 10.0 * hw * op.C;
+            break;
+        case OP_LINATTN:
+            fl = 4.0 * 2.0 * 2.0 * 32.0 * 32.0 * op.n;        // 4 heads x (context + output) einsums (unet.py:146,148)
+            by = op.n * (384.0 + 128.0) * ob;
+            break;
+        case OP_MIDATTN:
+            fl = 4.0 * 2.0 * 2.0 * 32.0 * op.n * op.n;
+            by = op.n * (384.0 + 128.0) * ob;
+            break;
+        case OP_FINAL:
+            fl = 2.0 * hw * s.dim * s.channels;
+            by = hw * (s.dim * 4.0 + s.channels * 16.0);
+            break;
+    }
+    if (kind) *kind = op.kind;
+    if (flops_per_sample) *flops_per_sample = fl;
+    if (bytes_per_sample) *bytes_per_sample = by;
+    return FLO_OK;
+}
+
+int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !ms_per_op || reps < 1) { set_error("bad argument"); return FLO_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(h->spec.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan* pl = nullptr;
+    int rc = get_plan(*h, B, &pl);
+    if (rc) return rc;
+    const Spec& s = h->spec;
+    const int n_ops = (int)h->ops.size();
+    rc = ensure_stage_capacity(*h, 1);
+    if (rc) return rc;
+    // a plain forward on the current contents of the state buffers, FiLM rows for t = 500
+    std::vector<float> tvals(B, 500.0f);
+    float* d_t = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_t, (size_t)B * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(d_t, tvals.data(), (size_t)B * sizeof(float), cudaMemcpyHostToDevice));
+    TembParams tp = temb_params(*h);
+    tp.t = d_t; tp.t_stride = 1; tp.cls = nullptr; tp.n_rows = B; tp.film = pl->film_ps;
+    CUDA_TRY(launch_temb(tp, st));
+    Ctrl c{};
+    c.film_per_sample = 1; c.n_stages = 1;
+    c.y = pl->y; c.acc = pl->acc; c.xs = pl->xs; c.vcond = pl->vcond; c.vout = pl->vcond; c.film = pl->film_ps; c.stages = h->d_stages;
+    Stage s0{};
+    s0.kind = ST_PLAIN; s0.eval_idx = -1;
+    std::vector<cudaEvent_t> ev(n_ops + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    std::vector<float> best(n_ops, 1e30f);
+    for (int r = 0; r < reps + 1; ++r) {
+        CUDA_TRY(launch_setup_ctrl(pl->ctrl, c, h->d_stages, &s0, st));
+        for (int i = 0; i < n_ops; ++i) {
+            CUDA_TRY(cudaEventRecord(ev[i], st));
+            rc = launch_op(*h, *pl, i, st);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ev[n_ops], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (r == 0) continue;      // warm-up
+        for (int i = 0; i < n_ops; ++i) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            best[i] = std::min(best[i], ms);
+        }
+    }
+    for (int i = 0; i < n_ops; ++i) ms_per_op[i] = best[i];
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaFree(d_t);
+    (void)s;
+    h->launches += (int64_t)(reps + 1) * (n_ops + 1) + 1;
     return FLO_OK;
 }
 

@@ -127,8 +127,18 @@ FLO_API int flo_integrate_host(flo_unet_t* h, const float* x0, float* x1, const 
 FLO_API int flo_integrate_nfe(int method, int n_ts);
 
 /* ---- introspection (tests, bench) ---- */
+/* Host-only (no GPU needed): text description of the op program, activation buffers with their live
+ * ranges / arena offsets, and the tcgen05 tiling chosen for every convolution at batch B.
+ * Returns the length of the full text (which may exceed cap), or a negative flo_status. */
+FLO_API int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap);
 FLO_API int flo_unet_num_ops(flo_unet_t* h);
 FLO_API int flo_unet_op_name(flo_unet_t* h, int index, char* name, int name_cap);
+/* Per-op metadata: kind (0 init conv, 1 conv, 2 GroupNorm pass, 3 linear attention, 4 mid attention,
+ * 5 final conv + integrator epilogue), ALGORITHMIC flops and bytes per sample. */
+FLO_API int flo_unet_op_info(flo_unet_t* h, int index, int* kind, double* flops_per_sample, double* bytes_per_sample);
+/* Runs one forward at batch B op by op (no graph) `reps` times with a CUDA event around every kernel on
+ * `stream` and returns the best duration of each op in milliseconds (ms_per_op: HOST array, one per op). */
+FLO_API int flo_unet_profile_ops(flo_unet_t* h, int B, int reps, float* ms_per_op, void* stream);
 /* Kernel launches issued per forward pass (graph nodes) and total since creation. */
 FLO_API int flo_unet_launches_per_forward(flo_unet_t* h, int B);
 FLO_API int64_t flo_unet_launch_count(flo_unet_t* h);
