@@ -1,0 +1,322 @@
+"""Benchmark of the hot path: 50-step RK4 latent sampling of the flowers_sd-shaped U-Net.
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+A "step" is one whole trajectory (n_steps=50 -> 49 RK4 intervals, 196 U-Net evaluations) over one batch
+of synthetic latents.  At N=1 the workload is BASELINE.json configs[1] (flowers_sd, RK4-50, batch 256, bf16);
+for N>1 every rank integrates its own 256-sample slice (weak scaling; no per-step communication) and one
+NCCL all-gather assembles the global batch inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "samples/sec, 50-step RK4 latent sampling"
+UNIT = "samples/s"
+N_STEPS = 50                       # time-grid points -> 49 intervals, 196 evaluations (SURVEY.md TL;DR)
+NFE = 4 * (N_STEPS - 1)
+PER_GPU_BATCH = 256
+CONV_FLOP_PER_SAMPLE_FORWARD = 66_846_720      # 2*M*N*K over the 75 convolutions
+N_CLASSES = 102                                # flowers_sd
+LATENT = (4, 16, 16)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def workload_config(n_gpus, per_gpu_batch, dtype):
+    return {
+        "workload": f"flowers_sd latent U-Net (dim=16, mults 1-2-4-8, n_classes={N_CLASSES}, random init seed 1234), "
+                    f"RK4 n_steps={N_STEPS} (49 intervals, {NFE} evaluations), cond=None",
+        "global_batch": per_gpu_batch * n_gpus, "per_gpu_batch": per_gpu_batch, "latent": list(LATENT),
+        "nfe": NFE, "compute_dtype": dtype, "parallelism": f"batch-shard x{n_gpus} + final all-gather",
+        "l2": "256 MiB memset between steps (inside the timed region)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(batch, intervals, threads):
+    """Times `intervals` RK4 intervals (4 evaluations each) of the CPU oracle at `batch` and scales to the
+    full 49-interval trajectory.  Returns (samples/s for RK4-50, seconds measured)."""
+    import oracle
+    from oracle.unet_oracle import OracleModel, UnetSpec
+    from flocoder_b200.unet import Unet
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    sd = {k: v.detach().clone() for k, v in
+          Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=N_CLASSES).state_dict().items()}
+    model = OracleModel(sd, UnetSpec(dim=16, dim_mults=(1, 2, 4, 8), channels=4, groups=4, n_classes=N_CLASSES))
+    x0 = torch.randn(batch, *LATENT, generator=torch.Generator().manual_seed(5678))
+    ts = oracle.sampling_oracle.time_grid(N_STEPS)
+    t_vec = torch.zeros(batch)
+
+    def f(x, t):
+        return oracle.v_func_cfg(model, None, 0.0, t_vec, x, t)
+
+    t0 = time.perf_counter()
+    y = x0
+    with torch.no_grad():
+        for i in range(intervals):
+            y = oracle.rk4_step(f, y, ts[i], ts[i + 1] - ts[i])
+    dt = time.perf_counter() - t0
+    full = dt * (N_STEPS - 1) / intervals
+    return batch / full, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch, intervals = PER_GPU_BATCH, 1
+    for _ in range(args.warmup):
+        cpu_sample(batch, intervals, threads)
+    vals, secs = [], 0.0
+    for _ in range(args.steps):
+        v, s = cpu_sample(batch, intervals, threads)
+        vals.append(v)
+        secs += s
+    value = sum(vals) / len(vals)
+    sample = (f"per step: B={batch}, {intervals} of 49 RK4 intervals ({4 * intervals} of {NFE} evaluations) of the "
+              f"CPU oracle (PyTorch fp32, test-proven equal to the reference), scaled by 49/{intervals}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * PER_GPU_BATCH / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, PER_GPU_BATCH, "fp32"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from flocoder_b200 import sampling
+    from flocoder_b200.unet import Unet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    B = args.batch
+    torch.manual_seed(1234)
+    model = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=N_CLASSES, compute_dtype=args.dtype).to(dev).eval()
+    eng = model.engine(LATENT[1], LATENT[2])
+    gen = torch.Generator().manual_seed(5678 + rank)
+    x0_host = torch.randn(B, *LATENT, generator=gen).pin_memory()
+    x0_dev = x0_host.to(dev)
+    shape = (B, *LATENT)
+    gathered = torch.empty((world * B, *LATENT), device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        x1, _ = sampling.generate_latents_rk4(model, shape, n_steps=N_STEPS, source=x0_dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x1)
+        return x1
+
+    def step_e2e():
+        # the call a user makes, with HOST buffers: H2D of the noise, trajectory, D2H of the latents
+        x1, _ = sampling.generate_latents_rk4(model, shape, n_steps=N_STEPS, source=x0_host)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, x1)
+            return gathered.cpu() if rank == 0 else x1.cpu()
+        return x1.cpu()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            flush.zero_()
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = eng.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else {}
+    value = world * B * args.steps / (ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    # dominant kernel class: the tcgen05 implicit-GEMM convolution.  Per-launch durations measured live with CUDA
+    # events (one forward, op by op, best of 5); achieved = algorithmic conv FLOPs of those launches / their time.
+    info = eng.op_info()
+    ms_ops = eng.profile_ops(B, reps=5)
+    conv = [(i, fl) for i, (_, kind, fl, _) in enumerate(info) if kind == 1]
+    conv_ms = sum(ms_ops[i] for i, _ in conv)
+    conv_flop = sum(fl for _, fl in conv) * B
+    gn = [(i, by) for i, (_, kind, _, by) in enumerate(info) if kind == 2]
+    gn_ms = sum(ms_ops[i] for i, _ in gn)
+    gn_bytes = sum(by for _, by in gn) * B
+    fwd_ms = sum(ms_ops)
+    achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak = peaks["bf16_tflops"] if args.dtype == "bf16" else None
+    roofline = {
+        "bound": "tensor", "kernel": "k_conv_umma (tcgen05 implicit-GEMM conv, %d launches/forward)" % len(conv),
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": (achieved / peak) if peak else None, "traffic": None,
+        "peak_source": f"{peaks['source']} burst bf16 cuBLAS (kernel timed alone)",
+        "share_of_forward": conv_ms / fwd_ms if fwd_ms > 0 else None,
+        "end_to_end_tensor_frac_of_sustained": value / world * NFE * CONV_FLOP_PER_SAMPLE_FORWARD / 1e12 / peaks["bf16_tflops_sustained"],
+        "gn_pass": {"kernel": "k_gn (GroupNorm+FiLM+SiLU+residual, %d launches/forward)" % len(gn),
+                    "achieved_gbs": gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0, "peak_gbs": peaks["hbm_gbs"],
+                    "frac": (gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if gn_ms > 0 else None,
+                    "share_of_forward": gn_ms / fwd_ms if fwd_ms > 0 else None},
+        "forward_ms_sum_of_kernels": fwd_ms,
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v_cpu, s_cpu = cpu_sample(PER_GPU_BATCH, 2, threads)
+        cpu = {"value": v_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"B={PER_GPU_BATCH}, 2 of 49 RK4 intervals (8 of {NFE} evaluations) of the CPU oracle "
+                         f"(PyTorch fp32), {s_cpu:.1f} s measured, scaled by 49/2"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(world, B, args.dtype),
+        "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
+                   "samples": clk.get("samples", 0)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 4 * LATENT[0] * LATENT[1] * LATENT[2],
+                "d2h_bytes_per_step": (world if world > 1 else 1) * B * 4 * LATENT[0] * LATENT[1] * LATENT[2],
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

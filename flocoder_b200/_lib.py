@@ -28,6 +28,7 @@ EXPORTS = (
     "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
     "flo_integrate_nfe", "flo_unet_num_ops", "flo_unet_op_name", "flo_unet_launches_per_forward",
     "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma", "flo_describe_plan",
+    "flo_unet_op_info", "flo_unet_profile_ops",
 )
 
 
@@ -77,6 +78,8 @@ def lib() -> ctypes.CDLL:
                                            c_void_p]
     L.flo_selftest_umma.argtypes = [c_char_p, c_int, c_void_p]
     L.flo_describe_plan.argtypes = [POINTER(FloUnetCfg), c_int, c_char_p, c_int]
+    L.flo_unet_op_info.argtypes = [c_void_p, c_int, POINTER(c_int), POINTER(ctypes.c_double), POINTER(ctypes.c_double)]
+    L.flo_unet_profile_ops.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), c_void_p]
     _lib_handle = L
     return L
 
@@ -238,6 +241,24 @@ class Engine:
             check(self.L.flo_unet_op_name(self.handle, i, buf, 256))
             out.append(buf.value.decode())
         return out
+
+    def op_info(self):
+        """[(name, kind, algorithmic flops per sample, algorithmic bytes per sample)] per op."""
+        out = []
+        kind, fl, by = c_int(), ctypes.c_double(), ctypes.c_double()
+        for i, name in enumerate(self.op_names()):
+            check(self.L.flo_unet_op_info(self.handle, i, byref(kind), byref(fl), byref(by)))
+            out.append((name, kind.value, fl.value, by.value))
+        return out
+
+    def profile_ops(self, b: int, reps: int = 5):
+        """Best-of-`reps` CUDA-event duration (ms) of every kernel of one forward at batch b."""
+        n = self.L.flo_unet_num_ops(self.handle)
+        ms = (c_float * n)()
+        with torch.cuda.device(self.device):
+            check(self.L.flo_unet_profile_ops(self.handle, b, reps, ms, _stream_ptr(self.device)),
+                  "flo_unet_profile_ops")
+        return list(ms)
 
     def launches_per_forward(self, b: int) -> int:
         n = self.L.flo_unet_launches_per_forward(self.handle, b)
