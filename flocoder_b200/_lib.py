@@ -18,9 +18,9 @@ import torch
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "libflocoder_b200.so")
 
 FLO_OK, FLO_ERR_INVALID, FLO_ERR_UNSUPPORTED, FLO_ERR_CUDA, FLO_ERR_NOMEM = 0, -1, -2, -3, -4
-FLO_F32, FLO_BF16 = 0, 1
+FLO_F32, FLO_BF16, FLO_F16 = 0, 1, 2
 FLO_RK4, FLO_EULER_LEGACY, FLO_EULER_GRID = 0, 1, 2
-FLO_FLAG_NO_BUFFER_REUSE, FLO_FLAG_NO_GRAPH = 1, 2
+FLO_FLAG_NO_BUFFER_REUSE, FLO_FLAG_NO_GRAPH, FLO_FLAG_LAYERWISE = 1, 2, 4
 
 # every symbol include/flocoder_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them)
 EXPORTS = (
@@ -109,7 +109,7 @@ def make_cfg(dim, channels, dim_mults, groups, n_classes, height, width, compute
     for i, m in enumerate(dim_mults):
         cfg.mults[i] = int(m)
     cfg.groups, cfg.n_classes, cfg.height, cfg.width = groups, n_classes, height, width
-    cfg.compute_dtype = {"fp32": FLO_F32, "bf16": FLO_BF16}[compute_dtype]
+    cfg.compute_dtype = {"fp32": FLO_F32, "bf16": FLO_BF16, "fp16": FLO_F16}[compute_dtype]
     cfg.mask_cond, cfg.flags, cfg.device = 0, flags, device_index
     return cfg
 

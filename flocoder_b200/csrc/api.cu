@@ -1,6 +1,7 @@
 // C ABI of flocoder_b200 (include/flocoder_b200.h): parameter manifest, weight packing, the
 // static op program of the U-Net forward (unet.py:289-372), per-batch plans (workspace, TMA
 // tensor maps, CUDA graph) and the device-side integrators (sampling.py:36-122).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -56,7 +57,9 @@ EncodeTiledFn get_encode_tiled() {
 // ------------------------------------------------------------------------------------------------
 struct Spec {
     int dim, channels, n_levels, groups, n_classes, H, W;
-    bool bf16;
+    bool bf16;                 // 16-bit tensor-core operand path (bf16 or fp16)
+    bool f16;                  // operands are fp16 instead of bf16 (fused path only)
+    bool fused;                // fused stage kernels (default for the 16-bit paths)
     int flags, device;
     std::vector<int> dims;     // [dim, dim*m0, dim*m1, ...]   (unet.py:189)
     int time_dim;              // dim*8                         (unet.py:197)
@@ -80,8 +83,9 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
     }
     if (c->n_mults < 1 || c->n_mults > 8) { set_error("n_mults must be in 1..8"); return FLO_ERR_INVALID; }
     if (c->dim <= 0 || c->dim % 8) { set_error("dim must be a positive multiple of 8, got %d", c->dim); return FLO_ERR_UNSUPPORTED; }
-    if (c->compute_dtype != FLO_F32 && c->compute_dtype != FLO_BF16) { set_error("bad compute_dtype"); return FLO_ERR_INVALID; }
-    if (c->compute_dtype == FLO_BF16 && c->dim % 16) {
+    if (c->compute_dtype != FLO_F32 && c->compute_dtype != FLO_BF16 && c->compute_dtype != FLO_F16) { set_error("bad compute_dtype"); return FLO_ERR_INVALID; }
+    if (c->compute_dtype == FLO_F16 && (c->flags & FLO_FLAG_LAYERWISE)) { set_error("fp16 operands are only available on the fused path"); return FLO_ERR_UNSUPPORTED; }
+    if (c->compute_dtype != FLO_F32 && c->dim % 16) {
         set_error("the bf16 tcgen05 path needs dim %% 16 == 0 (K slices of 16 channels), got %d", c->dim);
         return FLO_ERR_UNSUPPORTED;
     }
@@ -89,7 +93,8 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
     if (c->dim > 64) { set_error("dim > 64 is not supported by the final-conv kernel"); return FLO_ERR_UNSUPPORTED; }
     if (c->n_classes < 0) { set_error("n_classes < 0"); return FLO_ERR_INVALID; }
     s.dim = c->dim; s.channels = c->channels; s.n_levels = c->n_mults; s.groups = c->groups;
-    s.n_classes = c->n_classes; s.H = c->height; s.W = c->width; s.bf16 = c->compute_dtype == FLO_BF16;
+    s.n_classes = c->n_classes; s.H = c->height; s.W = c->width; s.bf16 = c->compute_dtype != FLO_F32;
+    s.f16 = c->compute_dtype == FLO_F16; s.fused = s.bf16 && !(c->flags & FLO_FLAG_LAYERWISE);
     s.flags = c->flags; s.device = c->device;
     s.dims.clear();
     s.dims.push_back(c->dim);
@@ -214,6 +219,24 @@ struct Op {
     int qkv = -1, attn_out = -1, n = 0;
 };
 
+// ---- fused path (fused_plan.inc)
+struct FTensor {
+    std::string name;
+    int C, H, W;
+    size_t bytes_ps, off_ps;
+};
+struct FStage {
+    int kind;                 // 0 = k_chain, 1 = k_attn
+    std::string name;
+    ChainParams cp;
+    AttnFusedParams ap;
+    int nb;
+    int n_maps;
+    int map_tensor[CH_MAX_LOADS];   // tensors loaded by TMA (chain: padded box, attn: plain box)
+    int gt_tensor[CH_MAX_GT];       // chain: global tensor table -> tensor ids (-1 unused)
+    int x2_t, out_t, out_un_t, out_up_t;   // attn
+};
+
 struct Handle;
 struct Plan {
     int B = 0;
@@ -228,6 +251,11 @@ struct Plan {
     cudaGraphExec_t graph = nullptr;
     size_t total_bytes = 0;
     uint8_t* base = nullptr;
+    // fused path
+    uint8_t* farena = nullptr;
+    std::vector<CUtensorMap> fstage_maps;
+    std::vector<ChainParams> fchain;
+    std::vector<AttnFusedParams> fattn;
 };
 
 struct Handle {
@@ -255,6 +283,9 @@ struct Handle {
     cudaStream_t capture_stream = nullptr;
     int64_t launches = 0;
     Val r_val;
+    std::vector<FTensor> ftensors;
+    std::vector<FStage> fstages;
+    size_t farena_ps = 0;
 };
 
 // ---- program builder ---------------------------------------------------------------------------
@@ -324,7 +355,7 @@ struct Builder {
             if (n_tile) {
                 size_t off = (h.blob_bf16.size() + 63) & ~(size_t)63;     // 128-byte aligned streams
                 h.blob_bf16.resize(off);
-                pack_umma_weights(w.data(), cout, cin, ksize, perm ? perm->data() : nullptr, n_tile, h.blob_bf16);
+                pack_umma_weights(w.data(), cout, cin, ksize, perm ? perm->data() : nullptr, n_tile, s.f16, h.blob_bf16);
                 op.w_umma = off;
             }
         }
@@ -665,6 +696,13 @@ static int launch_op(Handle& h, Plan& pl, int i, cudaStream_t st) {
     return FLO_OK;
 }
 
+static int finalize_fused(Handle& h, Plan& pl);
+static int launch_fused_stage(Handle& h, Plan& pl, int i, cudaStream_t st);
+static int n_units(const Handle& h) { return h.spec.fused ? (int)h.fstages.size() : (int)h.ops.size(); }
+static int launch_unit(Handle& h, Plan& pl, int i, cudaStream_t st) {
+    return h.spec.fused ? launch_fused_stage(h, pl, i, st) : launch_op(h, pl, i, st);
+}
+
 static void destroy_plan(Plan& pl) {
     if (pl.graph) cudaGraphExecDestroy(pl.graph);
     if (pl.base) cudaFree(pl.base);
@@ -682,12 +720,14 @@ static int get_plan(Handle& h, int B, Plan** out) {
     const size_t state_bytes = al((size_t)B * s.channels * s.H * s.W * 4);
     const size_t film_bytes = al((size_t)B * h.film_dim * 4);
     const size_t cls_bytes = al((size_t)B * 8);
-    pl->arena_bytes = al(h.arena_ps * (size_t)B);
-    pl->total_bytes = pl->arena_bytes + 4 * state_bytes + film_bytes + cls_bytes + 256;
+    pl->arena_bytes = s.fused ? 256 : al(h.arena_ps * (size_t)B);     // layer-by-layer activations
+    const size_t farena_bytes = s.fused ? al(h.farena_ps * (size_t)B) : 0;   // stage-boundary tensors of the fused path
+    pl->total_bytes = pl->arena_bytes + farena_bytes + 4 * state_bytes + film_bytes + cls_bytes + 256;
     cudaError_t e = cudaMalloc((void**)&pl->base, pl->total_bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes for B=%d failed: %s", pl->total_bytes, B, cudaGetErrorString(e)); cudaGetLastError(); return FLO_ERR_NOMEM; }
     uint8_t* q = pl->base;
     pl->arena = q; q += pl->arena_bytes;
+    pl->farena = q; q += farena_bytes;
     pl->y = (float*)q; q += state_bytes;
     pl->acc = (float*)q; q += state_bytes;
     pl->xs = (float*)q; q += state_bytes;
@@ -696,13 +736,16 @@ static int get_plan(Handle& h, int B, Plan** out) {
     pl->cls = (int64_t*)q; q += cls_bytes;
     pl->ctrl = (Ctrl*)q;
     pl->buf_ptr.resize(h.bufs.size());
-    for (size_t i = 0; i < h.bufs.size(); ++i) pl->buf_ptr[i] = pl->arena + h.bufs[i].off_ps * (size_t)B;
+    for (size_t i = 0; i < h.bufs.size(); ++i) pl->buf_ptr[i] = s.fused ? nullptr : pl->arena + h.bufs[i].off_ps * (size_t)B;
     // halo / padding rows of the arena are never read as data, but keep everything finite
     CUDA_TRY(cudaMemset(pl->base, 0, pl->total_bytes));
 
     const int n_ops = (int)h.ops.size();
     pl->umma.resize(n_ops); pl->tmA0.resize(n_ops); pl->tmA1.resize(n_ops);
-    if (s.bf16) {
+    if (s.fused) {
+        int rc = finalize_fused(h, *pl);
+        if (rc) { destroy_plan(*pl); return rc; }
+    } else if (s.bf16) {
         for (int i = 0; i < n_ops; ++i) {
             const Op& op = h.ops[i];
             if (op.kind != OP_CONV) continue;
@@ -721,7 +764,7 @@ static int get_plan(Handle& h, int B, Plan** out) {
         cudaGraph_t g = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(h.capture_stream, cudaStreamCaptureModeThreadLocal));
         int rc = FLO_OK;
-        for (int i = 0; i < n_ops && rc == FLO_OK; ++i) rc = launch_op(h, *pl, i, h.capture_stream);
+        for (int i = 0; i < n_units(h) && rc == FLO_OK; ++i) rc = launch_unit(h, *pl, i, h.capture_stream);
         cudaError_t ce = cudaStreamEndCapture(h.capture_stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); destroy_plan(*pl); return rc; }
         if (ce != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(ce)); destroy_plan(*pl); return FLO_ERR_CUDA; }
@@ -738,12 +781,12 @@ static int run_forward(Handle& h, Plan& pl, cudaStream_t st) {
     if (pl.graph) {
         CUDA_TRY(cudaGraphLaunch(pl.graph, st));
     } else {
-        for (int i = 0; i < (int)h.ops.size(); ++i) {
-            int rc = launch_op(h, pl, i, st);
+        for (int i = 0; i < n_units(h); ++i) {
+            int rc = launch_unit(h, pl, i, st);
             if (rc) return rc;
         }
     }
-    h.launches += (int64_t)h.ops.size();
+    h.launches += (int64_t)n_units(h);
     return FLO_OK;
 }
 
@@ -783,6 +826,8 @@ static int ensure_host_staging(Handle& h, int n) {
     h.h_cap = cap;
     return FLO_OK;
 }
+
+#include "fused_plan.inc"
 
 }  // namespace flo
 
@@ -869,6 +914,11 @@ int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const
     rc = b.build();
     if (rc) return rc;
     allocate_arena(*h);
+    if (h->spec.fused) {
+        FusedBuilder fb(*h, h->ftensors, h->fstages);
+        rc = fb.build();
+        if (rc) return rc;
+    }
     h->host.clear();
     CUDA_TRY(cudaMalloc((void**)&h->d_f32, h->blob_f32.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(h->d_f32, h->blob_f32.data(), h->blob_f32.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -878,6 +928,7 @@ int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const
         CUDA_TRY(conv_umma_configure());
     }
     CUDA_TRY(simt_configure());
+    if (h->spec.fused) CUDA_TRY(fused_configure());
     CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     *out = reinterpret_cast<flo_unet_t*>(h.release());
     return FLO_OK;
@@ -1129,17 +1180,52 @@ int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap) {
                  bf.W, bf.bf16 ? "bf16" : "f32 ", bf.bytes_ps, bf.def, bf.last, bf.off_ps);
         t += line;
     }
+    if (h.spec.fused) {
+        FusedBuilder fb(h, h.ftensors, h.fstages);
+        rc = fb.build();
+        if (rc) return rc;
+        snprintf(line, sizeof(line), "fused: %d stages, %d boundary tensors, %zu bytes/sample\n", (int)h.fstages.size(),
+                 (int)h.ftensors.size(), h.farena_ps);
+        t += line;
+        for (size_t i = 0; i < h.fstages.size(); ++i) {
+            const FStage& st = h.fstages[i];
+            if (st.kind == 0) {
+                const ChainParams& c = st.cp;
+                snprintf(line, sizeof(line), "stage %2zu chain %-12s %dx%d nb=%d mt=%d strips=%d steps=%d loads=%d smem=%d (slots %d, ring %dx%d) tmem=%d ctas=%d\n",
+                         i, st.name.c_str(), c.H, c.W, c.nb, c.n_mtiles, c.strips, c.n_steps, c.n_loads, c.smem_bytes, c.ring_off,
+                         c.n_ring, c.ring_slot_bytes, c.tmem_cols, (B + c.nb - 1) / c.nb);
+                t += line;
+                for (int k = 0; k < c.n_steps; ++k) {
+                    const ChainStep& cs = c.st[k];
+                    snprintf(line, sizeof(line), "      step %d: conv=%d k=%d cin=%d+%d n=%d chunks=%dx%d res=%d(%dx%d) epi=%d C=%d G=%d film=%d resmode=%d out_slot=%d out_g=%d un=%d up=%d pn=%d final=%d a0=%d a1=%d\n",
+                             k, cs.has_conv, cs.ksize, cs.a0_ncb * 8, cs.a1_ncb * 8, cs.n, cs.n_chunks, cs.slices_per_chunk, cs.has_res,
+                             cs.res_chunks, cs.res_slices_per_chunk, cs.epi, cs.C, cs.groups, cs.film_off, cs.res_mode, cs.out_slot_off,
+                             cs.out_g, cs.out_un_g, cs.out_up_g, cs.pn_g, cs.final, cs.a0_off, cs.a1_off);
+                    t += line;
+                }
+            } else {
+                const AttnFusedParams& a = st.ap;
+                snprintf(line, sizeof(line), "stage %2zu attn  %-12s %dx%d C=%d nb=%d n=%d n_pad=%d mt=%d full=%d smem=%d plane=%d tmem=%d cols(k=%d v=%d ctx=%d q=%d out=%d proj=%d) ctas=%d\n",
+                         i, st.name.c_str(), a.H, a.W, a.C, a.nb, a.n, a.n_pad, a.n_mtiles, a.full, a.smem_bytes, a.plane_bytes, a.tmem_cols,
+                         a.col_k, a.col_v, a.col_ctx, a.col_q, a.col_out, a.col_proj, (B + a.nb - 1) / a.nb);
+                t += line;
+            }
+        }
+        for (size_t i = 0; i < h.ftensors.size(); ++i) {
+            snprintf(line, sizeof(line), "ftensor %2zu %-24s C=%d %dx%d off_ps=%zu\n", i, h.ftensors[i].name.c_str(), h.ftensors[i].C,
+                     h.ftensors[i].H, h.ftensors[i].W, h.ftensors[i].off_ps);
+            t += line;
+        }
+    }
     if (out && cap > 0) snprintf(out, cap, "%s", t.c_str());
     return (int)t.size();
 }
 
-int flo_unet_op_info(flo_unet_t* hh, int index, int* kind, double* flops_per_sample, double* bytes_per_sample) {
-    Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h || index < 0 || index >= (int)h->ops.size()) { set_error("op index out of range"); return FLO_ERR_INVALID; }
-    const Op& op = h->ops[index];
-    const Spec& s = h->spec;
+// algorithmic flops / bytes of one layer-by-layer op (per sample)
+static void op_cost(const Handle& h, const Op& op, double& fl, double& by) {
+    const Spec& s = h.spec;
     const double ob = s.bf16 ? 2.0 : 4.0;      // operand bytes
-    double fl = 0, by = 0;
+    fl = 0; by = 0;
     const double hw = (double)op.H * op.W;
     switch (op.kind) {
         case OP_INIT:
@@ -1169,7 +1255,47 @@ int flo_unet_op_info(flo_unet_t* hh, int index, int* kind, double* flops_per_sam
             by = hw * (s.dim * 4.0 + s.channels * 16.0);
             break;
     }
-    if (kind) *kind = op.kind;
+}
+
+// Launch units of the active path: layer-by-layer ops, or fused stages.
+// kind: 0 init conv, 1 conv, 2 GroupNorm pass, 3 linear attention core, 4 mid attention core, 5 final conv + integrator
+//       epilogue, 6 fused conv-chain stage (k_chain), 7 fused attention stage (k_attn).
+// flops = algorithmic CONV flops inside the unit (2*M*N*K); bytes = algorithmic global-memory bytes.
+int flo_unet_op_info(flo_unet_t* hh, int index, int* kind, double* flops_per_sample, double* bytes_per_sample) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || index < 0 || index >= n_units(*h)) { set_error("op index out of range"); return FLO_ERR_INVALID; }
+    double fl = 0, by = 0;
+    int k = 0;
+    if (!h->spec.fused) {
+        const Op& op = h->ops[index];
+        op_cost(*h, op, fl, by);
+        k = op.kind;
+    } else {
+        const FStage& st = h->fstages[index];
+        auto tbytes = [&](int t) { return t >= 0 ? (double)h->ftensors[t].C * h->ftensors[t].H * h->ftensors[t].W * 2.0 : 0.0; };
+        if (st.kind == 0) {
+            k = 6;
+            const ChainParams& c = st.cp;
+            const double hw = (double)c.H * c.W;
+            for (int i = 0; i < c.n_steps; ++i) {
+                const ChainStep& cs = c.st[i];
+                if (cs.epi == CE_INIT) fl += 2.0 * hw * h->spec.dim * h->spec.channels;
+                if (!cs.has_conv) continue;
+                const double cin = (cs.a0_ncb + cs.a1_ncb) * 8.0;
+                fl += 2.0 * hw * cs.n * cin * cs.ksize * cs.ksize;
+                if (cs.has_res) fl += 2.0 * hw * cs.n * cin;
+                if (cs.final) fl += 2.0 * hw * h->spec.dim * h->spec.channels;
+            }
+            for (int m = 0; m < st.n_maps; ++m) by += tbytes(st.map_tensor[m]);
+            for (int g = 0; g < CH_MAX_GT; ++g) by += tbytes(st.gt_tensor[g]);
+        } else {
+            k = 7;
+            const AttnFusedParams& a = st.ap;
+            fl = 2.0 * a.n * a.C * 384.0 + 2.0 * a.n * 128.0 * a.C;          // to_qkv + to_out 1x1 convs
+            by = tbytes(st.map_tensor[0]) + tbytes(st.x2_t) + tbytes(st.out_t) + tbytes(st.out_un_t) + tbytes(st.out_up_t);
+        }
+    }
+    if (kind) *kind = k;
     if (flops_per_sample) *flops_per_sample = fl;
     if (bytes_per_sample) *bytes_per_sample = by;
     return FLO_OK;
@@ -1183,8 +1309,7 @@ int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void
     Plan* pl = nullptr;
     int rc = get_plan(*h, B, &pl);
     if (rc) return rc;
-    const Spec& s = h->spec;
-    const int n_ops = (int)h->ops.size();
+    const int n_ops = n_units(*h);
     rc = ensure_stage_capacity(*h, 1);
     if (rc) return rc;
     // a plain forward on the current contents of the state buffers, FiLM rows for t = 500
@@ -1207,7 +1332,7 @@ int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void
         CUDA_TRY(launch_setup_ctrl(pl->ctrl, c, h->d_stages, &s0, st));
         for (int i = 0; i < n_ops; ++i) {
             CUDA_TRY(cudaEventRecord(ev[i], st));
-            rc = launch_op(*h, *pl, i, st);
+            rc = launch_unit(*h, *pl, i, st);
             if (rc) return rc;
         }
         CUDA_TRY(cudaEventRecord(ev[n_ops], st));
@@ -1222,25 +1347,24 @@ int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void
     for (int i = 0; i < n_ops; ++i) ms_per_op[i] = best[i];
     for (auto& e : ev) cudaEventDestroy(e);
     cudaFree(d_t);
-    (void)s;
     h->launches += (int64_t)(reps + 1) * (n_ops + 1) + 1;
     return FLO_OK;
 }
 
 int flo_unet_num_ops(flo_unet_t* hh) {
     Handle* h = reinterpret_cast<Handle*>(hh);
-    return h ? (int)h->ops.size() : 0;
+    return h ? n_units(*h) : 0;
 }
 int flo_unet_op_name(flo_unet_t* hh, int index, char* name, int name_cap) {
     Handle* h = reinterpret_cast<Handle*>(hh);
-    if (!h || index < 0 || index >= (int)h->ops.size()) { set_error("op index out of range"); return FLO_ERR_INVALID; }
-    snprintf(name, name_cap, "%s", h->ops[index].name.c_str());
+    if (!h || index < 0 || index >= n_units(*h)) { set_error("op index out of range"); return FLO_ERR_INVALID; }
+    snprintf(name, name_cap, "%s", h->spec.fused ? h->fstages[index].name.c_str() : h->ops[index].name.c_str());
     return FLO_OK;
 }
 int flo_unet_launches_per_forward(flo_unet_t* hh, int B) {
     Handle* h = reinterpret_cast<Handle*>(hh);
     (void)B;
-    return h ? (int)h->ops.size() : 0;
+    return h ? n_units(*h) : 0;
 }
 int64_t flo_unet_launch_count(flo_unet_t* hh) {
     Handle* h = reinterpret_cast<Handle*>(hh);
@@ -1256,32 +1380,49 @@ int flo_unet_read_activation(flo_unet_t* hh, const char* name, int B, float* out
     auto it = h->plans.find(B);
     if (it == h->plans.end()) { set_error("no forward has run at B=%d", B); return FLO_ERR_INVALID; }
     Plan& pl = *it->second;
-    int id = -1;
     const std::string n(name);
-    for (const char* suffix : {"", ":m", ":o"}) {
-        for (size_t i = 0; i < h->bufs.size(); ++i)
-            if (h->bufs[i].name == n + suffix) { id = (int)i; break; }
-        if (id >= 0) break;
+    int C = 0, H = 0, W = 0, elem = 0;      // elem: 0 fp32, 1 bf16, 2 fp16
+    const void* src_ptr = nullptr;
+    if (h->spec.fused) {
+        for (size_t i = 0; i < h->ftensors.size(); ++i)
+            if (h->ftensors[i].name == n) {
+                const FTensor& t = h->ftensors[i];
+                C = t.C; H = t.H; W = t.W; elem = h->spec.f16 ? 2 : 1;
+                src_ptr = pl.farena + t.off_ps * (size_t)B;
+                break;
+            }
+    } else {
+        int id = -1;
+        for (const char* suffix : {"", ":m", ":o"}) {
+            for (size_t i = 0; i < h->bufs.size(); ++i)
+                if (h->bufs[i].name == n + suffix) { id = (int)i; break; }
+            if (id >= 0) break;
+        }
+        if (id >= 0) {
+            const Buf& b = h->bufs[id];
+            C = b.C; H = b.H; W = b.W; elem = b.bf16 ? 1 : 0;
+            src_ptr = pl.buf_ptr[id];
+        }
     }
-    if (id < 0) { set_error("no activation named '%s'", name); return FLO_ERR_INVALID; }
-    const Buf& b = h->bufs[id];
-    const int64_t numel = (int64_t)B * b.C * b.H * b.W;
+    if (!src_ptr) { set_error("no activation named '%s'", name); return FLO_ERR_INVALID; }
+    const int64_t numel = (int64_t)B * C * H * W;
     if (numel > cap) { set_error("output buffer too small"); return FLO_ERR_INVALID; }
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    std::vector<uint8_t> raw((size_t)numel * (b.bf16 ? 2 : 4));
-    CUDA_TRY(cudaMemcpy(raw.data(), pl.buf_ptr[id], raw.size(), cudaMemcpyDeviceToHost));
-    const int HW = b.H * b.W;
-    for (int cb = 0; cb < b.C / 8; ++cb)
+    std::vector<uint8_t> raw((size_t)numel * (elem ? 2 : 4));
+    CUDA_TRY(cudaMemcpy(raw.data(), src_ptr, raw.size(), cudaMemcpyDeviceToHost));
+    const int HW = H * W;
+    for (int cb = 0; cb < C / 8; ++cb)
         for (int bb = 0; bb < B; ++bb)
             for (int px = 0; px < HW; ++px)
                 for (int j = 0; j < 8; ++j) {
                     const size_t src = (((size_t)cb * B + bb) * HW + px) * 8 + j;
                     float v;
-                    if (b.bf16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(raw.data())[src]);
+                    if (elem == 1) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(raw.data())[src]);
+                    else if (elem == 2) v = __half2float(reinterpret_cast<const __half*>(raw.data())[src]);
                     else v = reinterpret_cast<const float*>(raw.data())[src];
-                    out[((size_t)bb * b.C + cb * 8 + j) * HW + px] = v;
+                    out[((size_t)bb * C + cb * 8 + j) * HW + px] = v;
                 }
-    shape[0] = B; shape[1] = b.C; shape[2] = b.H; shape[3] = b.W;
+    shape[0] = B; shape[1] = C; shape[2] = H; shape[3] = W;
     return FLO_OK;
 }
 

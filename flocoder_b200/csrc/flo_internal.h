@@ -181,8 +181,8 @@ int make_tmap(CUtensorMap* tm, void* base, int ncb, int B, int H, int W, int pad
 
 // host-side packing of OIHW fp32 weights (with input-channel permutation `perm`, or null) into the
 // bf16 stream the tcgen05 kernel consumes; returns elements written.
-size_t pack_umma_weights(const float* w_oihw, int cout, int cin, int ksize, const int* perm, int n_tile,
-                         std::vector<__nv_bfloat16>& out);
+size_t pack_umma_weights(const float* w_oihw, int cout, int cin, int ksize, const int* perm, int n_tile, bool f16,
+                         std::vector<__nv_bfloat16>& out);   // f16: the 16-bit container holds IEEE half bits
 
 // TMA tensor-map encoder obtained through the runtime (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -191,5 +191,80 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_tiled();
 
 void set_error(const char* fmt, ...);
+
+// ---------------------------------------------------------------------------------------------
+// fused stage kernels (fused.cu): a CTA owns `nb` whole samples and runs a chain of convolutions with
+// GroupNorm/FiLM/SiLU/residual epilogues entirely on-chip (activations in shared memory, accumulators
+// in TMEM, weights streamed by bulk TMA); see DESIGN.md "Fused stage kernels".
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_WSTAGES = 4;          // depth of the shared-memory weight ring
+constexpr int CH_MAX_STEPS = 8;
+constexpr int CH_MAX_LOADS = 4;
+constexpr int CH_MAX_GT = 10;
+enum ChainEpi : int { CE_GN = 1, CE_BIAS = 2, CE_INIT = 3 };
+
+struct ChainStep {
+    // ---- MMA part (has_conv == 0: none)
+    int has_conv;
+    int a0_off, a0_ncb, a1_off, a1_ncb;     // A operand slots: byte offset in smem, channel blocks (a1_ncb = 0: none)
+    int ksize, n;                           // kernel size, output channels
+    int acc_col;                            // TMEM column of tile 0 (tile t at acc_col + t*n)
+    unsigned w_off; int n_chunks, slices_per_chunk;            // weight stream (16-bit elements into wblob)
+    int has_res, res_col; unsigned wres_off; int res_chunks, res_slices_per_chunk;   // 1x1 res_conv on the same A
+    // ---- epilogue part
+    int epi;                                // ChainEpi
+    int C, groups, silu, film_off;          // film_off < 0: no FiLM
+    int bias_off, gamma_off, beta_off;      // offsets into fblob (< 0: none)
+    int res_mode;                           // 0 none, 1 TMEM (res_col) + res_bias_off, 2 shared-memory slot (16-bit)
+    int res_slot_off, res_bias_off;
+    int out_slot_off;                       // < 0: none
+    int out_g, out_un_g, out_up_g;          // global tensor table indices (< 0: none)
+    int pn_g, pn_gamma_off, pn_beta_off;    // fused PreNorm (GroupNorm(1,C) of the result) -> global tensor
+    int final;                              // 1: final 1x1 conv + integrator stage update instead of tensor outputs
+};
+
+struct ChainParams {
+    int n_steps;
+    ChainStep st[CH_MAX_STEPS];
+    int B, H, W, nb, n_mtiles, strips, plane_px;
+    int n_loads, load_off[CH_MAX_LOADS], load_ncb[CH_MAX_LOADS];
+    int zero_off, zero_bytes;               // shared-memory range to clear at start (epilogue-written slots)
+    int ring_off, ring_slot_bytes, n_ring;
+    int stats_off, bar_off, smem_bytes, tmem_cols;
+    int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16
+    int film_dim;
+    int cin0, dim, channels;                // init conv / final conv shapes
+    int init_w_off, init_b_off, final_w_off, final_b_off;
+    const uint16_t* wblob;
+    const float* fblob;
+    void* gt[CH_MAX_GT];
+    Ctrl* ctrl;
+};
+
+// linear-attention block  Residual(PreNorm(dim, LinearAttention(dim)))  (unet.py:33-39,125-161) and the
+// mid-block full attention (unet.py:99-122), one kernel, `nb` samples per CTA
+struct AttnFusedParams {
+    int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
+                                            // n_mtiles = 128-row tiles of the dense rows (s*n + p)
+    int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)
+    int fmt;
+    unsigned wq_off, wk_off, wv_off, wo_off; // 16-bit weight streams in wblob (N = 128,128,128,C)
+    int qkv_chunks, qkv_S, o_chunks, o_S;   // ring chunking of those streams
+    int bo_off, gamma_off, beta_off;        // to_out bias, to_out.1 GroupNorm affine (fblob)
+    int xh_off, p_off, v_off, ct_off, kmax_off, stats_off;   // shared-memory regions
+    int plane_bytes;                        // plane stride of the P/Q and V/O slots
+    int ring_off, ring_slot_bytes, n_ring, bar_off, smem_bytes, tmem_cols;
+    int zero_off, zero_bytes;
+    int col_k, col_v, col_ctx, col_q, col_out, col_proj;     // TMEM column plan
+    const uint16_t* wblob;
+    const float* fblob;
+    const void* x2;                         // residual input (16-bit blocked, global)
+    void* out; void* out_un; void* out_up;  // outputs (16-bit blocked); un/up may be null
+};
+
+cudaError_t fused_configure();
+cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s);
+cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s);
+
 
 }  // namespace flo

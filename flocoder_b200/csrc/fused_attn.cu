@@ -1,0 +1,465 @@
+// k_attn: one attention block of the U-Net in one kernel (sm_100a).
+//
+// Linear attention  Residual(PreNorm(dim, LinearAttention(dim)))  (unet.py:33-39,125-161):
+//   input  xhat = GroupNorm(1,C)(x2)   (written by the preceding k_chain epilogue) and x2 (residual)
+//   K,V = to_qkv 1x1 convs (tcgen05, N=128 each)            -> TMEM
+//   P = exp(k - max_n k) (column softmax numerator, per sample and channel), V  -> 16-bit shared memory
+//   ctx[(h,d)][(h,e)] = sum_n P[n][(h,d)] V[n][(h,e)]  : ONE tcgen05.mma chain per sample with BOTH operands
+//        MN-major -- the blocked [C/8][pixel][8] layout is the canonical MN-major operand with K = pixels, so no
+//        transposes; a column of ones appended to V yields the softmax denominators sum_n P for free
+//   Q = softmax_d(q) (per pixel and head, thread-local)      -> shared memory (reuses P)
+//   out[n][(h,e)] = sum_d Q[n][(h,d)] * ctx[d][e]/sum * 32^-0.5  : tcgen05.mma per (sample, head), N=32
+//   y = to_out conv (tcgen05) + bias -> GroupNorm(1,C) -> + x2   -> global (normal / unshuffled / upsampled)
+// Mid-block attention (unet.py:99-122), n = H*W <= 16: K,V,Q convs on tcgen05, softmax(QK^T)V per row on CUDA
+// cores out of shared memory, to_out conv on tcgen05, + bias + x2.
+//
+// Rows: "dense" row = s*n + p for the convolutions and the final epilogue; the P/V/Q operand slots use
+// s*n_pad + p (n_pad = max(n,16)) so every sample's pixel range is a whole number of K=16 slices.
+#include "flo_internal.h"
+#include "fused_common.cuh"
+
+namespace flo {
+
+struct RingA { int cc; };
+
+__device__ __forceinline__ void attn_stream(const AttnFusedParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
+                                            RingA& rs, const uint16_t* w, int n_chunks, int chunk_bytes) {
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int slot = rs.cc % p.n_ring;
+        if (rs.cc >= p.n_ring) mbar_wait(bar_empty + 8 * slot, ((rs.cc / p.n_ring) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * slot, (uint32_t)chunk_bytes);
+        bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes,
+                     reinterpret_cast<const uint8_t*>(w) + (size_t)ci * chunk_bytes, (uint32_t)chunk_bytes, bar_full + 8 * slot);
+        ++rs.cc;
+    }
+}
+// 1x1 conv over a K-major operand slot: A rows = tile t rows [128t, 128t+128), planes at `a_plane` stride
+__device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t smem_base, uint32_t tmem_base, uint32_t bar_full,
+                                          uint32_t bar_empty, RingA& rs, uint32_t a_off, uint32_t a_plane, int n, int col,
+                                          int n_chunks, int S) {
+    const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
+    for (int ci = 0; ci < n_chunks; ++ci) {
+        const int slot = rs.cc % p.n_ring;
+        mbar_wait(bar_full + 8 * slot, (rs.cc / p.n_ring) & 1);
+        tc_fence_after();
+        const uint32_t bstage = smem_base + p.ring_off + slot * p.ring_slot_bytes;
+        for (int s = 0; s < S; ++s) {
+            const int ks = ci * S + s;
+            const uint64_t bdesc = make_smem_desc(bstage + (uint32_t)s * (uint32_t)n * 32u, (uint32_t)n * 16u, 128u);
+            for (int t = 0; t < p.n_mtiles; ++t) {
+                const uint32_t a_addr = smem_base + a_off + (uint32_t)(2 * ks) * a_plane + (uint32_t)(t * 128) * 16u;
+                umma_bf16(tmem_base + (uint32_t)(col + t * n), make_smem_desc(a_addr, a_plane, 128u), bdesc, idesc,
+                          ks > 0 ? 1u : 0u);
+            }
+        }
+        umma_commit(bar_empty + 8 * slot);
+        ++rs.cc;
+    }
+}
+
+__device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, int px, int c16, const float* v) {
+    const int ncb = p.C >> 3;
+    const int h = px / p.W, w = px - h * p.W;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        const int cb = (c16 >> 3) + hb;
+        const uint4 u = pack8(v + hb * 8, p.fmt);
+        if (p.out) reinterpret_cast<uint4*>(p.out)[(size_t)(cb * p.B + b) * p.n + px] = u;
+        if (p.out_un) {
+            const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
+            const int q = (h >> 1) * (p.W >> 1) + (w >> 1);
+            reinterpret_cast<uint4*>(p.out_un)[(size_t)(plane * p.B + b) * (p.n >> 2) + q] = u;
+        }
+        if (p.out_up) {
+            const int W2 = p.W * 2;
+            uint4* dst = reinterpret_cast<uint4*>(p.out_up) + (size_t)(cb * p.B + b) * (p.n * 4);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) dst[(2 * h + (d >> 1)) * W2 + 2 * w + (d & 1)] = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
+                                                        const __grid_constant__ AttnFusedParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_base + p.bar_off;
+    const uint32_t bar_empty = bar_full + 8 * MAX_WSTAGES;
+    const uint32_t bar_load = bar_empty + 8 * MAX_WSTAGES;
+    const uint32_t bar_mma = bar_load + 8;
+    const uint32_t bar_epi = bar_mma + 8;
+    const uint32_t tmem_slot = bar_epi + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
+    const int b0 = blockIdx.x * p.nb;
+    const int n = p.n, n_pad = p.n_pad, C = p.C;
+    const uint32_t plane = (uint32_t)p.plane_bytes;
+    const uint32_t xh_plane = (uint32_t)(p.nb * n) * 16u;
+    const int mtS = (n + 127) / 128;                    // 128-row tiles per sample in the out contraction
+
+    if (warp == 4 && lane == 0) {
+        for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_epi, EPI_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    for (int i = tid * 16; i < p.zero_bytes; i += FUSED_THREADS * 16)
+        *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * xh_plane);
+            tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
+            RingA rs{0};
+            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wk_off, p.qkv_chunks, qkv_bytes);
+            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wv_off, p.qkv_chunks, qkv_bytes);
+            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wq_off, p.qkv_chunks, qkv_bytes);
+            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wo_off, p.o_chunks, o_bytes);
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            RingA rs{0};
+            mbar_wait(bar_load, 0);
+            tc_fence_after();
+            // ---- phase 0: K and V convolutions (and Q for the mid attention)
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_k, p.qkv_chunks, p.qkv_S);
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_v, p.qkv_chunks, p.qkv_S);
+            if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+            umma_commit(bar_mma);
+            int ph = 0;
+            if (!p.full) {
+                // ---- phase 1: context per sample (both operands MN-major, K = pixels), then the Q convolution
+                mbar_wait(bar_epi, ph & 1); ++ph;
+                tc_fence_after();
+                const uint32_t idesc_ctx = make_idesc16(128, 144, p.fmt, 1, 1);
+                for (int s = 0; s < p.nb; ++s)
+                    for (int ks = 0; ks < n_pad / 16; ++ks) {
+                        const uint32_t roff = (uint32_t)(s * n_pad + ks * 16) * 16u;
+                        umma_bf16(tmem_base + (uint32_t)(p.col_ctx + s * 144), make_smem_desc(smem_base + p.p_off + roff, 128u, plane),
+                                  make_smem_desc(smem_base + p.v_off + roff, 128u, plane), idesc_ctx, ks > 0 ? 1u : 0u);
+                    }
+                attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+                umma_commit(bar_mma);
+                // ---- phase 2: out[n][(h,e)] per (sample, tile, head)
+                mbar_wait(bar_epi, ph & 1); ++ph;
+                tc_fence_after();
+                const uint32_t idesc_out = make_idesc16(128, 32, p.fmt, 0, 0);
+                for (int s = 0; s < p.nb; ++s)
+                    for (int t = 0; t < mtS; ++t)
+                        for (int h = 0; h < 4; ++h)
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t a_addr = smem_base + p.p_off + (uint32_t)(4 * h + 2 * k) * plane +
+                                                        (uint32_t)(s * n_pad + t * 128) * 16u;
+                                const uint32_t b_addr = smem_base + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)k * 1024u;
+                                umma_bf16(tmem_base + (uint32_t)(p.col_out + (s * mtS + t) * 128 + h * 32),
+                                          make_smem_desc(a_addr, plane, 128u), make_smem_desc(b_addr, 512u, 128u), idesc_out,
+                                          k > 0 ? 1u : 0u);
+                            }
+                umma_commit(bar_mma);
+            }
+            // ---- last phase: to_out convolution over the O slot
+            mbar_wait(bar_epi, ph & 1); ++ph;
+            tc_fence_after();
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, p.col_proj,
+                      p.o_chunks, p.o_S);
+            umma_commit(bar_mma);
+        }
+    } else {
+        const int r = warp * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float* kmax = reinterpret_cast<float*>(smem + p.kmax_off);          // [nb][128]
+        float* kpart = kmax + p.nb * 128;                                   // [n_mtiles*4][128]
+        float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);    // [n_mtiles*128]
+        float2* partial = rowstat + p.n_mtiles * 128;
+        float2* stat = partial + EPI_THREADS;
+        int ph = 0;
+        mbar_wait(bar_load, 0);
+        mbar_wait(bar_mma, ph & 1); ++ph;
+        tc_fence_after();
+        if (!p.full) {
+            // ================= EPI 0: column softmax numerators of K, V to shared memory =================
+            const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
+            for (int c16 = 0; c16 < 128; c16 += 16) {
+                for (int t = 0; t < p.n_mtiles; ++t) {
+                    const int rd = t * 128 + r, s = rd / n;
+                    const bool valid = s < p.nb && b0 + s < p.B;
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_k + t * 128 + c16), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float m = valid ? v[j] : -INFINITY;
+                        for (int o = seg >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        v[j] = m;
+                    }
+                    if (n >= 32) {
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) kpart[(t * 4 + warp) * 128 + c16 + j] = v[j];
+                        }
+                    } else if ((lane & (seg - 1)) == 0 && s < p.nb) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) kmax[s * 128 + c16 + j] = v[j];
+                    }
+                }
+            }
+            epi_sync();
+            if (n >= 32) {
+                const int wps = n / 32;                      // warp-rows per sample
+                for (int idx = r; idx < p.nb * 128; idx += EPI_THREADS) {
+                    const int s = idx >> 7, c = idx & 127;
+                    float m = -INFINITY;
+                    for (int w = 0; w < wps; ++w) m = fmaxf(m, kpart[(s * wps + w) * 128 + c]);
+                    kmax[idx] = m;
+                }
+                epi_sync();
+            }
+            for (int t = 0; t < p.n_mtiles; ++t) {
+                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const bool valid = s < p.nb && b0 + s < p.B;
+                const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
+                for (int c16 = 0; c16 < 128; c16 += 16) {
+                    float kv[16], vv[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_k + t * 128 + c16), kv);
+                    tmem_ld16(tlane + (uint32_t)(p.col_v + t * 128 + c16), vv);
+                    if (!valid) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) kv[j] = __expf(kv[j] - kmax[s * 128 + c16 + j]);
+                    uint8_t* pd = smem + p.p_off + (uint32_t)(c16 >> 3) * plane + row_off;
+                    uint8_t* vd = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
+                    *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
+                    *reinterpret_cast<uint4*>(pd + plane) = pack8(kv + 8, p.fmt);
+                    *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
+                    *reinterpret_cast<uint4*>(vd + plane) = pack8(vv + 8, p.fmt);
+                }
+                if (valid) {
+                    const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+                    *reinterpret_cast<uint4*>(smem + p.v_off + 16u * plane + row_off) = pack8(ones, p.fmt);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+            // ================= EPI 1: context normalisation -> B operand; softmax_d(q) -> A operand =================
+            mbar_wait(bar_mma, ph & 1); ++ph;
+            tc_fence_after();
+            {
+                const int h = warp, d = lane;                // TMEM row r = (h, d)
+                for (int s = 0; s < p.nb; ++s) {
+                    float c0[16], c1[16], sm[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32), c0);
+                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32 + 16), c1);
+                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + 128), sm);
+                    const float inv = 0.17677669529663687f / sm[0];      // 32^-0.5 / sum_n exp(k - max)
+                    uint8_t* base = smem + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float val = (e < 16 ? c0[e] : c1[e - 16]) * inv;
+                        const uint32_t u = pack2(val, 0.f, p.fmt);
+                        *reinterpret_cast<uint16_t*>(base + (uint32_t)(e >> 3) * 128u + (uint32_t)(e & 7) * 16u) = (uint16_t)(u & 0xFFFFu);
+                    }
+                }
+            }
+            for (int t = 0; t < p.n_mtiles; ++t) {
+                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const bool valid = s < p.nb && b0 + s < p.B;
+                const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
+                for (int h = 0; h < 4; ++h) {
+                    float q[32];
+                    tmem_ld16(tlane + (uint32_t)(p.col_q + t * 128 + h * 32), q);
+                    tmem_ld16(tlane + (uint32_t)(p.col_q + t * 128 + h * 32 + 16), q + 16);
+                    if (!valid) continue;
+                    float m = q[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, q[j]);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { q[j] = __expf(q[j] - m); sum += q[j]; }
+                    const float inv = 1.0f / sum;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) q[j] *= inv;
+                    uint8_t* qd = smem + p.p_off + (uint32_t)(4 * h) * plane + row_off;
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, p.fmt);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+            // ================= EPI 2: attention output -> O slot (dense rows), reuses the V slot =================
+            mbar_wait(bar_mma, ph & 1); ++ph;
+            tc_fence_after();
+            for (int s = 0; s < p.nb; ++s)
+                for (int t = 0; t < mtS; ++t) {
+                    const int px = t * 128 + r;
+                    const bool valid = px < n && b0 + s < p.B;
+                    const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
+                    for (int c16 = 0; c16 < 128; c16 += 16) {
+                        float v[16];
+                        tmem_ld16(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c16), v);
+                        if (!valid) continue;
+                        uint8_t* od = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
+                        *reinterpret_cast<uint4*>(od) = pack8(v, p.fmt);
+                        *reinterpret_cast<uint4*>(od + plane) = pack8(v + 8, p.fmt);
+                    }
+                }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+        } else {
+            // ================= mid attention: softmax(q k^T) v per row on CUDA cores =================
+            // K rows -> p_off region [row][128], V rows -> v_off region [row][128] (16-bit)
+            const int rd = r, s = rd / n, i = rd - s * n;
+            const bool valid = s < p.nb && b0 + s < p.B;
+            for (int c16 = 0; c16 < 128; c16 += 16) {
+                float kv[16], vv[16];
+                tmem_ld16(tlane + (uint32_t)(p.col_k + c16), kv);
+                tmem_ld16(tlane + (uint32_t)(p.col_v + c16), vv);
+                uint8_t* kd = smem + p.p_off + (uint32_t)rd * 256u + (uint32_t)c16 * 2u;
+                uint8_t* vd = smem + p.v_off + (uint32_t)rd * 256u + (uint32_t)c16 * 2u;
+                *reinterpret_cast<uint4*>(kd) = pack8(kv, p.fmt);
+                *reinterpret_cast<uint4*>(kd + 16) = pack8(kv + 8, p.fmt);
+                *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
+                *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, p.fmt);
+            }
+            epi_sync();
+            float o[128];
+            for (int h = 0; h < 4; ++h) {
+                float q[32];
+                tmem_ld16(tlane + (uint32_t)(p.col_q + h * 32), q);
+                tmem_ld16(tlane + (uint32_t)(p.col_q + h * 32 + 16), q + 16);
+                float sim[16];
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    sim[j] = -INFINITY;
+                    if (j < n && valid) {
+                        const uint8_t* kr = smem + p.p_off + (uint32_t)(s * n + j) * 256u + (uint32_t)h * 64u;
+                        float a = 0.f;
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) {
+                            float kk[8];
+                            unpack8(*reinterpret_cast<const uint4*>(kr + cb * 16), kk, p.fmt);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) a = fmaf(q[cb * 8 + e] * 0.17677669529663687f, kk[e], a);
+                        }
+                        sim[j] = a;
+                        m = fmaxf(m, a);
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { sim[j] = (j < n && valid) ? __expf(sim[j] - m) : 0.f; sum += sim[j]; }
+                const float inv = valid ? 1.0f / sum : 0.f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[h * 32 + e] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < n && valid) {
+                        const uint8_t* vr = smem + p.v_off + (uint32_t)(s * n + j) * 256u + (uint32_t)h * 64u;
+                        const float a = sim[j] * inv;
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) {
+                            float vv[8];
+                            unpack8(*reinterpret_cast<const uint4*>(vr + cb * 16), vv, p.fmt);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[h * 32 + cb * 8 + e] = fmaf(a, vv[e], o[h * 32 + cb * 8 + e]);
+                        }
+                    }
+                }
+            }
+            epi_sync();                                      // everyone is done reading K/V rows
+            (void)i;
+#pragma unroll
+            for (int cb = 0; cb < 16; ++cb)
+                *reinterpret_cast<uint4*>(smem + p.p_off + (uint32_t)cb * plane + (uint32_t)rd * 16u) = pack8(o + cb * 8, p.fmt);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+        }
+        // ================= last EPI: to_out bias -> GroupNorm(1,C) -> + x2 -> global =================
+        mbar_wait(bar_mma, ph & 1); ++ph;
+        tc_fence_after();
+        const float* bias = p.fblob + p.bo_off;
+        if (!p.full) {
+            for (int t = 0; t < p.n_mtiles; ++t) {
+                const int rd = t * 128 + r, s = rd / n;
+                const bool valid = s < p.nb && b0 + s < p.B;
+                float sx = 0.f, sq = 0.f;
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float x = v[j] + bias[c16 + j]; sx += x; sq += x * x; }
+                }
+                rowstat[rd] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+            }
+            // per-sample totals in a fixed order (deterministic)
+            int parts = 1;
+            while (parts * 2 * p.nb <= EPI_THREADS && parts < 16) parts *= 2;
+            epi_sync();
+            if (r < p.nb * parts) {
+                const int part = r % parts, s = r / parts;
+                const int per = (n + parts - 1) / parts;
+                const int a = s * n + part * per, bnd = min((s + 1) * n, a + per);
+                float sx = 0.f, sq = 0.f;
+                for (int k = a; k < bnd; ++k) { sx += rowstat[k].x; sq += rowstat[k].y; }
+                partial[r] = make_float2(sx, sq);
+            }
+            epi_sync();
+            if (r < p.nb) {
+                float sx = 0.f, sq = 0.f;
+                for (int k = 0; k < parts; ++k) { sx += partial[r * parts + k].x; sq += partial[r * parts + k].y; }
+                const float cnt = (float)(C * n);
+                const float mean = sx / cnt;
+                const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+                stat[r] = make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
+            }
+            epi_sync();
+        }
+        const float* gamma = p.fblob + p.gamma_off;
+        const float* beta = p.fblob + p.beta_off;
+        for (int t = 0; t < p.n_mtiles; ++t) {
+            const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+            const bool valid = s < p.nb && b0 + s < p.B;
+            const int b = b0 + s;
+            const float2 ms = (!p.full && s < p.nb) ? stat[s] : make_float2(0.f, 1.f);
+            for (int c16 = 0; c16 < C; c16 += 16) {
+                float v[16], x2[16];
+                tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+                if (!valid) continue;
+                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+                unpack8(xsrc[(size_t)((c16 >> 3) * p.B + b) * n + px], x2, p.fmt);
+                unpack8(xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * n + px], x2 + 8, p.fmt);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float y = v[j] + bias[c16 + j];
+                    if (!p.full) y = (y - ms.x) * ms.y * gamma[c16 + j] + beta[c16 + j];
+                    v[j] = y + x2[j];
+                }
+                attn_write_out(p, b, px, c16, v);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+cudaError_t attn_configure() {
+    return cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
+    k_attn<<<grid, FUSED_THREADS, p.smem_bytes, s>>>(xh_map, p);
+    return cudaGetLastError();
+}
+
+}  // namespace flo

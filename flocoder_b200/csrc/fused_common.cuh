@@ -1,0 +1,37 @@
+// helpers shared by the fused stage kernels (device code only)
+#pragma once
+#include <cuda_fp16.h>
+
+#include "umma_common.cuh"
+
+namespace flo {
+
+constexpr int FUSED_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit helpers (fmt: 1 = bf16, 0 = fp16)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+    if (fmt) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
+    if (fmt) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ uint4 pack8(const float* v, int fmt) {
+    return make_uint4(pack2(v[0], v[1], fmt), pack2(v[2], v[3], fmt), pack2(v[4], v[5], fmt), pack2(v[6], v[7], fmt));
+}
+__device__ __forceinline__ void unpack8(uint4 u, float* v, int fmt) {
+    float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt), c = unpack2(u.z, fmt), d = unpack2(u.w, fmt);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void epi_sync() { named_bar_sync(1, EPI_THREADS); }
+
+
+}  // namespace flo

@@ -97,7 +97,7 @@ static int conv_case(Report& rep, cudaStream_t st, const char* name, int B, int 
         for (int ci = 0; ci < cin; ++ci)
             for (int t = 0; t < taps; ++t) wsimt[((size_t)t * cin + ci) * cout + co] = w[((size_t)co * cin + ci) * taps + t];
     std::vector<__nv_bfloat16> wumma;
-    pack_umma_weights(w.data(), cout, cin, ksize, nullptr, n_tile, wumma);
+    pack_umma_weights(w.data(), cout, cin, ksize, nullptr, n_tile, false, wumma);
 
     __nv_bfloat16 *d_in0 = nullptr, *d_in1 = nullptr, *d_wu = nullptr, *d_oo = nullptr;
     float *d_ws = nullptr, *d_bias = nullptr, *d_res = nullptr, *d_ref = nullptr, *d_om = nullptr;

@@ -158,23 +158,26 @@ class Unet(nn.Module):
 
         self._engine = None
         self._engine_key = None
+        self.engine_flags = 0           # _lib.FLO_FLAG_* (e.g. FLO_FLAG_LAYERWISE: one kernel per layer)
 
     # ------------------------------------------------------------------ engine
     def _resolved_compute_dtype(self) -> str:
         if self.compute_dtype is not None:
-            if self.compute_dtype not in ("fp32", "bf16"):
-                raise ValueError(f"compute_dtype must be None, 'fp32' or 'bf16', got {self.compute_dtype!r}")
+            if self.compute_dtype not in ("fp32", "bf16", "fp16"):
+                raise ValueError(f"compute_dtype must be None, 'fp32', 'bf16' or 'fp16', got {self.compute_dtype!r}")
             return self.compute_dtype
         p = next(self.parameters())
         if p.dtype == torch.float32:
             return "fp32"
         if p.dtype == torch.bfloat16:
             return "bf16"
+        if p.dtype == torch.float16:
+            return "fp16"
         raise TypeError(f"unsupported parameter dtype {p.dtype}: the B200 path computes in fp32 or bf16")
 
     def _params_key(self, height: int, width: int):
         ps = list(self.parameters())
-        return (ps[0].device, self._resolved_compute_dtype(), height, width,
+        return (ps[0].device, self._resolved_compute_dtype(), height, width, self.engine_flags,
                 tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps))
 
     def engine(self, height: int, width: int) -> "_lib.Engine":
@@ -192,7 +195,7 @@ class Unet(nn.Module):
             self._engine = _lib.Engine(
                 dim=self.dim, channels=self.channels, dim_mults=self.dim_mults, groups=self.groups,
                 n_classes=self.n_classes, height=height, width=width, compute_dtype=key[1],
-                device=dev, state_dict=sd)
+                device=dev, state_dict=sd, flags=self.engine_flags)
             self._engine_key = key
         return self._engine
 

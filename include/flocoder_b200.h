@@ -42,7 +42,7 @@ typedef enum flo_status {
     FLO_ERR_NOMEM = -4
 } flo_status;
 
-typedef enum flo_dtype { FLO_F32 = 0, FLO_BF16 = 1 } flo_dtype;
+typedef enum flo_dtype { FLO_F32 = 0, FLO_BF16 = 1, FLO_F16 = 2 } flo_dtype;
 
 /* Integrators.  Stage times are formed in fp32 exactly as the reference forms them on 0-d
  * tensors (sampling.py:44-47,117): dt = ts[i+1]-ts[i];  t, t+dt/2, t+dt;  time fed to the
@@ -56,7 +56,9 @@ typedef enum flo_method {
 
 enum {
     FLO_FLAG_NO_BUFFER_REUSE = 1, /* debug: every op output keeps its own buffer (flo_unet_read_activation) */
-    FLO_FLAG_NO_GRAPH = 2         /* debug: launch kernels directly instead of replaying a CUDA graph */
+    FLO_FLAG_NO_GRAPH = 2,        /* debug: launch kernels directly instead of replaying a CUDA graph */
+    FLO_FLAG_LAYERWISE = 4        /* 16-bit paths: one kernel per layer (139 launches/forward) instead of the fused
+                                     stage kernels; the reference point the fused path is validated against */
 };
 
 /* Constructor arguments of flocoder.unet.Unet (unet.py:165-175) + latent size + compute type. */
@@ -69,7 +71,7 @@ typedef struct flo_unet_cfg {
     int32_t n_classes;     /* 0 = no class_cond_mlp                 */
     int32_t height, width; /* latent H, W                           */
     int32_t compute_dtype; /* flo_dtype: FLO_F32 = fp32 CUDA-core path (<=1e-5 parity),
-                              FLO_BF16 = bf16 tcgen05 convolutions, fp32 accumulate */
+                              FLO_BF16 / FLO_F16 = 16-bit tcgen05 operands, fp32 accumulate */
     int32_t mask_cond;     /* must be 0 (inpainting U-Net is out of scope) */
     int32_t flags;         /* FLO_FLAG_*                            */
     int32_t device;        /* CUDA device ordinal                   */

@@ -61,22 +61,29 @@ class UnetSpec:
 @dataclass(frozen=True)
 class Precision:
     name: str = "fp32"
-    gemm_operands_bf16: bool = False   # round conv inputs+weights (tensor-core convs)
-    qkv_store_bf16: bool = False       # round to_qkv outputs where CUDA stores bf16
+    gemm_operands_bf16: bool = False   # round conv inputs+weights (tensor-core convs) to the 16-bit type
+    qkv_store_bf16: bool = False       # round to_qkv outputs where the layer-by-layer CUDA path stores 16-bit
+    stream_16: bool = False            # fused path: the residual stream itself (block / attention / conv outputs)
+                                       # is stored in the 16-bit type between ops
+    dtype16: torch.dtype = torch.bfloat16
+
+    def _r(self, t: Tensor) -> Tensor:
+        return t.to(self.dtype16).to(t.dtype)
 
     def op(self, t: Tensor) -> Tensor:
-        if not self.gemm_operands_bf16:
-            return t
-        return t.to(torch.bfloat16).to(t.dtype)
+        return self._r(t) if self.gemm_operands_bf16 else t
 
     def qkv(self, t: Tensor) -> Tensor:
-        if not self.qkv_store_bf16:
-            return t
-        return t.to(torch.bfloat16).to(t.dtype)
+        return self._r(t) if self.qkv_store_bf16 else t
+
+    def act(self, t: Tensor) -> Tensor:
+        return self._r(t) if self.stream_16 else t
 
 
 FP32 = Precision("fp32")
 BF16_MATCHED = Precision("bf16_matched", gemm_operands_bf16=True, qkv_store_bf16=True)
+FUSED_BF16 = Precision("fused_bf16", gemm_operands_bf16=True, stream_16=True)
+FUSED_FP16 = Precision("fused_fp16", gemm_operands_bf16=True, stream_16=True, dtype16=torch.float16)
 
 
 def key_usable(d, key) -> bool:
@@ -140,7 +147,7 @@ def resnet_block(sd, p: str, x: Tensor, t_emb: Tensor, groups: int, prec: Precis
         res = _conv(sd, p + ".res_conv", x, 0, prec)
     else:
         res = x
-    out = h + res
+    out = prec.act(h + res)
     if tr is not None:
         tr[p] = out
     return out
@@ -179,8 +186,10 @@ def attention(sd, p: str, x: Tensor, prec: Precision) -> Tensor:
 
 def residual_prenorm(sd, p: str, x: Tensor, fn, prec: Precision, tr=None) -> Tensor:
     """Residual(PreNorm(dim, fn)): fn(GN1(x)) + x  (unet.py:38-39,159-161)."""
-    y = fn(sd, p + ".fn.fn", _group_norm(sd, p + ".fn.norm", x, 1), prec) + x
+    xn = _group_norm(sd, p + ".fn.norm", x, 1)
+    y = prec.act(fn(sd, p + ".fn.fn", xn, prec) + x)
     if tr is not None:
+        tr[p + ".fn.norm"] = xn
         tr[p] = y
     return y
 
@@ -221,7 +230,7 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
     tr = trace
     n_res = len(spec.in_out)
 
-    x = _conv(sd, "init_conv", x, 0, prec, tensor_core=False)          # unet.py:295
+    x = prec.act(_conv(sd, "init_conv", x, 0, prec, tensor_core=False))   # unet.py:295
     if tr is not None:
         tr["init_conv"] = x
     r = x                                                              # unet.py:308 (clone)
@@ -238,9 +247,9 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         x = residual_prenorm(sd, p + ".2", x, linear_attention, prec, tr)
         skips.append(x)
         if i < n_res - 1:
-            x = downsample(sd, p + ".3", x, prec)
+            x = prec.act(downsample(sd, p + ".3", x, prec))
         else:
-            x = _conv(sd, p + ".3", x, 1, prec)
+            x = prec.act(_conv(sd, p + ".3", x, 1, prec))
         if tr is not None:
             tr[p + ".3"] = x
 
@@ -256,9 +265,9 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         x = resnet_block(sd, p + ".1", x, t, g, prec, tr)
         x = residual_prenorm(sd, p + ".2", x, linear_attention, prec, tr)
         if i < n_res - 1:
-            x = upsample(sd, p + ".3", x, prec)
+            x = prec.act(upsample(sd, p + ".3", x, prec))
         else:
-            x = _conv(sd, p + ".3", x, 1, prec)
+            x = prec.act(_conv(sd, p + ".3", x, 1, prec))
         if tr is not None:
             tr[p + ".3"] = x
 

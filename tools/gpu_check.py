@@ -15,7 +15,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from conftest import CONFIGS, rel_l2, seeded_state_dict  # noqa: E402
-from oracle.unet_oracle import BF16_MATCHED, FP32, OracleModel, UnetSpec, unet_forward  # noqa: E402
+from oracle.unet_oracle import (BF16_MATCHED, FP32, FUSED_BF16, FUSED_FP16, OracleModel, UnetSpec,  # noqa: E402
+                                unet_forward)
 import oracle  # noqa: E402
 
 
@@ -27,10 +28,17 @@ def load_golden(name):
     return torch.load(os.path.join(ROOT, "tests", "golden", f"{name}.pt"), weights_only=False)
 
 
+LAYERWISE = False
+
+
 def model(n_classes, cd):
+    from flocoder_b200 import _lib
     from flocoder_b200.unet import Unet
     torch.manual_seed(1234)
-    return Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=n_classes, compute_dtype=cd).cuda().eval()
+    m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=n_classes, compute_dtype=cd).cuda().eval()
+    if LAYERWISE:
+        m.engine_flags = _lib.FLO_FLAG_LAYERWISE
+    return m
 
 
 def layer_table(m, n_classes, x, t, prec, flags_extra=0):
@@ -38,19 +46,20 @@ def layer_table(m, n_classes, x, t, prec, flags_extra=0):
     _, sd = seeded_state_dict(n_classes)
     eng = _lib.Engine(dim=m.dim, channels=m.channels, dim_mults=m.dim_mults, groups=m.groups, n_classes=m.n_classes,
                       height=16, width=16, compute_dtype=m._resolved_compute_dtype(), device=x.device,
-                      state_dict=m.state_dict(), flags=_lib.FLO_FLAG_NO_BUFFER_REUSE | flags_extra)
+                      state_dict=m.state_dict(), flags=_lib.FLO_FLAG_NO_BUFFER_REUSE | flags_extra | m.engine_flags)
     v = eng.forward(x.float().contiguous(), t.float().contiguous(), None)
     torch.cuda.synchronize()
     trace = {}
     with torch.no_grad():
         vref = unet_forward(sd, spec_for(n_classes), x.cpu(), t.cpu(), None, prec, trace)
-    for name in eng.op_names():
-        if name in trace:
-            try:
-                a = eng.read_activation(name, x.shape[0])
-                print(f"  {name:42s} rel_l2={rel_l2(a, trace[name]):.3e}")
-            except Exception as e:  # noqa: BLE001
-                print(f"  {name:42s} (unreadable: {e})")
+    for name in trace:
+        if trace[name].dim() != 4:
+            continue
+        try:
+            a = eng.read_activation(name, x.shape[0])
+        except ValueError:
+            continue
+        print(f"  {name:42s} rel_l2={rel_l2(a, trace[name]):.3e}")
     print(f"  {'OUTPUT v':42s} rel_l2={rel_l2(v, vref):.3e}")
     eng.close()
 
@@ -65,7 +74,7 @@ def run_selftest():
 
 def run_path(cd):
     from flocoder_b200 import sampling
-    prec = FP32 if cd == "fp32" else BF16_MATCHED
+    prec = FP32 if cd == "fp32" else (BF16_MATCHED if LAYERWISE else (FUSED_FP16 if cd == "fp16" else FUSED_BF16))
     g = load_golden("midi_vqgan")
     m = model(0, cd)
     print(f"== per-layer ({cd}) vs {'fp32 oracle' if cd == 'fp32' else 'matched oracle'}")
@@ -103,10 +112,13 @@ def run_time(cd, B):
 
 
 if __name__ == "__main__":
+    if "layerwise" in sys.argv:
+        LAYERWISE = True
+        sys.argv.remove("layerwise")
     mode = sys.argv[1]
     if mode == "selftest":
         sys.exit(1 if run_selftest() else 0)
-    elif mode in ("fp32", "bf16"):
+    elif mode in ("fp32", "bf16", "fp16"):
         run_path(mode)
     elif mode == "time":
         run_time(sys.argv[2], int(sys.argv[3]))
