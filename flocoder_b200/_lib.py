@@ -28,7 +28,7 @@ EXPORTS = (
     "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
     "flo_integrate_nfe", "flo_unet_num_ops", "flo_unet_op_name", "flo_unet_launches_per_forward",
     "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma", "flo_describe_plan",
-    "flo_unet_op_info", "flo_unet_profile_ops",
+    "flo_unet_op_info", "flo_unet_profile_ops", "flo_unet_read_timeline",
 )
 
 
@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
     L.flo_describe_plan.argtypes = [POINTER(FloUnetCfg), c_int, c_char_p, c_int]
     L.flo_unet_op_info.argtypes = [c_void_p, c_int, POINTER(c_int), POINTER(ctypes.c_double), POINTER(ctypes.c_double)]
     L.flo_unet_profile_ops.argtypes = [c_void_p, c_int, c_int, POINTER(c_float), c_void_p]
+    L.flo_unet_read_timeline.argtypes = [c_void_p, c_int, c_int, POINTER(ctypes.c_longlong)]
     _lib_handle = L
     return L
 
@@ -259,6 +260,11 @@ class Engine:
             check(self.L.flo_unet_profile_ops(self.handle, b, reps, ms, _stream_ptr(self.device)),
                   "flo_unet_profile_ops")
         return list(ms)
+
+    def read_timeline(self, b: int, stage: int):
+        out = (ctypes.c_longlong * 128)()
+        check(self.L.flo_unet_read_timeline(self.handle, b, stage, out), "flo_unet_read_timeline")
+        return list(out)
 
     def launches_per_forward(self, b: int) -> int:
         n = self.L.flo_unet_launches_per_forward(self.handle, b)

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -207,6 +208,8 @@ static const size_t NONE = (size_t)-1;
 struct Op {
     int kind;
     std::string name;
+    std::string pname;        // parameter prefix of a conv ('<pname>.weight')
+    bool unshuf_in = false;   // conv input is the pixel-unshuffled tensor in (p1 p2 c) channel order
     // conv
     int in0 = -1, in1 = -1, ncb0 = 0, ncb1 = 0, cout = 0, ksize = 0, H = 0, W = 0;
     size_t w_simt = NONE, w_umma = NONE, bias = NONE;
@@ -256,6 +259,7 @@ struct Plan {
     std::vector<CUtensorMap> fstage_maps;
     std::vector<ChainParams> fchain;
     std::vector<AttnFusedParams> fattn;
+    long long* dbg = nullptr;
 };
 
 struct Handle {
@@ -333,7 +337,7 @@ struct Builder {
     // conv with optional second (concatenated) source; perm maps OUR input-channel order to the reference's
     Val conv(const std::string& pname, const std::string& vname, int in0, int C0, int in1, int C1, int H, int W,
              int cout, int ksize, bool bias, bool need_m, bool need_o, int res_m = -1, const std::vector<int>* perm = nullptr) {
-        Op op; op.kind = OP_CONV; op.name = vname;
+        Op op; op.kind = OP_CONV; op.name = vname; op.pname = pname; op.unshuf_in = perm != nullptr;
         op.in0 = in0; op.in1 = in1; op.ncb0 = C0 / 8; op.ncb1 = C1 / 8; op.cout = cout; op.ksize = ksize; op.H = H; op.W = W;
         const int cin = C0 + C1, taps = ksize * ksize;
         const auto& w = P(pname + ".weight");
@@ -1198,8 +1202,8 @@ int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap) {
                 for (int k = 0; k < c.n_steps; ++k) {
                     const ChainStep& cs = c.st[k];
                     snprintf(line, sizeof(line), "      step %d: conv=%d k=%d cin=%d+%d n=%d chunks=%dx%d res=%d(%dx%d) epi=%d C=%d G=%d film=%d resmode=%d out_slot=%d out_g=%d un=%d up=%d pn=%d final=%d a0=%d a1=%d\n",
-                             k, cs.has_conv, cs.ksize, cs.a0_ncb * 8, cs.a1_ncb * 8, cs.n, cs.n_chunks, cs.slices_per_chunk, cs.has_res,
-                             cs.res_chunks, cs.res_slices_per_chunk, cs.epi, cs.C, cs.groups, cs.film_off, cs.res_mode, cs.out_slot_off,
+                             k, cs.has_conv, cs.ksize, cs.a0_ncb * 8, cs.a1_ncb * 8, cs.n, cs.slices, cs.slices_per_chunk, cs.has_res,
+                             cs.res_slices, cs.res_slices_per_chunk, cs.epi, cs.C, cs.groups, cs.film_off, cs.res_mode, cs.out_slot_off,
                              cs.out_g, cs.out_un_g, cs.out_up_g, cs.pn_g, cs.final, cs.a0_off, cs.a1_off);
                     t += line;
                 }
@@ -1348,6 +1352,18 @@ int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void
     for (auto& e : ev) cudaEventDestroy(e);
     cudaFree(d_t);
     h->launches += (int64_t)(reps + 1) * (n_ops + 1) + 1;
+    return FLO_OK;
+}
+
+// debug: clock64 timeline of CTA 0 of fused chain stage `stage` (needs env FLO_TIMELINE=1 at plan creation)
+int flo_unet_read_timeline(flo_unet_t* hh, int B, int stage, long long* out128) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h || !out128) { set_error("NULL argument"); return FLO_ERR_INVALID; }
+    auto it = h->plans.find(B);
+    if (it == h->plans.end() || !it->second->dbg || stage < 0 || stage >= (int)h->fstages.size()) { set_error("no timeline"); return FLO_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(h->spec.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out128, it->second->dbg + stage * 128, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
     return FLO_OK;
 }
 

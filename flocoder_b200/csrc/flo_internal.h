@@ -209,8 +209,9 @@ struct ChainStep {
     int a0_off, a0_ncb, a1_off, a1_ncb;     // A operand slots: byte offset in smem, channel blocks (a1_ncb = 0: none)
     int ksize, n;                           // kernel size, output channels
     int acc_col;                            // TMEM column of tile 0 (tile t at acc_col + t*n)
-    unsigned w_off; int n_chunks, slices_per_chunk;            // weight stream (16-bit elements into wblob)
-    int has_res, res_col; unsigned wres_off; int res_chunks, res_slices_per_chunk;   // 1x1 res_conv on the same A
+    unsigned w_off; int slices, slices_per_chunk;              // weight stream (16-bit elements into wblob): K16 slices
+                                                               // incl. the trailing bias slice, slices per ring chunk
+    int has_res, res_col; unsigned wres_off; int res_slices, res_slices_per_chunk;   // 1x1 res_conv on the same A
     // ---- epilogue part
     int epi;                                // ChainEpi
     int C, groups, silu, film_off;          // film_off < 0: no FiLM
@@ -229,6 +230,8 @@ struct ChainParams {
     int B, H, W, nb, n_mtiles, strips, plane_px;
     int n_loads, load_off[CH_MAX_LOADS], load_ncb[CH_MAX_LOADS];
     int zero_off, zero_bytes;               // shared-memory range to clear at start (epilogue-written slots)
+    int ones_off;                           // 4 KB constant A tile [1,0,...] that multiplies the bias slice
+    int g_max, coef_n;                      // stats region layout: rowstat[rows*g_max] partial[128] stat[128] coef[coef_n] cpar[256]
     int ring_off, ring_slot_bytes, n_ring;
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16
@@ -239,6 +242,7 @@ struct ChainParams {
     const float* fblob;
     void* gt[CH_MAX_GT];
     Ctrl* ctrl;
+    long long* dbg;                         // optional clock64 timeline of CTA 0: [step][8] (null in production)
 };
 
 // linear-attention block  Residual(PreNorm(dim, LinearAttention(dim)))  (unet.py:33-39,125-161) and the

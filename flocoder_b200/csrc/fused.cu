@@ -1,20 +1,23 @@
-// Fused stage kernels (sm_100a): whole ResnetBlock chains and the attention blocks of one resolution
-// level in ONE kernel each.  A CTA owns `nb` complete samples; activations never leave the SM inside a
-// stage -- 16-bit operands live in shared memory in the blocked/padded layout that doubles as the tcgen05
-// no-swizzle K-major operand (3x3 taps = shifted descriptors, torch.cat = two operand slots), fp32
-// accumulators live in TMEM, weights are streamed through a shared-memory ring by bulk TMA copies.
+// Fused stage kernels (sm_100a): whole ResnetBlock chains of one resolution level in ONE kernel.
+// A CTA owns `nb` complete samples; activations never leave the SM inside a stage -- 16-bit operands live in
+// shared memory in the blocked/padded layout that doubles as the tcgen05 no-swizzle K-major operand (3x3 taps
+// = shifted descriptors, torch.cat = two operand slots), fp32 accumulators live in TMEM, weights are streamed
+// through a shared-memory ring by bulk TMA copies.
 //
-// k_chain   [conv -> GroupNorm+FiLM+SiLU(+residual)]* with the ResnetBlock 1x1 res_conv accumulated into a
-//           second TMEM region, the PreNorm of the following attention block fused into the last epilogue,
-//           init_conv (unet.py:295) as the first epilogue of the first stage and final_conv + the RK4/Euler
-//           /CFG stage update (unet.py:372, sampling.py:43-48,69-74) as the last epilogue of the last stage.
-// k_attn    Residual(PreNorm(LinearAttention)) (unet.py:125-161): q/k/v 1x1 convs, both softmaxes,
-//           context and output contractions and the to_out conv on tcgen05, GroupNorm + residual epilogue;
-//           and the mid-block softmax attention (unet.py:99-122).
+// k_chain   [conv -> GroupNorm+FiLM+SiLU(+residual)]* with
+//           * the conv bias folded into the GEMM (one extra K slice: a constant "ones" A tile x a bias B tile),
+//           * the ResnetBlock 1x1 res_conv accumulated into a second TMEM region (never leaves TMEM),
+//           * GroupNorm affine, FiLM and bias collapsed per step into ONE (scale, offset) pair per
+//             (sample, channel) in shared memory, so the normalise pass is one FMA + SiLU per element,
+//           * the PreNorm of the following attention block fused into the last epilogue,
+//           * init_conv (unet.py:295) as the first epilogue of the first stage and final_conv + the RK4 / Euler
+//             / CFG stage update (unet.py:372, sampling.py:43-48,69-74) as the last epilogue of the last stage.
 //
 // Three decoupled loops per CTA (192 threads): warp 4 lane 0 = TMA producer (input tiles, weight ring),
 // warp 5 lane 0 = tcgen05.mma issuer, warps 0-3 = epilogue (TMEM lane quadrants).  Steps alternate
 // MMA(i) -> EPI(i) -> MMA(i+1) ... through two mbarriers (bar_mma: tcgen05.commit, bar_epi: 128 arrivals).
+// Every role copies what it needs of the (constant-bank) parameter block into registers first: the
+// asm-volatile "memory" clobbers of the PTX wrappers would otherwise force re-loads inside the hot loops.
 #include <cuda_fp16.h>
 
 #include "flo_internal.h"
@@ -23,128 +26,165 @@
 
 namespace flo {
 
-// one thread's row of an M tile: padded pixel -> (sample, h, w)
+// geometry of the M tiles, in registers
+struct Geo {
+    int W, H, Wp, PP, nb, B, n_mtiles, strips, sbo_px, tx_n;
+};
+__device__ __forceinline__ Geo make_geo(const ChainParams& p) {
+    Geo g;
+    g.W = p.W; g.H = p.H; g.Wp = p.W + 2; g.PP = g.Wp * (p.H + 2); g.nb = p.nb; g.B = p.B; g.n_mtiles = p.n_mtiles;
+    g.strips = p.strips; g.sbo_px = p.strips ? g.Wp : 8; g.tx_n = p.W >> 3;
+    return g;
+}
+__device__ __forceinline__ int tile_row0(const Geo& g, int t) {
+    if (g.strips) return ((t / g.tx_n) * 16 + 1) * g.Wp + 1 + 8 * (t % g.tx_n);
+    return g.Wp + 1 + t * 128;
+}
 struct RowInfo {
     int pp;        // flattened padded pixel index inside the CTA's planes
     int s, px;     // sample within the CTA, unpadded pixel index h*W+w
     int h, w;
     bool valid;
 };
-__device__ __forceinline__ int chain_tile_row0(const ChainParams& p, int t) {
-    const int Wp = p.W + 2;
-    if (p.strips) {
-        const int tx_n = p.W >> 3;
-        return ((t / tx_n) * 16 + 1) * Wp + 1 + 8 * (t % tx_n);
-    }
-    return Wp + 1 + t * 128;
-}
-__device__ __forceinline__ RowInfo chain_row(const ChainParams& p, int t, int r, int b0) {
-    const int Wp = p.W + 2, PP = Wp * (p.H + 2);
+__device__ __forceinline__ RowInfo make_row(const Geo& g, int t, int r, int b0) {
     RowInfo ri;
-    ri.pp = chain_tile_row0(p, t) + (r >> 3) * (p.strips ? Wp : 8) + (r & 7);
-    ri.s = ri.pp / PP;
-    const int rem = ri.pp - ri.s * PP;
-    const int hh = rem / Wp, ww = rem - hh * Wp;
+    ri.pp = tile_row0(g, t) + (r >> 3) * g.sbo_px + (r & 7);
+    ri.s = ri.pp / g.PP;
+    const int rem = ri.pp - ri.s * g.PP;
+    const int hh = rem / g.Wp, ww = rem - hh * g.Wp;
     ri.h = hh - 1; ri.w = ww - 1;
-    ri.px = ri.h * p.W + ri.w;
-    ri.valid = (ri.s < p.nb) && (b0 + ri.s < p.B) && hh >= 1 && hh <= p.H && ww >= 1 && ww <= p.W;
+    ri.px = ri.h * g.W + ri.w;
+    ri.valid = (ri.s < g.nb) && (b0 + ri.s < g.B) && hh >= 1 && hh <= g.H && ww >= 1 && ww <= g.W;
     return ri;
 }
 
-// issue one convolution (all taps, all K slices, all M tiles) whose weights arrive through the ring
-struct RingState { int cc; };   // global chunk counter (producer and issuer advance in lock step)
-
-__device__ __forceinline__ void issue_conv(const ChainParams& p, uint32_t smem_base, uint32_t tmem_base, uint32_t bar_full,
-                                           uint32_t bar_empty, RingState& rs, int a0_off, int a0_ncb, int a1_off, int a1_ncb,
-                                           int ksize, int n, int col, int n_chunks, int S) {
-    const int Wp = p.W + 2;
-    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const uint32_t a_sbo = (uint32_t)(p.strips ? Wp : 8) * 16u;
-    const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
-    const int cpT = (a0_ncb + a1_ncb) >> 1;
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        const int slot = rs.cc % p.n_ring;
-        mbar_wait(bar_full + 8 * slot, (rs.cc / p.n_ring) & 1);
-        tc_fence_after();
-        const uint32_t bstage = smem_base + p.ring_off + slot * p.ring_slot_bytes;
-        for (int s = 0; s < S; ++s) {
-            const int ks = ci * S + s;
-            const int tap = ks / cpT, cp = ks - tap * cpT;
-            const int shift = (ksize == 3) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
-            const uint32_t a_plane = (2 * cp < a0_ncb) ? (uint32_t)a0_off + (uint32_t)(2 * cp) * plane_bytes
-                                                       : (uint32_t)a1_off + (uint32_t)(2 * cp - a0_ncb) * plane_bytes;
-            const uint64_t bdesc = make_smem_desc(bstage + (uint32_t)s * (uint32_t)n * 32u, (uint32_t)n * 16u, 128u);
-            for (int t = 0; t < p.n_mtiles; ++t) {
-                const uint32_t a_addr = smem_base + a_plane + (uint32_t)(chain_tile_row0(p, t) + shift) * 16u;
-                umma_bf16(tmem_base + (uint32_t)(col + t * n), make_smem_desc(a_addr, plane_bytes, a_sbo), bdesc, idesc,
-                          ks > 0 ? 1u : 0u);
+// ------------------------------------------------------------------------------------------------
+// MMA issue: one convolution = taps x channel-pair slices (+ 1 bias slice), weights from the ring
+// ------------------------------------------------------------------------------------------------
+struct ConvIssue {
+    uint32_t a0_lo, a1_lo;     // (smem address >> 4) of plane 0 of each operand slot
+    int a0_pairs, a1_pairs;    // channel-block pairs (K16 slices per tap) in each slot
+    int ksize, n, col, slices, S;
+};
+struct IssueCtx {
+    uint32_t tmem_base, bar_full, bar_empty, ring_lo, ring_slot16, ones_lo;
+    uint32_t plane16;          // plane stride >> 4
+    uint32_t desc_hi_a, desc_hi_ones;
+    int n_ring, fmt, n_mtiles, Wp;
+    int row0[4];
+    int cc;                    // global ring chunk counter
+};
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo14, uint32_t lbo16, uint32_t hi) {
+    return ((uint64_t)hi << 32) | (uint64_t)((lo14 & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16));
+}
+__device__ __forceinline__ void issue_conv(IssueCtx& x, const ConvIssue& c) {
+    const uint32_t idesc = make_idesc16(128, c.n, x.fmt, 0, 0);
+    const uint32_t b_lbo16 = (uint32_t)c.n;                      // n*16 bytes >> 4
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t slice16 = (uint32_t)c.n * 2u;                 // n*32 bytes >> 4
+    const int taps = c.ksize * c.ksize;
+    int sidx = 0, ks = 0;
+    uint32_t b_lo = 0;
+    int slot = 0;
+    for (int tap = 0; tap <= taps; ++tap) {
+        const bool bias_slice = tap == taps;
+        const int shift = (c.ksize == 3 && !bias_slice) ? ((tap / 3 - 1) * x.Wp + (tap % 3 - 1)) : 0;
+        const int pairs = bias_slice ? 1 : c.a0_pairs + c.a1_pairs;
+        for (int cp = 0; cp < pairs; ++cp, ++ks) {
+            if (sidx == 0) {
+                slot = x.cc % x.n_ring;
+                mbar_wait(x.bar_full + 8 * slot, (x.cc / x.n_ring) & 1);
+                tc_fence_after();
+                b_lo = x.ring_lo + (uint32_t)slot * x.ring_slot16;
             }
+            const uint64_t bdesc = mk_desc(b_lo + (uint32_t)sidx * slice16, b_lbo16, b_hi);
+            if (bias_slice) {
+                const uint64_t adesc = mk_desc(x.ones_lo, 128u, x.desc_hi_ones);       // rows of [1,0,..,0]; K half 1 = zeros
+                if (elect_one())
+                    for (int t = 0; t < x.n_mtiles; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
+            } else {
+                const uint32_t plane_lo = (cp < c.a0_pairs) ? c.a0_lo + (uint32_t)(2 * cp) * x.plane16
+                                                            : c.a1_lo + (uint32_t)(2 * (cp - c.a0_pairs)) * x.plane16;
+                if (elect_one())
+                    for (int t = 0; t < x.n_mtiles; ++t)
+                        umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n),
+                                  mk_desc(plane_lo + (uint32_t)(x.row0[t] + shift), x.plane16, x.desc_hi_a), bdesc, idesc, ks > 0 ? 1u : 0u);
+            }
+            if (++sidx == c.S || ks + 1 == c.slices) {
+                if (elect_one()) umma_commit(x.bar_empty + 8 * slot);
+                ++x.cc;
+                sidx = 0;
+            }
+            __syncwarp();
         }
-        umma_commit(bar_empty + 8 * slot);
-        ++rs.cc;
     }
 }
-__device__ __forceinline__ void stream_weights(const ChainParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
-                                               RingState& rs, const uint16_t* w, int n_chunks, int chunk_bytes) {
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        const int slot = rs.cc % p.n_ring;
-        if (rs.cc >= p.n_ring) mbar_wait(bar_empty + 8 * slot, ((rs.cc / p.n_ring) - 1) & 1);
-        mbar_expect_tx(bar_full + 8 * slot, (uint32_t)chunk_bytes);
-        bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes,
-                     reinterpret_cast<const uint8_t*>(w) + (size_t)ci * chunk_bytes, (uint32_t)chunk_bytes, bar_full + 8 * slot);
-        ++rs.cc;
+// producer side of the same chunk sequence
+__device__ __forceinline__ void stream_weights(uint32_t smem_base, uint32_t ring_off, uint32_t ring_slot_bytes, int n_ring,
+                                               uint32_t bar_full, uint32_t bar_empty, int& cc, const uint16_t* w, int slices, int S,
+                                               int n) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(w);
+    for (int done = 0; done < slices; done += S) {
+        const uint32_t bytes = (uint32_t)min(S, slices - done) * (uint32_t)n * 32u;
+        const int slot = cc % n_ring;
+        if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, ((cc / n_ring) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * slot, bytes);
+        bulk_load_1d(smem_base + ring_off + (uint32_t)slot * ring_slot_bytes, src, bytes, bar_full + 8 * slot);
+        src += bytes;
+        ++cc;
     }
 }
 
-// write one 16-channel chunk of an output row to every requested destination
-__device__ __forceinline__ void write_outputs(const ChainParams& p, const ChainStep& st, uint8_t* smem, const RowInfo& ri, int b,
-                                              int c16, const float* v) {
-    const int HW = p.H * p.W;
-    const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const int ncb = st.C >> 3;
+// ------------------------------------------------------------------------------------------------
+// epilogue helpers
+// ------------------------------------------------------------------------------------------------
+struct OutDst {                 // destinations of one step's result, in registers
+    int slot_off;               // shared-memory slot or -1
+    uint4* g; uint4* g_un; uint4* g_up;
+    int ncb;
+};
+__device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uint8_t* smem, uint32_t plane_bytes, const RowInfo& ri,
+                                              int b, int c16, const float* v, int fmt) {
+    const int HW = g.H * g.W;
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const int cb = (c16 >> 3) + hb;
-        const uint4 u = pack8(v + hb * 8, p.fmt);
-        if (st.out_slot_off >= 0)
-            *reinterpret_cast<uint4*>(smem + st.out_slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u) = u;
-        if (st.out_g >= 0)
-            reinterpret_cast<uint4*>(p.gt[st.out_g])[(size_t)(cb * p.B + b) * HW + ri.px] = u;
-        if (st.out_un_g >= 0) {     // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)  (unet.py:52)
-            const int plane = ((ri.h & 1) * 2 + (ri.w & 1)) * ncb + cb;
-            const int q = (ri.h >> 1) * (p.W >> 1) + (ri.w >> 1);
-            reinterpret_cast<uint4*>(p.gt[st.out_un_g])[(size_t)(plane * p.B + b) * (HW >> 2) + q] = u;
+        const uint4 u = pack8(v + hb * 8, fmt);
+        if (o.slot_off >= 0) *reinterpret_cast<uint4*>(smem + o.slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u) = u;
+        if (o.g) o.g[(size_t)(cb * g.B + b) * HW + ri.px] = u;
+        if (o.g_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)  (unet.py:52)
+            const int plane = ((ri.h & 1) * 2 + (ri.w & 1)) * o.ncb + cb;
+            const int q = (ri.h >> 1) * (g.W >> 1) + (ri.w >> 1);
+            o.g_un[(size_t)(plane * g.B + b) * (HW >> 2) + q] = u;
         }
-        if (st.out_up_g >= 0) {     // nearest x2 (unet.py:44)
-            const int W2 = p.W * 2;
-            uint4* dst = reinterpret_cast<uint4*>(p.gt[st.out_up_g]) + (size_t)(cb * p.B + b) * (HW * 4);
+        if (o.g_up) {   // nearest x2 (unet.py:44)
+            const int W2 = g.W * 2;
+            uint4* dst = o.g_up + (size_t)(cb * g.B + b) * (HW * 4);
 #pragma unroll
             for (int d = 0; d < 4; ++d) dst[(2 * ri.h + (d >> 1)) * W2 + 2 * ri.w + (d & 1)] = u;
         }
     }
 }
 
-// deterministic per-(sample, group) reduction of per-row (sum, sumsq) pairs held in shared memory
+// per-(sample, group) totals of the per-row (sum, sumsq) pairs in shared memory, fixed order (deterministic).
 //   rowstat[row * G + g], rows = n_mtiles*128;  result stat[s*G+g] = (mean, rstd)
-__device__ void reduce_stats(const ChainParams& p, float2* rowstat, float2* partial, float2* stat, int G, float count,
-                             int tid) {
-    const int Wp = p.W + 2, PP = Wp * (p.H + 2);
-    const int R = p.n_mtiles * 128;
-    const int combos = p.nb * G;
+__device__ void reduce_stats(const Geo& g, float2* rowstat, float2* partial, float2* stat, int G, float count, int tid) {
+    const int R = g.n_mtiles * 128;
+    const int combos = g.nb * G;
     int parts = 1;
-    while (parts * 2 * combos <= EPI_THREADS && parts < 16) parts *= 2;
+    while (parts * 2 * combos <= EPI_THREADS && parts < 32) parts *= 2;
     epi_sync();
     if (tid < combos * parts) {
-        const int part = tid % parts, sg = tid / parts, g = sg % G, s = sg / G;
+        const int part = tid % parts, sg = tid / parts, gi = sg % G, s = sg / G;
         int lo = 0, hi = R;
-        if (!p.strips) {
-            lo = min(max(s * PP - (Wp + 1), 0), R);
-            hi = min(max((s + 1) * PP - (Wp + 1), 0), R);
+        if (!g.strips) {
+            lo = min(max(s * g.PP - (g.Wp + 1), 0), R);
+            hi = min(max((s + 1) * g.PP - (g.Wp + 1), 0), R);
         }
         const int per = (hi - lo + parts - 1) / parts;
         const int a = lo + part * per, b = min(hi, a + per);
         float sx = 0.f, sq = 0.f;
-        for (int r = a; r < b; ++r) { const float2 v = rowstat[r * G + g]; sx += v.x; sq += v.y; }
+        for (int r = a; r < b; ++r) { const float2 v = rowstat[r * G + gi]; sx += v.x; sq += v.y; }
         partial[tid] = make_float2(sx, sq);
     }
     epi_sync();
@@ -169,73 +209,100 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_full = smem_base + p.bar_off;
+    const int bar_off = p.bar_off;
+    const uint32_t bar_full = smem_base + bar_off;
     const uint32_t bar_empty = bar_full + 8 * MAX_WSTAGES;
     const uint32_t bar_load = bar_empty + 8 * MAX_WSTAGES;
     const uint32_t bar_mma = bar_load + 8;
     const uint32_t bar_epi = bar_mma + 8;
     const uint32_t tmem_slot = bar_epi + 8;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
-    const int b0 = blockIdx.x * p.nb;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 24);
+    const Geo geo = make_geo(p);
+    const int b0 = blockIdx.x * geo.nb;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
+    const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
+    const int ones_off = p.ones_off;
+    long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
 
     if (warp == 4 && lane == 0) {
-        for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         mbar_init(bar_epi, EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    // clear the slots the epilogues write (their halo must read as zero)
-    for (int i = tid * 16; i < p.zero_bytes; i += FUSED_THREADS * 16)
-        *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
+    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    {   // clear the slots the epilogues write (their halo must read as zero) and build the "ones" A tile
+        const int zoff = p.zero_off, zbytes = p.zero_bytes;
+        for (int i = tid * 16; i < zbytes; i += FUSED_THREADS * 16) *reinterpret_cast<uint4*>(smem + zoff + i) = make_uint4(0, 0, 0, 0);
+        const uint32_t one = pack2(1.0f, 0.f, fmt) & 0xFFFFu;
+        for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,0,0,0,0,0,0,0] per row; plane 1: zeros
+            *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? one : 0u, 0, 0, 0);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8] = clock64();
 
     if (warp == 4) {
         // ============================ producer ============================
         if (lane == 0) {
-            if (p.n_loads > 0) {
+            if (n_loads > 0) {
                 uint32_t bytes = 0;
-                for (int i = 0; i < p.n_loads; ++i) bytes += (uint32_t)p.load_ncb[i] * plane_bytes;
+                for (int i = 0; i < n_loads; ++i) bytes += (uint32_t)p.load_ncb[i] * plane_bytes;
                 mbar_expect_tx(bar_load, bytes);
                 const CUtensorMap* maps[4] = {&tm0, &tm1, &tm2, &tm3};
-                for (int i = 0; i < p.n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
+                for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
-            RingState rs{0};
-            for (int i = 0; i < p.n_steps; ++i) {
-                const ChainStep& st = p.st[i];
-                if (!st.has_conv) continue;
-                stream_weights(p, smem_base, bar_full, bar_empty, rs, p.wblob + st.w_off, st.n_chunks,
-                               st.slices_per_chunk * st.n * 32);
-                if (st.has_res)
-                    stream_weights(p, smem_base, bar_full, bar_empty, rs, p.wblob + st.wres_off, st.res_chunks,
-                                   st.res_slices_per_chunk * st.n * 32);
+            const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
+            const uint16_t* wblob = p.wblob;
+            int cc = 0;
+            for (int i = 0; i < n_steps; ++i) {
+                if (!p.st[i].has_conv) continue;
+                const int n = p.st[i].n;
+                stream_weights(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, wblob + p.st[i].w_off,
+                               p.st[i].slices, p.st[i].slices_per_chunk, n);
+                if (p.st[i].has_res)
+                    stream_weights(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, wblob + p.st[i].wres_off,
+                                   p.st[i].res_slices, p.st[i].res_slices_per_chunk, n);
             }
         }
     } else if (warp == 5) {
-        // ============================ MMA issuer ============================
-        if (lane == 0) {
-            RingState rs{0};
-            if (p.n_loads > 0) mbar_wait(bar_load, 0);
-            for (int i = 0; i < p.n_steps; ++i) {
-                const ChainStep& st = p.st[i];
+        // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
+        {
+            IssueCtx x;
+            x.tmem_base = tmem_base; x.bar_full = bar_full; x.bar_empty = bar_empty;
+            x.ring_lo = (smem_base + p.ring_off) >> 4; x.ring_slot16 = (uint32_t)p.ring_slot_bytes >> 4;
+            x.ones_lo = (smem_base + ones_off) >> 4;
+            x.plane16 = plane_bytes >> 4;
+            x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
+            x.desc_hi_ones = (128u >> 4) | (1u << 14);
+            x.n_ring = n_ring; x.fmt = fmt; x.n_mtiles = geo.n_mtiles; x.Wp = geo.Wp; x.cc = 0;
+            for (int t = 0; t < 4; ++t) x.row0[t] = t < geo.n_mtiles ? tile_row0(geo, t) : 0;
+            if (n_loads > 0) mbar_wait(bar_load, 0);
+            for (int i = 0; i < n_steps; ++i) {
                 if (i > 0) mbar_wait(bar_epi, (i - 1) & 1);
                 tc_fence_after();
-                if (st.has_conv) {
-                    issue_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, st.a0_off, st.a0_ncb, st.a1_off, st.a1_ncb,
-                               st.ksize, st.n, st.acc_col, st.n_chunks, st.slices_per_chunk);
-                    if (st.has_res)
-                        issue_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, st.a0_off, st.a0_ncb, st.a1_off, st.a1_ncb,
-                                   1, st.n, st.res_col, st.res_chunks, st.res_slices_per_chunk);
-                    umma_commit(bar_mma);
+                if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
+                if (p.st[i].has_conv) {
+                    ConvIssue c;
+                    c.a0_lo = (smem_base + p.st[i].a0_off) >> 4; c.a1_lo = (smem_base + p.st[i].a1_off) >> 4;
+                    c.a0_pairs = p.st[i].a0_ncb >> 1; c.a1_pairs = p.st[i].a1_ncb >> 1;
+                    c.ksize = p.st[i].ksize; c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
+                    c.S = p.st[i].slices_per_chunk;
+                    issue_conv(x, c);
+                    if (p.st[i].has_res) {
+                        c.ksize = 1; c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
+                        issue_conv(x, c);
+                    }
+                    if (dbg && lane == 0) dbg[i * 8 + 1] = clock64();
+                    if (elect_one()) umma_commit(bar_mma);
                 } else {
-                    mbar_arrive(bar_mma);
+                    if (elect_one()) mbar_arrive(bar_mma);
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -243,94 +310,120 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
         const int r = warp * 32 + lane;                       // row inside every M tile == TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);
-        float2* partial = rowstat + p.n_mtiles * 128 * 8;
+        float2* partial = rowstat + geo.n_mtiles * 128 * p.g_max;
         float2* stat = partial + EPI_THREADS;
-        const Ctrl* ctrl = p.ctrl;
-        const int HW = p.H * p.W;
-        if (p.n_loads > 0) mbar_wait(bar_load, 0);
-        for (int i = 0; i < p.n_steps; ++i) {
-            const ChainStep& st = p.st[i];
+        float2* coef = stat + EPI_THREADS;                    // [nb][C] (scale, offset)
+        float* cpar = reinterpret_cast<float*>(coef + p.coef_n);   // small per-step constants (init / final conv weights)
+        Ctrl* ctrl = p.ctrl;
+        const float* fblob = p.fblob;
+        const int HW = geo.H * geo.W, film_dim = p.film_dim;
+        void* gt[CH_MAX_GT];
+#pragma unroll
+        for (int i = 0; i < CH_MAX_GT; ++i) gt[i] = p.gt[i];
+        const int step_idx = ctrl->step;
+        const Stage sg = ctrl->stages[step_idx];
+        const int film_per_sample = ctrl->film_per_sample;
+        const float* film_tab = ctrl->film;
+        if (n_loads > 0) mbar_wait(bar_load, 0);
+
+        for (int i = 0; i < n_steps; ++i) {
+            // ---- step parameters into registers
+            const int epi = p.st[i].epi, C = p.st[i].C, acc_col = p.st[i].acc_col, res_col = p.st[i].res_col;
+            const int res_mode = p.st[i].res_mode, res_slot_off = p.st[i].res_slot_off;
+            const int is_final = p.st[i].final, pn_g = p.st[i].pn_g;
+            OutDst od;
+            od.slot_off = p.st[i].out_slot_off; od.ncb = C >> 3;
+            od.g = p.st[i].out_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_g]) : nullptr;
+            od.g_un = p.st[i].out_un_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_un_g]) : nullptr;
+            od.g_up = p.st[i].out_up_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_up_g]) : nullptr;
+            // small constants staged while the MMAs of this step run
+            if (epi == CE_INIT) {
+                const float* w = fblob + p.init_w_off;
+                const float* bias = fblob + p.init_b_off;
+                const int cin0 = p.cin0;
+                for (int k = r; k < C * cin0; k += EPI_THREADS) cpar[k] = w[k];
+                for (int k = r; k < C; k += EPI_THREADS) cpar[C * cin0 + k] = bias[k];
+                epi_sync();
+            } else if (is_final) {
+                const float* w = fblob + p.final_w_off;
+                const float* bias = fblob + p.final_b_off;
+                const int nch = p.channels, dim = p.dim;
+                for (int k = r; k < nch * dim; k += EPI_THREADS) cpar[k] = w[k];
+                for (int k = r; k < nch; k += EPI_THREADS) cpar[nch * dim + k] = bias[k];
+            }
             mbar_wait(bar_mma, i & 1);
             tc_fence_after();
-            const int C = st.C;
-            if (st.epi == CE_INIT) {
+            if (dbg && r == 0) dbg[i * 8 + 2] = clock64();
+
+            if (epi == CE_INIT) {
                 // ---- init_conv 1x1 from the NCHW fp32 integrator state (unet.py:295)
                 const float* xs = ctrl->xs;
-                const float* w = p.fblob + p.init_w_off;
-                const float* bias = p.fblob + p.init_b_off;
-                for (int t = 0; t < p.n_mtiles; ++t) {
-                    const RowInfo ri = chain_row(p, t, r, b0);
+                const int cin0 = p.cin0;
+                for (int t = 0; t < geo.n_mtiles; ++t) {
+                    const RowInfo ri = make_row(geo, t, r, b0);
                     if (!ri.valid) continue;
                     const int b = b0 + ri.s;
                     float xin[16];
-                    for (int ci = 0; ci < p.cin0; ++ci) xin[ci] = xs[((size_t)b * p.cin0 + ci) * HW + ri.px];
+                    for (int ci = 0; ci < cin0; ++ci) xin[ci] = xs[((size_t)b * cin0 + ci) * HW + ri.px];
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float a = 0.f;
-                            for (int ci = 0; ci < p.cin0; ++ci) a = fmaf(xin[ci], w[(c16 + j) * p.cin0 + ci], a);
-                            v[j] = a + bias[c16 + j];
+                            float a = cpar[C * cin0 + c16 + j];
+                            for (int ci = 0; ci < cin0; ++ci) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
+                            v[j] = a;
                         }
-                        write_outputs(p, st, smem, ri, b, c16, v);
+                        write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
                     }
                 }
-            } else if (st.epi == CE_BIAS) {
-                // ---- conv + bias (+ residual from a shared-memory slot)
-                const float* bias = p.fblob + st.bias_off;
-                for (int t = 0; t < p.n_mtiles; ++t) {
-                    const RowInfo ri = chain_row(p, t, r, b0);
+            } else if (epi == CE_BIAS) {
+                // ---- conv (+bias via the GEMM) (+ residual from a shared-memory slot)
+                for (int t = 0; t < geo.n_mtiles; ++t) {
+                    const RowInfo ri = make_row(geo, t, r, b0);
                     const int b = b0 + ri.s;
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16];
-                        tmem_ld16(tlane + (uint32_t)(st.acc_col + t * C + c16), v);
+                        tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
                         if (!ri.valid) continue;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += bias[c16 + j];
-                        if (st.res_mode == 2) {
+                        if (res_mode == 2) {
                             float rr[16];
-                            const uint8_t* src = smem + st.res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
-                            unpack8(*reinterpret_cast<const uint4*>(src), rr, p.fmt);
-                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, p.fmt);
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
+                            unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += rr[j];
                         }
-                        write_outputs(p, st, smem, ri, b, c16, v);
+                        write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
                     }
                 }
             } else {
-                // ---- conv + bias -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
-                const int G = st.groups, cpg = C / G;
-                const float* bias = p.fblob + st.bias_off;
-                const float* gamma = p.fblob + st.gamma_off;
-                const float* beta = p.fblob + st.beta_off;
+                // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
+                const int G = p.st[i].groups, cpg = C / G, silu = p.st[i].silu, film_off = p.st[i].film_off;
                 // pass 1: per-row (sum, sumsq) per group
-                for (int t = 0; t < p.n_mtiles; ++t) {
-                    const RowInfo ri = chain_row(p, t, r, b0);
+                for (int t = 0; t < geo.n_mtiles; ++t) {
+                    const RowInfo ri = make_row(geo, t, r, b0);
                     float2* rs_row = rowstat + (size_t)(t * 128 + r) * G;
                     if (cpg >= 16) {
-                        for (int g = 0; g < G; ++g) {
+                        for (int gi = 0; gi < G; ++gi) {
                             float sx = 0.f, sq = 0.f;
-                            for (int c16 = g * cpg; c16 < (g + 1) * cpg; c16 += 16) {
+                            for (int c16 = gi * cpg; c16 < (gi + 1) * cpg; c16 += 16) {
                                 float v[16];
-                                tmem_ld16(tlane + (uint32_t)(st.acc_col + t * C + c16), v);
+                                tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) { const float x = v[j] + bias[c16 + j]; sx += x; sq += x * x; }
+                                for (int j = 0; j < 16; ++j) { sx += v[j]; sq = fmaf(v[j], v[j], sq); }
                             }
-                            rs_row[g] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                            rs_row[gi] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                         }
                     } else {
                         for (int c16 = 0; c16 < C; c16 += 16) {
                             float v[16];
-                            tmem_ld16(tlane + (uint32_t)(st.acc_col + t * C + c16), v);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += bias[c16 + j];
+                            tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
                             if (cpg == 4) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) { const float x = v[q * 4 + j]; sx += x; sq += x * x; }
+                                    for (int j = 0; j < 4; ++j) { const float xv = v[q * 4 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
                                     rs_row[(c16 >> 2) + q] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             } else {   // cpg == 8
@@ -338,144 +431,160 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                                 for (int q = 0; q < 2; ++q) {
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) { const float x = v[q * 8 + j]; sx += x; sq += x * x; }
+                                    for (int j = 0; j < 8; ++j) { const float xv = v[q * 8 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
                                     rs_row[(c16 >> 3) + q] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             }
                         }
                     }
                 }
-                reduce_stats(p, rowstat, partial, stat, G, (float)(cpg * HW), r);
-                // pass 2: normalise, modulate, activate, add residual, write
-                const Stage sg = ctrl->stages[ctrl->step];
-                for (int t = 0; t < p.n_mtiles; ++t) {
+                if (dbg && r == 0) dbg[i * 8 + 3] = clock64();
+                reduce_stats(geo, rowstat, partial, stat, G, (float)(cpg * HW), r);
+                // collapse GroupNorm affine and FiLM into one (scale, offset) per (sample, channel)
+                {
+                    const float* gamma = fblob + p.st[i].gamma_off;
+                    const float* beta = fblob + p.st[i].beta_off;
+                    for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
+                        const int s = idx / C, c = idx - s * C;
+                        const float2 ms = stat[s * G + c / cpg];
+                        float a = ms.y * gamma[c], bb = beta[c] - ms.x * a;
+                        if (film_off >= 0 && b0 + s < geo.B) {
+                            const int row = film_per_sample ? (b0 + s) : sg.film_row;
+                            const float* film = film_tab + (size_t)row * film_dim + film_off;
+                            const float sc = film[c] + 1.0f, sh = film[C + c];      // x*(scale+1)+shift, unet.py:70
+                            a *= sc; bb = bb * sc + sh;
+                        }
+                        coef[idx] = make_float2(a, bb);
+                    }
+                }
+                epi_sync();
+                if (dbg && r == 0) dbg[i * 8 + 4] = clock64();
+                // pass 2: y = x*scale + offset, SiLU, + residual, write
+                for (int t = 0; t < geo.n_mtiles; ++t) {
                     float kacc[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) kacc[j] = 0.f;
-                    const RowInfo ri = chain_row(p, t, r, b0);
+                    const RowInfo ri = make_row(geo, t, r, b0);
                     const int b = b0 + ri.s;
-                    const float* film = nullptr;
-                    if (st.film_off >= 0 && ri.valid) {
-                        const int row = ctrl->film_per_sample ? b : sg.film_row;
-                        film = ctrl->film + (size_t)row * p.film_dim + st.film_off;
-                    }
+                    const float2* cf = coef + (ri.valid ? ri.s : 0) * C;
                     float psx = 0.f, psq = 0.f;
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16], rr[16];
-                        tmem_ld16(tlane + (uint32_t)(st.acc_col + t * C + c16), v);
-                        if (st.res_mode == 1) tmem_ld16(tlane + (uint32_t)(st.res_col + t * C + c16), rr);
+                        tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
+                        if (res_mode == 1) tmem_ld16(tlane + (uint32_t)(res_col + t * C + c16), rr);
                         if (!ri.valid) continue;
-                        if (st.res_mode == 1) {
-                            const float* rb = p.fblob + st.res_bias_off;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) rr[j] += rb[c16 + j];
-                        } else if (st.res_mode == 2) {
-                            const uint8_t* src = smem + st.res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
-                            unpack8(*reinterpret_cast<const uint4*>(src), rr, p.fmt);
-                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, p.fmt);
+                        if (res_mode == 2) {
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
+                            unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const int c = c16 + j;
-                            const float2 ms = stat[ri.s * G + c / cpg];
-                            float y = (v[j] + bias[c] - ms.x) * ms.y * gamma[c] + beta[c];
-                            if (film) y = y * (film[c] + 1.0f) + film[C + c];
-                            if (st.silu) y = y / (1.0f + __expf(-y));
-                            if (st.res_mode) y += rr[j];
+                            const float2 ab = cf[c16 + j];
+                            float y = fmaf(v[j], ab.x, ab.y);
+                            if (silu) y = __fdividef(y, 1.0f + __expf(-y));
+                            if (res_mode) y += rr[j];
                             v[j] = y;
-                            psx += y; psq += y * y;
+                            psx += y; psq = fmaf(y, y, psq);
                         }
-                        if (st.final) {
-                            const float* fw = p.fblob + p.final_w_off;
+                        if (is_final) {
+                            const int nch = p.channels, dim = p.dim;
 #pragma unroll
                             for (int co = 0; co < 16; ++co) {
-                                if (co < p.channels) {
+                                if (co < nch) {
                                     float a = kacc[co];
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) a = fmaf(v[j], fw[co * p.dim + c16 + j], a);
+                                    for (int j = 0; j < 16; ++j) a = fmaf(v[j], cpar[co * dim + c16 + j], a);
                                     kacc[co] = a;
                                 }
                             }
                         } else {
-                            write_outputs(p, st, smem, ri, b, c16, v);
+                            write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
                         }
                     }
-                    if (st.pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = ri.valid ? make_float2(psx, psq) : make_float2(0.f, 0.f);
-                    if (st.final && ri.valid) {
+                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = ri.valid ? make_float2(psx, psq) : make_float2(0.f, 0.f);
+                    if (is_final && ri.valid) {
                         // ---- final_conv bias + RK4 / Euler / CFG stage update (sampling.py:43-48,69-74)
-                        Ctrl* c = p.ctrl;
-                        const float* fb = p.fblob + p.final_b_off;
-                        const size_t plane = (size_t)p.B * p.channels * HW;
+                        const int nch = p.channels, dim = p.dim;
+                        const size_t plane = (size_t)geo.B * nch * HW;
 #pragma unroll
                         for (int co = 0; co < 16; ++co) {
-                            if (co >= p.channels) continue;
-                            float k = kacc[co] + fb[co];
-                            const size_t o = ((size_t)b * p.channels + co) * HW + ri.px;
-                            if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(c->cfg, __fsub_rn(c->vcond[o], k)));
-                            if (c->vtrace && sg.eval_idx >= 0) c->vtrace[(size_t)sg.eval_idx * plane + o] = k;
+                            if (co >= nch) continue;
+                            float k = kacc[co] + cpar[nch * dim + co];
+                            const size_t o = ((size_t)b * nch + co) * HW + ri.px;
+                            if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(ctrl->cfg, __fsub_rn(ctrl->vcond[o], k)));
+                            if (ctrl->vtrace && sg.eval_idx >= 0) ctrl->vtrace[(size_t)sg.eval_idx * plane + o] = k;
                             switch (sg.kind) {
-                                case ST_PLAIN: c->vout[o] = k; break;
-                                case ST_CFG_COND: c->vcond[o] = k; break;
+                                case ST_PLAIN: ctrl->vout[o] = k; break;
+                                case ST_CFG_COND: ctrl->vcond[o] = k; break;
                                 case ST_RK1:
-                                    c->acc[o] = k;
-                                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
+                                    ctrl->acc[o] = k;
+                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
                                     break;
                                 case ST_RK2:
-                                    c->acc[o] = __fadd_rn(c->acc[o], __fmul_rn(2.0f, k));
-                                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
+                                    ctrl->acc[o] = __fadd_rn(ctrl->acc[o], __fmul_rn(2.0f, k));
+                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
                                     break;
                                 case ST_RK3:
-                                    c->acc[o] = __fadd_rn(c->acc[o], __fmul_rn(2.0f, k));
-                                    c->xs[o] = __fadd_rn(c->y[o], __fmul_rn(sg.dt, k));
+                                    ctrl->acc[o] = __fadd_rn(ctrl->acc[o], __fmul_rn(2.0f, k));
+                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(sg.dt, k));
                                     break;
                                 case ST_RK4: {
-                                    const float yn = __fadd_rn(c->y[o], __fmul_rn(sg.dt6, __fadd_rn(c->acc[o], k)));
-                                    c->y[o] = yn; c->xs[o] = yn;
+                                    const float yn = __fadd_rn(ctrl->y[o], __fmul_rn(sg.dt6, __fadd_rn(ctrl->acc[o], k)));
+                                    ctrl->y[o] = yn; ctrl->xs[o] = yn;
                                 } break;
                                 case ST_EULER: {
-                                    const float yn = __fadd_rn(c->y[o], __fmul_rn(k, sg.dt));
-                                    c->y[o] = yn; c->xs[o] = yn;
+                                    const float yn = __fadd_rn(ctrl->y[o], __fmul_rn(k, sg.dt));
+                                    ctrl->y[o] = yn; ctrl->xs[o] = yn;
                                 } break;
                                 default: break;
                             }
                         }
                     }
                 }
-                if (st.pn_g >= 0) {
+                if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
-                    reduce_stats(p, rowstat, partial, stat, 1, (float)(C * HW), r);
-                    const float* g2 = p.fblob + st.pn_gamma_off;
-                    const float* b2 = p.fblob + st.pn_beta_off;
-                    for (int t = 0; t < p.n_mtiles; ++t) {
-                        const RowInfo ri = chain_row(p, t, r, b0);
+                    reduce_stats(geo, rowstat, partial, stat, 1, (float)(C * HW), r);
+                    const float* g2 = fblob + p.st[i].pn_gamma_off;
+                    const float* b2 = fblob + p.st[i].pn_beta_off;
+                    for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
+                        const int s = idx / C, c = idx - s * C;
+                        const float2 ms = stat[s];
+                        const float a = ms.y * g2[c];
+                        coef[idx] = make_float2(a, b2[c] - ms.x * a);
+                    }
+                    epi_sync();
+                    uint4* dst = reinterpret_cast<uint4*>(gt[pn_g]);
+                    const int out_slot = od.slot_off;
+                    for (int t = 0; t < geo.n_mtiles; ++t) {
+                        const RowInfo ri = make_row(geo, t, r, b0);
                         if (!ri.valid) continue;
                         const int b = b0 + ri.s;
-                        const float2 ms = stat[ri.s];
+                        const float2* cf = coef + ri.s * C;
                         for (int cb = 0; cb < (C >> 3); ++cb) {
-                            float x[8];
-                            unpack8(*reinterpret_cast<const uint4*>(smem + st.out_slot_off + (uint32_t)cb * plane_bytes +
-                                                                    (uint32_t)ri.pp * 16u), x, p.fmt);
+                            float xv[8];
+                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u), xv, fmt);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = (x[j] - ms.x) * ms.y * g2[cb * 8 + j] + b2[cb * 8 + j];
-                            reinterpret_cast<uint4*>(p.gt[st.pn_g])[(size_t)(cb * p.B + b) * HW + ri.px] = pack8(x, p.fmt);
+                            for (int j = 0; j < 8; ++j) { const float2 ab = cf[cb * 8 + j]; xv[j] = fmaf(xv[j], ab.x, ab.y); }
+                            dst[(size_t)(cb * geo.B + b) * HW + ri.px] = pack8(xv, fmt);
                         }
                     }
                 }
-                if (st.final) {
+                if (is_final) {
                     // the last CTA to finish advances the stage counter (every CTA has read ctrl->step by now)
                     epi_sync();
                     if (r == 0) {
-                        Ctrl* c = p.ctrl;
                         __threadfence();
-                        const int done = atomicAdd(&c->done_ctr, 1);
+                        const int done = atomicAdd(&ctrl->done_ctr, 1);
                         if (done == (int)gridDim.x - 1) {
-                            c->done_ctr = 0;
-                            c->step = c->step + 1;
+                            ctrl->done_ctr = 0;
+                            ctrl->step = step_idx + 1;
                             __threadfence();
                         }
                     }
                 }
             }
+            if (dbg && r == 0) dbg[i * 8 + 5] = clock64();
             fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
             tc_fence_before();
             mbar_arrive(bar_epi);
@@ -483,7 +592,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8 + 1] = clock64();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 cudaError_t attn_configure();

@@ -38,21 +38,25 @@ __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t sme
                                           uint32_t bar_empty, RingA& rs, uint32_t a_off, uint32_t a_plane, int n, int col,
                                           int n_chunks, int S) {
     const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
+    const int n_ring = p.n_ring, n_mtiles = p.n_mtiles;
+    const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
     for (int ci = 0; ci < n_chunks; ++ci) {
-        const int slot = rs.cc % p.n_ring;
-        mbar_wait(bar_full + 8 * slot, (rs.cc / p.n_ring) & 1);
+        const int slot = rs.cc % n_ring;
+        mbar_wait(bar_full + 8 * slot, (rs.cc / n_ring) & 1);
         tc_fence_after();
-        const uint32_t bstage = smem_base + p.ring_off + slot * p.ring_slot_bytes;
+        const uint32_t bstage = smem_base + ring_off + slot * ring_slot_bytes;
         for (int s = 0; s < S; ++s) {
             const int ks = ci * S + s;
             const uint64_t bdesc = make_smem_desc(bstage + (uint32_t)s * (uint32_t)n * 32u, (uint32_t)n * 16u, 128u);
-            for (int t = 0; t < p.n_mtiles; ++t) {
-                const uint32_t a_addr = smem_base + a_off + (uint32_t)(2 * ks) * a_plane + (uint32_t)(t * 128) * 16u;
-                umma_bf16(tmem_base + (uint32_t)(col + t * n), make_smem_desc(a_addr, a_plane, 128u), bdesc, idesc,
-                          ks > 0 ? 1u : 0u);
-            }
+            if (elect_one())
+                for (int t = 0; t < n_mtiles; ++t) {
+                    const uint32_t a_addr = smem_base + a_off + (uint32_t)(2 * ks) * a_plane + (uint32_t)(t * 128) * 16u;
+                    umma_bf16(tmem_base + (uint32_t)(col + t * n), make_smem_desc(a_addr, a_plane, 128u), bdesc, idesc,
+                              ks > 0 ? 1u : 0u);
+                }
         }
-        umma_commit(bar_empty + 8 * slot);
+        if (elect_one()) umma_commit(bar_empty + 8 * slot);
+        __syncwarp();
         ++rs.cc;
     }
 }
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wo_off, p.o_chunks, o_bytes);
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform; one elected lane issues the tcgen05 instructions
             RingA rs{0};
             mbar_wait(bar_load, 0);
             tc_fence_after();
@@ -133,44 +137,60 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_k, p.qkv_chunks, p.qkv_S);
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_v, p.qkv_chunks, p.qkv_S);
             if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
-            umma_commit(bar_mma);
+            if (elect_one()) umma_commit(bar_mma);
+            __syncwarp();
             int ph = 0;
             if (!p.full) {
                 // ---- phase 1: context per sample (both operands MN-major, K = pixels), then the Q convolution
                 mbar_wait(bar_epi, ph & 1); ++ph;
                 tc_fence_after();
                 const uint32_t idesc_ctx = make_idesc16(128, 144, p.fmt, 1, 1);
-                for (int s = 0; s < p.nb; ++s)
-                    for (int ks = 0; ks < n_pad / 16; ++ks) {
-                        const uint32_t roff = (uint32_t)(s * n_pad + ks * 16) * 16u;
-                        umma_bf16(tmem_base + (uint32_t)(p.col_ctx + s * 144), make_smem_desc(smem_base + p.p_off + roff, 128u, plane),
-                                  make_smem_desc(smem_base + p.v_off + roff, 128u, plane), idesc_ctx, ks > 0 ? 1u : 0u);
-                    }
+                {
+                    const int nb = p.nb, col_ctx = p.col_ctx;
+                    const uint32_t p_off = p.p_off, v_off = p.v_off;
+                    if (elect_one())
+                        for (int s = 0; s < nb; ++s)
+                            for (int ks = 0; ks < n_pad / 16; ++ks) {
+                                const uint32_t roff = (uint32_t)(s * n_pad + ks * 16) * 16u;
+                                umma_bf16(tmem_base + (uint32_t)(col_ctx + s * 144), make_smem_desc(smem_base + p_off + roff, 128u, plane),
+                                          make_smem_desc(smem_base + v_off + roff, 128u, plane), idesc_ctx, ks > 0 ? 1u : 0u);
+                            }
+                    __syncwarp();
+                }
                 attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
-                umma_commit(bar_mma);
+                if (elect_one()) umma_commit(bar_mma);
+                __syncwarp();
                 // ---- phase 2: out[n][(h,e)] per (sample, tile, head)
                 mbar_wait(bar_epi, ph & 1); ++ph;
                 tc_fence_after();
                 const uint32_t idesc_out = make_idesc16(128, 32, p.fmt, 0, 0);
-                for (int s = 0; s < p.nb; ++s)
-                    for (int t = 0; t < mtS; ++t)
-                        for (int h = 0; h < 4; ++h)
-                            for (int k = 0; k < 2; ++k) {
-                                const uint32_t a_addr = smem_base + p.p_off + (uint32_t)(4 * h + 2 * k) * plane +
-                                                        (uint32_t)(s * n_pad + t * 128) * 16u;
-                                const uint32_t b_addr = smem_base + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)k * 1024u;
-                                umma_bf16(tmem_base + (uint32_t)(p.col_out + (s * mtS + t) * 128 + h * 32),
-                                          make_smem_desc(a_addr, plane, 128u), make_smem_desc(b_addr, 512u, 128u), idesc_out,
-                                          k > 0 ? 1u : 0u);
-                            }
-                umma_commit(bar_mma);
+                {
+                    const int nb = p.nb, col_out = p.col_out;
+                    const uint32_t p_off = p.p_off, ct_off = p.ct_off;
+                    if (elect_one()) {
+                        for (int s = 0; s < nb; ++s)
+                            for (int t = 0; t < mtS; ++t)
+                                for (int h = 0; h < 4; ++h)
+                                    for (int k = 0; k < 2; ++k) {
+                                        const uint32_t a_addr = smem_base + p_off + (uint32_t)(4 * h + 2 * k) * plane +
+                                                                (uint32_t)(s * n_pad + t * 128) * 16u;
+                                        const uint32_t b_addr = smem_base + ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)k * 1024u;
+                                        umma_bf16(tmem_base + (uint32_t)(col_out + (s * mtS + t) * 128 + h * 32),
+                                                  make_smem_desc(a_addr, plane, 128u), make_smem_desc(b_addr, 512u, 128u), idesc_out,
+                                                  k > 0 ? 1u : 0u);
+                                    }
+                        umma_commit(bar_mma);
+                    }
+                    __syncwarp();
+                }
             }
             // ---- last phase: to_out convolution over the O slot
             mbar_wait(bar_epi, ph & 1); ++ph;
             tc_fence_after();
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, p.col_proj,
                       p.o_chunks, p.o_S);
-            umma_commit(bar_mma);
+            if (elect_one()) umma_commit(bar_mma);
+            __syncwarp();
         }
     } else {
         const int r = warp * 32 + lane;

@@ -94,6 +94,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 }
 
 
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom): keeps the surrounding code warp-uniform so
+// descriptors stay in uniform registers instead of being round-tripped through R2UR/ELECT loops
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

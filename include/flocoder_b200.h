@@ -141,6 +141,9 @@ FLO_API int flo_unet_op_info(flo_unet_t* h, int index, int* kind, double* flops_
 /* Runs one forward at batch B op by op (no graph) `reps` times with a CUDA event around every kernel on
  * `stream` and returns the best duration of each op in milliseconds (ms_per_op: HOST array, one per op). */
 FLO_API int flo_unet_profile_ops(flo_unet_t* h, int B, int reps, float* ms_per_op, void* stream);
+/* Debug: SM-clock timeline (clock64) of CTA 0 of fused stage `stage` from the last forward at batch B; needs the
+ * environment variable FLO_TIMELINE=1 when the batch plan is created.  out128: HOST array of 128 int64. */
+FLO_API int flo_unet_read_timeline(flo_unet_t* h, int B, int stage, long long* out128);
 /* Kernel launches issued per forward pass (graph nodes) and total since creation. */
 FLO_API int flo_unet_launches_per_forward(flo_unet_t* h, int B);
 FLO_API int64_t flo_unet_launch_count(flo_unet_t* h);

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from flocoder_b200.unet import Unet  # noqa: E402
 
-KINDS = ["init", "conv", "gn", "linattn", "midattn", "final"]
+KINDS = ["init", "conv", "gn", "linattn", "midattn", "final", "chain", "attn"]
 
 
 def main():

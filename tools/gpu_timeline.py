@@ -1,0 +1,34 @@
+"""clock64 timeline of CTA 0 of every fused chain stage (developer tool): python tools/gpu_timeline.py bf16 256"""
+import os
+import sys
+
+import torch
+
+os.environ["FLO_TIMELINE"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flocoder_b200.unet import Unet  # noqa: E402
+
+cd, B = sys.argv[1], int(sys.argv[2])
+torch.manual_seed(1234)
+m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, compute_dtype=cd).cuda().eval()
+x = torch.randn(B, 4, 16, 16, device="cuda")
+t = torch.full((B,), 300.0, device="cuda")
+for _ in range(3):
+    m(x, t)
+torch.cuda.synchronize()
+eng = m.engine(16, 16)
+names = eng.op_names()
+for i, name in enumerate(names):
+    tl = eng.read_timeline(B, i)
+    start, end = tl[64], tl[65]
+    if start == 0:
+        continue
+    print(f"== stage {i} {name}: kernel body {end - start} cycles")
+    for s in range(8):
+        row = tl[s * 8: s * 8 + 8]
+        if row[2] == 0:
+            continue
+        print(f"   step {s}: mma_start +{row[0]-start:7d} issue {row[1]-row[0] if row[1] else 0:6d} | epi_start +{row[2]-start:7d} "
+              f"(after issue {row[2]-row[1] if row[1] else 0:6d}) pass1 {row[3]-row[2] if row[3] else 0:6d} reduce {row[4]-row[3] if row[4] else 0:6d} "
+              f"pass2 {row[5]-(row[4] if row[4] else row[2]):6d}")
