@@ -185,6 +185,9 @@ def run_gpu_arm(args):
     B = args.batch
     torch.manual_seed(1234)
     model = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=N_CLASSES, compute_dtype=args.dtype).to(dev).eval()
+    if args.layerwise:
+        from flocoder_b200 import _lib
+        model.engine_flags = _lib.FLO_FLAG_LAYERWISE
     eng = model.engine(LATENT[1], LATENT[2])
     gen = torch.Generator().manual_seed(5678 + rank)
     x0_host = torch.randn(B, *LATENT, generator=gen).pin_memory()
@@ -249,31 +252,35 @@ def run_gpu_arm(args):
         return
 
     peaks = load_peaks()
-    # dominant kernel class: the tcgen05 implicit-GEMM convolution.  Per-launch durations measured live with CUDA
-    # events (one forward, op by op, best of 5); achieved = algorithmic conv FLOPs of those launches / their time.
+    # Per-launch durations measured live with CUDA events on the launching stream (one forward, launch by launch,
+    # best of 5); achieved = ALGORITHMIC conv FLOPs of the dominant kernel's launches / their summed duration.
+    KIND = {0: "k_init_conv", 1: "k_conv_umma (tcgen05 implicit-GEMM conv)", 2: "k_gn (GroupNorm+FiLM+SiLU+residual pass)",
+            3: "k_linattn", 4: "k_midattn", 5: "k_final",
+            6: "k_chain (fused ResnetBlock-chain stage: tcgen05 implicit-GEMM convs + GroupNorm/FiLM/SiLU/residual epilogues)",
+            7: "k_attn (fused attention block: tcgen05 q/k/v/out convs + context/output contractions)"}
     info = eng.op_info()
     ms_ops = eng.profile_ops(B, reps=5)
-    conv = [(i, fl) for i, (_, kind, fl, _) in enumerate(info) if kind == 1]
-    conv_ms = sum(ms_ops[i] for i, _ in conv)
-    conv_flop = sum(fl for _, fl in conv) * B
-    gn = [(i, by) for i, (_, kind, _, by) in enumerate(info) if kind == 2]
-    gn_ms = sum(ms_ops[i] for i, _ in gn)
-    gn_bytes = sum(by for _, by in gn) * B
+    groups = {}
+    for (name, kind, fl, by), t in zip(info, ms_ops):
+        g = groups.setdefault(kind, {"n": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
+        g["n"] += 1; g["ms"] += t; g["flop"] += fl * B; g["bytes"] += by * B
     fwd_ms = sum(ms_ops)
-    achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    peak = peaks["bf16_tflops"] if args.dtype == "bf16" else None
+    dom = max((k for k in groups if k in (1, 6, 7)), key=lambda k: groups[k]["ms"])
+    gd = groups[dom]
+    achieved = gd["flop"] / (gd["ms"] * 1e-3) / 1e12 if gd["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops"] if args.dtype in ("bf16", "fp16") else None
     roofline = {
-        "bound": "tensor", "kernel": "k_conv_umma (tcgen05 implicit-GEMM conv, %d launches/forward)" % len(conv),
+        "bound": "tensor", "kernel": f"{KIND[dom]}, {gd['n']} launches/forward",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if peak else None, "traffic": None,
         "peak_source": f"{peaks['source']} burst bf16 cuBLAS (kernel timed alone)",
-        "share_of_forward": conv_ms / fwd_ms if fwd_ms > 0 else None,
+        "share_of_forward": gd["ms"] / fwd_ms if fwd_ms > 0 else None,
         "end_to_end_tensor_frac_of_sustained": value / world * NFE * CONV_FLOP_PER_SAMPLE_FORWARD / 1e12 / peaks["bf16_tflops_sustained"],
-        "gn_pass": {"kernel": "k_gn (GroupNorm+FiLM+SiLU+residual, %d launches/forward)" % len(gn),
-                    "achieved_gbs": gn_bytes / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0, "peak_gbs": peaks["hbm_gbs"],
-                    "frac": (gn_bytes / (gn_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if gn_ms > 0 else None,
-                    "share_of_forward": gn_ms / fwd_ms if fwd_ms > 0 else None},
         "forward_ms_sum_of_kernels": fwd_ms,
+        "kernels": {KIND[k].split(" ")[0]: {"launches": g["n"], "ms": g["ms"], "conv_tflops": g["flop"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0,
+                                            "gbs": g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] else 0.0,
+                                            "hbm_frac": g["bytes"] / (g["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"] if g["ms"] else 0.0}
+                    for k, g in groups.items()},
     }
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -285,8 +292,8 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(world, B, args.dtype),
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.dtype], "data": "synthetic",
+        "config": dict(workload_config(world, B, args.dtype), kernels="layerwise" if args.layerwise else "fused-stage"),
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
                    "samples": clk.get("samples", 0)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 4 * LATENT[0] * LATENT[1] * LATENT[2],
@@ -308,7 +315,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--layerwise", action="store_true", help="one kernel per layer instead of the fused stage kernels")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
