@@ -114,53 +114,55 @@ def run_reference_arm(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML in a background thread (spawning
+    nvidia-smi every 100 ms was measured to halve the throughput of a launch-bound step by contending for the driver)."""
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, period=0.25):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.thread, self.stop_flag = None, False
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self.thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, mx = [], set(), None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                f = [x.strip() for x in ln.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx = float(f[2])
-                except ValueError:
-                    continue
-                for n, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if self.samples:
+            sm = sorted(self.samples)
+            out.update(sm_mhz=sm[len(sm) // 2], reasons=sorted(self.reasons), samples=len(sm))
         return out
 
 

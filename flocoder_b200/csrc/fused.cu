@@ -5,7 +5,8 @@
 // through a shared-memory ring by bulk TMA copies.
 //
 // k_chain   [conv -> GroupNorm+FiLM+SiLU(+residual)]* with
-//           * the conv bias folded into the GEMM (one extra K slice: a constant "ones" A tile x a bias B tile),
+//           * the conv bias folded into the GEMM (one extra K slice: a constant "ones" A tile x a B tile holding the
+//             bias split into a 16-bit high part and a 16-bit remainder, so it is exact to ~2^-17),
 //           * the ResnetBlock 1x1 res_conv accumulated into a second TMEM region (never leaves TMEM),
 //           * GroupNorm affine, FiLM and bias collapsed per step into ONE (scale, offset) pair per
 //             (sample, channel) in shared memory, so the normalise pass is one FMA + SiLU per element,
@@ -235,9 +236,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
     {   // clear the slots the epilogues write (their halo must read as zero) and build the "ones" A tile
         const int zoff = p.zero_off, zbytes = p.zero_bytes;
         for (int i = tid * 16; i < zbytes; i += FUSED_THREADS * 16) *reinterpret_cast<uint4*>(smem + zoff + i) = make_uint4(0, 0, 0, 0);
-        const uint32_t one = pack2(1.0f, 0.f, fmt) & 0xFFFFu;
-        for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,0,0,0,0,0,0,0] per row; plane 1: zeros
-            *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? one : 0u, 0, 0, 0);
+        const uint32_t ones2 = pack2(1.0f, 1.0f, fmt);
+        for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,1,0,0,0,0,0,0] per row (bias hi + lo); plane 1: zeros
+            *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? ones2 : 0u, 0, 0, 0);
     }
     fence_proxy_async();
     tc_fence_before();

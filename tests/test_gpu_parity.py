@@ -252,9 +252,15 @@ def test_batch_slices_are_independent_and_deterministic(compute_dtype):
     again, _ = sampling.generate_latents_rk4(m, (B, 4, 16, 16), n_steps=5, source=x0)
     assert torch.equal(full, again)
     assert torch.isfinite(full).all()
+    # Slices that start on a multiple of every stage's samples-per-CTA (lcm = 96) see the same tiling -> bit-identical.
+    # Other slices group samples differently inside a CTA, which only changes fp32 summation order (1e-7); on the
+    # 16-bit paths that can flip roundings, so the bound there is the format's noise, not 1e-6.
+    part, _ = sampling.generate_latents_rk4(m, (96, 4, 16, 16), n_steps=5, source=x0[96:192])
+    assert torch.equal(part, full[96:192])
+    tol = {"fp32": 1e-6, "fp16": 5e-4, "bf16": 4e-3}[compute_dtype]
     for lo, hi in ((0, 8), (100, 131), (248, 256)):
         part, _ = sampling.generate_latents_rk4(m, (hi - lo, 4, 16, 16), n_steps=5, source=x0[lo:hi])
-        assert rel_l2(part, full[lo:hi]) <= 1e-6
+        assert rel_l2(part, full[lo:hi]) <= tol
 
 
 def test_generic_rk4_step_composes_with_our_forward(goldens):
