@@ -324,4 +324,109 @@ cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, fl
     return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// swizzled-operand micro-test + issue-rate probe: K-major SWIZZLE_{32,64,128}B operands with shifted start
+// addresses (base_offset) and non-atom-multiple group strides; also times `reps` back-to-back MMAs.
+// ------------------------------------------------------------------------------------------------
+struct Micro2Params {
+    const __nv_bfloat16* a;   // [128][K]
+    const __nv_bfloat16* b;   // [N][K]
+    float* d;                 // [128][N]
+    long long* cycles;        // [1]: SM cycles for `reps` MMA chains (issue -> commit -> barrier)
+    int N, K;
+    int layout;               // 0 none, 2 = 128B, 4 = 64B, 6 = 32B swizzle
+    int row_bytes;            // bytes per operand row (K-major): 16 (none: core-matrix rows) / 32 / 64 / 128
+    int a_sbo, a_shift, a_lbo;
+    int use_base_offset;
+    int reps;
+};
+__device__ __forceinline__ uint32_t swz(uint32_t lin, int layout) {
+    const uint32_t mask = layout == 2 ? 7u : layout == 4 ? 3u : layout == 6 ? 1u : 0u;
+    return lin ^ (((lin >> 7) & mask) << 4);
+}
+__global__ void __launch_bounds__(128) k_umma_micro2(Micro2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tslot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t a_off = 0, b_off = 96 * 1024;
+    const int kpr = p.row_bytes / 2;          // K elements per row
+    for (int idx = tid; idx < 128 * p.K; idx += 128) {
+        const int m = idx / p.K, k = idx % p.K;
+        uint32_t lin;
+        if (p.layout == 0) lin = (uint32_t)p.a_shift + (uint32_t)(k / 8) * p.a_lbo + (uint32_t)(m / 8) * p.a_sbo + (uint32_t)(m % 8) * 16u + (uint32_t)(k % 8) * 2u;
+        else lin = (uint32_t)p.a_shift + (uint32_t)(m / 8) * p.a_sbo + (uint32_t)(m % 8) * p.row_bytes + (uint32_t)(k % kpr) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(smem + a_off + swz(lin, p.layout)) = p.a[idx];
+    }
+    const uint32_t b_sbo = p.layout == 0 ? 128u : 8u * p.row_bytes, b_lbo = (uint32_t)p.N * 16u;
+    for (int idx = tid; idx < p.N * p.K; idx += 128) {
+        const int n = idx / p.K, k = idx % p.K;
+        uint32_t lin;
+        if (p.layout == 0) lin = (uint32_t)(k / 8) * b_lbo + (uint32_t)(n / 8) * 128u + (uint32_t)(n % 8) * 16u + (uint32_t)(k % 8) * 2u;
+        else lin = (uint32_t)(n / 8) * b_sbo + (uint32_t)(n % 8) * p.row_bytes + (uint32_t)(k % kpr) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(smem + b_off + swz(lin, p.layout)) = p.b[idx];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int cols = 32;
+    while (cols < p.N) cols <<= 1;
+    if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(&tslot);
+    long long t0 = 0;
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc_bf16(128, p.N);
+        const uint32_t base = smem_u32(smem);
+        const uint64_t lt = (uint64_t)p.layout << 61;
+        t0 = clock64();
+        for (int rep = 0; rep < p.reps; ++rep) {
+            for (int s = 0; s < p.K / 16; ++s) {
+                uint32_t a_addr, b_addr, a_l, b_l, a_s, b_s;
+                if (p.layout == 0) {
+                    a_addr = base + a_off + p.a_shift + s * 2 * p.a_lbo; b_addr = base + b_off + s * 2 * b_lbo;
+                    a_l = p.a_lbo; b_l = b_lbo; a_s = p.a_sbo; b_s = 128;
+                } else {
+                    a_addr = base + a_off + p.a_shift + s * 32; b_addr = base + b_off + s * 32;
+                    a_l = 16; b_l = 16; a_s = p.a_sbo; b_s = b_sbo;
+                }
+                uint64_t ad = make_smem_desc(a_addr, a_l, a_s) | lt;
+                uint64_t bd = make_smem_desc(b_addr, b_l, b_s) | lt;
+                if (p.use_base_offset) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                if (elect_one()) umma_bf16(tbase, ad, bd, idesc, (rep | s) > 0);
+            }
+        }
+        if (elect_one()) umma_commit(smem_u32(&bar));
+        __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    if (warp == 1 && lane == 0) p.cycles[0] = clock64() - t0;
+    for (int c = 0; c < p.N; c += 16) {
+        float v[16];
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c, v);
+        for (int i = 0; i < 16; ++i) p.d[(size_t)(warp * 32 + lane) * p.N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, cols);
+}
+cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, long long* cycles, int N, int K, int layout,
+                               int row_bytes, int a_sbo, int a_shift, int a_lbo, int use_base_offset, int reps, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_umma_micro2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    Micro2Params p{a, b, d, cycles, N, K, layout, row_bytes, a_sbo, a_shift, a_lbo, use_base_offset, reps};
+    k_umma_micro2<<<1, 128, 200 * 1024, s>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace flo

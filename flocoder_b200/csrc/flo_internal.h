@@ -174,6 +174,9 @@ cudaError_t simt_configure();
 cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int N, int K, int a_lbo,
                               int a_sbo, int a_shift, int b_lbo, int b_sbo, cudaStream_t s);
 
+cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, long long* cycles, int N, int K, int layout,
+                               int row_bytes, int a_sbo, int a_shift, int a_lbo, int use_base_offset, int reps, cudaStream_t s);
+
 // tiling of one convolution for the tcgen05 kernel, and the TMA map of a blocked bf16 tensor
 struct ConvShape { const char* name; int H, W, ksize, ncb0, ncb1, cout, n_tile; };
 int plan_umma(const ConvShape& shape, int B, ConvUmmaParams& p);

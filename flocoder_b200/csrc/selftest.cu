@@ -74,6 +74,44 @@ static int micro_case(Report& rep, cudaStream_t st, int N, int K, int a_lbo, int
     return 0;
 }
 
+
+static int micro2_case(Report& rep, cudaStream_t st, const char* what, int N, int K, int layout, int row_bytes, int a_sbo, int a_shift,
+                       int a_lbo, int use_bo, int reps) {
+    uint32_t seed = 777u + N * 3 + K + layout;
+    std::vector<__nv_bfloat16> a((size_t)128 * K), b((size_t)N * K);
+    for (auto& v : a) v = __float2bfloat16(rnd(seed));
+    for (auto& v : b) v = __float2bfloat16(rnd(seed));
+    __nv_bfloat16 *da, *db; float* dd; long long* dc;
+    ST_CUDA(cudaMalloc(&da, a.size() * 2)); ST_CUDA(cudaMalloc(&db, b.size() * 2));
+    ST_CUDA(cudaMalloc(&dd, (size_t)128 * N * 4)); ST_CUDA(cudaMalloc(&dc, 8));
+    ST_CUDA(cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    ST_CUDA(cudaMemset(dd, 0, (size_t)128 * N * 4));
+    ST_CUDA(launch_umma_micro2(da, db, dd, dc, N, K, layout, row_bytes, a_sbo, a_shift, a_lbo, use_bo, reps, st));
+    ST_CUDA(cudaStreamSynchronize(st));
+    std::vector<float> d((size_t)128 * N);
+    long long cyc = 0;
+    ST_CUDA(cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost));
+    ST_CUDA(cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double r = 0;
+            for (int k = 0; k < K; ++k) r += (double)__bfloat162float(a[(size_t)m * K + k]) * __bfloat162float(b[(size_t)n * K + k]);
+            r *= reps;
+            maxerr = fmax(maxerr, fabs(r - d[(size_t)m * N + n]));
+            maxref = fmax(maxref, fabs(r));
+        }
+    const bool ok = maxerr <= 2e-3 * fmax(1.0, maxref);
+    rep.text += ok ? "INFO-PASS " : "INFO-FAIL ";
+    char buf[512];
+    snprintf(buf, sizeof(buf), "umma_swizzle %-28s N=%d K=%d layout=%d row=%d sbo=%d shift=%d base_off=%d reps=%d  max|err|=%.3g max|ref|=%.3g  cycles=%lld (%.1f per MMA)\n",
+             what, N, K, layout, row_bytes, a_sbo, a_shift, use_bo, reps, maxerr, maxref, cyc, (double)cyc / (reps * (K / 16)));
+    rep.text += buf;
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dc);
+    return 0;
+}
+
 static int conv_case(Report& rep, cudaStream_t st, const char* name, int B, int H, int W, int C0, int C1, int cout,
                      int ksize, int n_tile, bool with_res) {
     const int cin = C0 + C1, taps = ksize * ksize, HW = H * W;
@@ -183,6 +221,18 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
     rc |= micro_case(rep, st, 32, 32, 2560, 128, 16 * 19);        // odd-pixel start shift
     rc |= micro_case(rep, st, 16, 32, 5184, 288, 304);            // strip mode: group stride = padded row pitch
     rc |= micro_case(rep, st, 48, 16, 2048, 128, 0);              // N multiple of 16 but not a power of two
+    // ---- informational probes (not counted as failures): swizzled operands, shifted starts, issue rate
+    micro2_case(rep, st, "none aligned rate", 128, 64, 0, 16, 128, 0, 2048, 0, 16);
+    micro2_case(rep, st, "sw128 aligned", 128, 64, 2, 128, 1024, 0, 0, 0, 1);
+    micro2_case(rep, st, "sw128 aligned rate", 128, 64, 2, 128, 1024, 0, 0, 0, 16);
+    micro2_case(rep, st, "sw128 shift3 bo=0", 128, 64, 2, 128, 1024, 3 * 128, 0, 0, 1);
+    micro2_case(rep, st, "sw128 strip sbo=2304 bo=0", 32, 64, 2, 128, 2304, 19 * 128, 0, 0, 1);
+    micro2_case(rep, st, "sw32 aligned", 16, 16, 6, 32, 256, 0, 0, 0, 1);
+    micro2_case(rep, st, "sw32 aligned rate", 16, 16, 6, 32, 256, 0, 0, 0, 64);
+    micro2_case(rep, st, "none N=16 rate", 16, 16, 0, 16, 128, 0, 2048, 0, 64);
+    micro2_case(rep, st, "sw32 shift19 bo=0", 16, 16, 6, 32, 256, 19 * 32, 0, 0, 1);
+    micro2_case(rep, st, "sw32 strip sbo=576 bo=0", 16, 16, 6, 32, 18 * 32, 19 * 32, 0, 0, 1);
+    micro2_case(rep, st, "sw64 shift5 bo=0", 32, 32, 4, 64, 512, 5 * 64, 0, 0, 1);
     auto flush = [&]() { if (report && report_cap > 0) snprintf(report, report_cap, "%s", rep.text.c_str()); };
     if (rc) { flush(); return -1; }
     // ---- tcgen05 convolution vs CUDA-core convolution
