@@ -8,17 +8,20 @@
 //           * the conv bias folded into the GEMM (one extra K slice: a constant "ones" A tile x a B tile holding the
 //             bias split into a 16-bit high part and a 16-bit remainder, so it is exact to ~2^-17),
 //           * the ResnetBlock 1x1 res_conv accumulated into a second TMEM region (never leaves TMEM),
-//           * GroupNorm affine, FiLM and bias collapsed per step into ONE (scale, offset) pair per
-//             (sample, channel) in shared memory, so the normalise pass is one FMA + SiLU per element,
+//           * GroupNorm statistics reduced with warp shuffles, then GroupNorm affine and FiLM collapsed per step into
+//             ONE (scale, offset) pair per (sample, channel) in shared memory, so the normalise pass is one FMA +
+//             SiLU per element,
 //           * the PreNorm of the following attention block fused into the last epilogue,
 //           * init_conv (unet.py:295) as the first epilogue of the first stage and final_conv + the RK4 / Euler
 //             / CFG stage update (unet.py:372, sampling.py:43-48,69-74) as the last epilogue of the last stage.
 //
 // Three decoupled loops per CTA (192 threads): warp 4 lane 0 = TMA producer (input tiles, weight ring),
-// warp 5 lane 0 = tcgen05.mma issuer, warps 0-3 = epilogue (TMEM lane quadrants).  Steps alternate
+// warp 5 = tcgen05.mma issuer (warp-uniform code, one elected lane issues a whole weight chunk of MMAs with
+// incrementally updated descriptors), warps 0-3 = epilogue (TMEM lane quadrants).  Steps alternate
 // MMA(i) -> EPI(i) -> MMA(i+1) ... through two mbarriers (bar_mma: tcgen05.commit, bar_epi: 128 arrivals).
 // Every role copies what it needs of the (constant-bank) parameter block into registers first: the
 // asm-volatile "memory" clobbers of the PTX wrappers would otherwise force re-loads inside the hot loops.
+// The kernel is templated on the number of 128-row M tiles per CTA so tile loops and row bookkeeping are static.
 #include <cuda_fp16.h>
 
 #include "flo_internal.h"
@@ -29,11 +32,11 @@ namespace flo {
 
 // geometry of the M tiles, in registers
 struct Geo {
-    int W, H, Wp, PP, nb, B, n_mtiles, strips, sbo_px, tx_n;
+    int W, H, Wp, PP, nb, B, strips, sbo_px, tx_n;
 };
 __device__ __forceinline__ Geo make_geo(const ChainParams& p) {
     Geo g;
-    g.W = p.W; g.H = p.H; g.Wp = p.W + 2; g.PP = g.Wp * (p.H + 2); g.nb = p.nb; g.B = p.B; g.n_mtiles = p.n_mtiles;
+    g.W = p.W; g.H = p.H; g.Wp = p.W + 2; g.PP = g.Wp * (p.H + 2); g.nb = p.nb; g.B = p.B;
     g.strips = p.strips; g.sbo_px = p.strips ? g.Wp : 8; g.tx_n = p.W >> 3;
     return g;
 }
@@ -67,57 +70,62 @@ struct ConvIssue {
     int a0_pairs, a1_pairs;    // channel-block pairs (K16 slices per tap) in each slot
     int ksize, n, col, slices, S;
 };
+template <int MT>
 struct IssueCtx {
     uint32_t tmem_base, bar_full, bar_empty, ring_lo, ring_slot16, ones_lo;
     uint32_t plane16;          // plane stride >> 4
     uint32_t desc_hi_a, desc_hi_ones;
-    int n_ring, fmt, n_mtiles, Wp;
-    int row0[4];
+    int n_ring, fmt, Wp;
+    uint32_t row0[MT];
     int cc;                    // global ring chunk counter
 };
-__device__ __forceinline__ uint64_t mk_desc(uint32_t lo14, uint32_t lbo16, uint32_t hi) {
-    return ((uint64_t)hi << 32) | (uint64_t)((lo14 & 0x3FFFu) | ((lbo16 & 0x3FFFu) << 16));
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
-__device__ __forceinline__ void issue_conv(IssueCtx& x, const ConvIssue& c) {
+template <int MT>
+__device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) {
     const uint32_t idesc = make_idesc16(128, c.n, x.fmt, 0, 0);
-    const uint32_t b_lbo16 = (uint32_t)c.n;                      // n*16 bytes >> 4
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t b_lbo = ((uint32_t)c.n & 0x3FFFu) << 16;      // n*16 bytes >> 4 in the LBO field
+    const uint32_t a_lbo = (x.plane16 & 0x3FFFu) << 16;
     const uint32_t slice16 = (uint32_t)c.n * 2u;                 // n*32 bytes >> 4
-    const int taps = c.ksize * c.ksize;
-    int sidx = 0, ks = 0;
-    uint32_t b_lo = 0;
-    int slot = 0;
-    for (int tap = 0; tap <= taps; ++tap) {
-        const bool bias_slice = tap == taps;
-        const int shift = (c.ksize == 3 && !bias_slice) ? ((tap / 3 - 1) * x.Wp + (tap % 3 - 1)) : 0;
-        const int pairs = bias_slice ? 1 : c.a0_pairs + c.a1_pairs;
-        for (int cp = 0; cp < pairs; ++cp, ++ks) {
-            if (sidx == 0) {
-                slot = x.cc % x.n_ring;
-                mbar_wait(x.bar_full + 8 * slot, (x.cc / x.n_ring) & 1);
-                tc_fence_after();
-                b_lo = x.ring_lo + (uint32_t)slot * x.ring_slot16;
+    const uint32_t two_planes = 2u * x.plane16;
+    const int pairs = c.a0_pairs + c.a1_pairs;
+    const int conv_slices = c.slices - 1;                        // the last slice is the bias
+    for (int ks0 = 0; ks0 < c.slices; ks0 += c.S) {
+        const int cnt = min(c.S, c.slices - ks0);
+        const int slot = x.cc % x.n_ring;
+        mbar_wait(x.bar_full + 8 * slot, (x.cc / x.n_ring) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+            uint32_t b_lo = (x.ring_lo + (uint32_t)slot * x.ring_slot16) | b_lbo;
+            int tap = ks0 / pairs, cp = ks0 - tap * pairs;
+            for (int s = 0; s < cnt; ++s) {
+                const int ks = ks0 + s;
+                const uint64_t bdesc = desc64(b_lo, b_hi);
+                if (ks == conv_slices) {
+                    const uint64_t adesc = desc64(x.ones_lo | (8u << 16), x.desc_hi_ones);     // rows [1,1,0..]; K half 1 = zeros
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
+                } else {
+                    const int shift = (c.ksize == 3) ? ((tap / 3 - 1) * x.Wp + (tap % 3 - 1)) : 0;
+                    const uint32_t plane_lo = (cp < c.a0_pairs) ? c.a0_lo + (uint32_t)cp * two_planes
+                                                                : c.a1_lo + (uint32_t)(cp - c.a0_pairs) * two_planes;
+                    const uint32_t a_base = (plane_lo + (uint32_t)shift) | a_lbo;
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)
+                        umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), desc64(a_base + x.row0[t], x.desc_hi_a), bdesc, idesc, acc);
+                    if (++cp == pairs) { cp = 0; ++tap; }
+                }
+                b_lo += slice16;
             }
-            const uint64_t bdesc = mk_desc(b_lo + (uint32_t)sidx * slice16, b_lbo16, b_hi);
-            if (bias_slice) {
-                const uint64_t adesc = mk_desc(x.ones_lo, 128u, x.desc_hi_ones);       // rows of [1,0,..,0]; K half 1 = zeros
-                if (elect_one())
-                    for (int t = 0; t < x.n_mtiles; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
-            } else {
-                const uint32_t plane_lo = (cp < c.a0_pairs) ? c.a0_lo + (uint32_t)(2 * cp) * x.plane16
-                                                            : c.a1_lo + (uint32_t)(2 * (cp - c.a0_pairs)) * x.plane16;
-                if (elect_one())
-                    for (int t = 0; t < x.n_mtiles; ++t)
-                        umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n),
-                                  mk_desc(plane_lo + (uint32_t)(x.row0[t] + shift), x.plane16, x.desc_hi_a), bdesc, idesc, ks > 0 ? 1u : 0u);
-            }
-            if (++sidx == c.S || ks + 1 == c.slices) {
-                if (elect_one()) umma_commit(x.bar_empty + 8 * slot);
-                ++x.cc;
-                sidx = 0;
-            }
-            __syncwarp();
+            umma_commit(x.bar_empty + 8 * slot);
         }
+        __syncwarp();
+        ++x.cc;
     }
 }
 // producer side of the same chunk sequence
@@ -167,34 +175,54 @@ __device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uin
     }
 }
 
-// per-(sample, group) totals of the per-row (sum, sumsq) pairs in shared memory, fixed order (deterministic).
-//   rowstat[row * G + g], rows = n_mtiles*128;  result stat[s*G+g] = (mean, rstd)
-__device__ void reduce_stats(const Geo& g, float2* rowstat, float2* partial, float2* stat, int G, float count, int tid) {
-    const int R = g.n_mtiles * 128;
-    const int combos = g.nb * G;
-    int parts = 1;
-    while (parts * 2 * combos <= EPI_THREADS && parts < 32) parts *= 2;
+// Per-(sample, group) statistics from the per-row (sum, sumsq) pairs in shared memory, then the collapsed
+// (scale, offset) table:  y = x*scale + offset  ==  FiLM(GroupNorm(x)).
+//   rowstat[row * G + g], rows = MT*128.  A segment of `seg` lanes owns one (sample, group): every lane sums a
+//   strided share of the rows in a fixed order, a shuffle tree combines them (deterministic), and the same lanes
+//   then write the group's channels of coef[s*C + c].  Two named barriers per call.
+struct FilmSrc {
+    const float* tab;       // FiLM table or null
+    int per_sample, row, dim, off;   // off < 0: no FiLM
+};
+__device__ void stats_to_coef(const Geo& g, int R, int b0, const float2* rowstat, float2* coef, int G, int C, int HW,
+                              const float* gamma, const float* beta, const FilmSrc& film, int tid) {
+    const int combos = g.nb * G, cpg = C / G;
+    const int cpw = (combos + 3) >> 2;
+    int seg = 32;
+    while (seg * cpw > 32) seg >>= 1;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int combo = warp * (32 / seg) + lane / seg, li = lane & (seg - 1);
+    const bool active = combo < combos;
+    const int s = active ? combo / G : 0, gi = active ? combo - s * G : 0;
     epi_sync();
-    if (tid < combos * parts) {
-        const int part = tid % parts, sg = tid / parts, gi = sg % G, s = sg / G;
+    float sx = 0.f, sq = 0.f;
+    if (active) {
         int lo = 0, hi = R;
         if (!g.strips) {
             lo = min(max(s * g.PP - (g.Wp + 1), 0), R);
             hi = min(max((s + 1) * g.PP - (g.Wp + 1), 0), R);
         }
-        const int per = (hi - lo + parts - 1) / parts;
-        const int a = lo + part * per, b = min(hi, a + per);
-        float sx = 0.f, sq = 0.f;
-        for (int r = a; r < b; ++r) { const float2 v = rowstat[r * G + gi]; sx += v.x; sq += v.y; }
-        partial[tid] = make_float2(sx, sq);
+        for (int r = lo + li; r < hi; r += seg) { const float2 v = rowstat[r * G + gi]; sx += v.x; sq += v.y; }
     }
-    epi_sync();
-    if (tid < combos) {
-        float sx = 0.f, sq = 0.f;
-        for (int k = 0; k < parts; ++k) { const float2 v = partial[tid * parts + k]; sx += v.x; sq += v.y; }
-        const float mean = sx / count;
-        const float var = fmaxf(sq / count - mean * mean, 0.f);
-        stat[tid] = make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
+    for (int o = seg >> 1; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (active) {
+        const float cnt = (float)(cpg * HW);
+        const float mean = sx / cnt;
+        const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float* fl = nullptr;
+        if (film.off >= 0 && b0 + s < g.B) fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + film.off;
+        for (int c = gi * cpg + li; c < (gi + 1) * cpg; c += seg) {
+            float a = rstd * gamma[c], bb = beta[c] - mean * a;
+            if (fl) {
+                const float sc = fl[c] + 1.0f, sh = fl[C + c];          // x*(scale+1)+shift, unet.py:70
+                a *= sc; bb = bb * sc + sh;
+            }
+            coef[s * C + c] = make_float2(a, bb);
+        }
     }
     epi_sync();
 }
@@ -202,6 +230,7 @@ __device__ void reduce_stats(const Geo& g, float2* rowstat, float2* partial, flo
 // ------------------------------------------------------------------------------------------------
 // k_chain
 // ------------------------------------------------------------------------------------------------
+template <int MT>
 __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
@@ -272,59 +301,59 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
         }
     } else if (warp == 5) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
-        {
-            IssueCtx x;
-            x.tmem_base = tmem_base; x.bar_full = bar_full; x.bar_empty = bar_empty;
-            x.ring_lo = (smem_base + p.ring_off) >> 4; x.ring_slot16 = (uint32_t)p.ring_slot_bytes >> 4;
-            x.ones_lo = (smem_base + ones_off) >> 4;
-            x.plane16 = plane_bytes >> 4;
-            x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
-            x.desc_hi_ones = (128u >> 4) | (1u << 14);
-            x.n_ring = n_ring; x.fmt = fmt; x.n_mtiles = geo.n_mtiles; x.Wp = geo.Wp; x.cc = 0;
-            for (int t = 0; t < 4; ++t) x.row0[t] = t < geo.n_mtiles ? tile_row0(geo, t) : 0;
-            if (n_loads > 0) mbar_wait(bar_load, 0);
-            for (int i = 0; i < n_steps; ++i) {
-                if (i > 0) mbar_wait(bar_epi, (i - 1) & 1);
-                tc_fence_after();
-                if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
-                if (p.st[i].has_conv) {
-                    ConvIssue c;
-                    c.a0_lo = (smem_base + p.st[i].a0_off) >> 4; c.a1_lo = (smem_base + p.st[i].a1_off) >> 4;
-                    c.a0_pairs = p.st[i].a0_ncb >> 1; c.a1_pairs = p.st[i].a1_ncb >> 1;
-                    c.ksize = p.st[i].ksize; c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
-                    c.S = p.st[i].slices_per_chunk;
-                    issue_conv(x, c);
-                    if (p.st[i].has_res) {
-                        c.ksize = 1; c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
-                        issue_conv(x, c);
-                    }
-                    if (dbg && lane == 0) dbg[i * 8 + 1] = clock64();
-                    if (elect_one()) umma_commit(bar_mma);
-                } else {
-                    if (elect_one()) mbar_arrive(bar_mma);
+        IssueCtx<MT> x;
+        x.tmem_base = tmem_base; x.bar_full = bar_full; x.bar_empty = bar_empty;
+        x.ring_lo = (smem_base + p.ring_off) >> 4; x.ring_slot16 = (uint32_t)p.ring_slot_bytes >> 4;
+        x.ones_lo = (smem_base + ones_off) >> 4;
+        x.plane16 = plane_bytes >> 4;
+        x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
+        x.desc_hi_ones = (128u >> 4) | (1u << 14);
+        x.n_ring = n_ring; x.fmt = fmt; x.Wp = geo.Wp; x.cc = 0;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) x.row0[t] = (uint32_t)tile_row0(geo, t);
+        if (n_loads > 0) mbar_wait(bar_load, 0);
+        for (int i = 0; i < n_steps; ++i) {
+            if (i > 0) mbar_wait(bar_epi, (i - 1) & 1);
+            tc_fence_after();
+            if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
+            if (p.st[i].has_conv) {
+                ConvIssue c;
+                c.a0_lo = (smem_base + p.st[i].a0_off) >> 4; c.a1_lo = (smem_base + p.st[i].a1_off) >> 4;
+                c.a0_pairs = p.st[i].a0_ncb >> 1; c.a1_pairs = p.st[i].a1_ncb >> 1;
+                c.ksize = p.st[i].ksize; c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
+                c.S = p.st[i].slices_per_chunk;
+                issue_conv<MT>(x, c);
+                if (p.st[i].has_res) {
+                    c.ksize = 1; c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
+                    issue_conv<MT>(x, c);
                 }
-                __syncwarp();
+                if (dbg && lane == 0) dbg[i * 8 + 1] = clock64();
+                if (elect_one()) umma_commit(bar_mma);
+            } else {
+                if (elect_one()) mbar_arrive(bar_mma);
             }
+            __syncwarp();
         }
     } else {
         // ============================ epilogue warps ============================
         const int r = warp * 32 + lane;                       // row inside every M tile == TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);
-        float2* partial = rowstat + geo.n_mtiles * 128 * p.g_max;
-        float2* stat = partial + EPI_THREADS;
-        float2* coef = stat + EPI_THREADS;                    // [nb][C] (scale, offset)
+        float2* coef = rowstat + MT * 128 * p.g_max;          // [nb][C] (scale, offset)
         float* cpar = reinterpret_cast<float*>(coef + p.coef_n);   // small per-step constants (init / final conv weights)
         Ctrl* ctrl = p.ctrl;
         const float* fblob = p.fblob;
-        const int HW = geo.H * geo.W, film_dim = p.film_dim;
+        const int HW = geo.H * geo.W;
         void* gt[CH_MAX_GT];
 #pragma unroll
         for (int i = 0; i < CH_MAX_GT; ++i) gt[i] = p.gt[i];
         const int step_idx = ctrl->step;
         const Stage sg = ctrl->stages[step_idx];
-        const int film_per_sample = ctrl->film_per_sample;
-        const float* film_tab = ctrl->film;
+        FilmSrc film;
+        film.tab = ctrl->film; film.per_sample = ctrl->film_per_sample; film.row = sg.film_row; film.dim = p.film_dim; film.off = -1;
+        RowInfo ri[MT];
+#pragma unroll
+        for (int t = 0; t < MT; ++t) ri[t] = make_row(geo, t, r, b0);
         if (n_loads > 0) mbar_wait(bar_load, 0);
 
         for (int i = 0; i < n_steps; ++i) {
@@ -360,50 +389,54 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                 // ---- init_conv 1x1 from the NCHW fp32 integrator state (unet.py:295)
                 const float* xs = ctrl->xs;
                 const int cin0 = p.cin0;
-                for (int t = 0; t < geo.n_mtiles; ++t) {
-                    const RowInfo ri = make_row(geo, t, r, b0);
-                    if (!ri.valid) continue;
-                    const int b = b0 + ri.s;
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
+                    if (!ri[t].valid) continue;
+                    const int b = b0 + ri[t].s;
                     float xin[16];
-                    for (int ci = 0; ci < cin0; ++ci) xin[ci] = xs[((size_t)b * cin0 + ci) * HW + ri.px];
+#pragma unroll
+                    for (int ci = 0; ci < 16; ++ci) xin[ci] = ci < cin0 ? xs[((size_t)b * cin0 + ci) * HW + ri[t].px] : 0.f;
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = cpar[C * cin0 + c16 + j];
-                            for (int ci = 0; ci < cin0; ++ci) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
+#pragma unroll
+                            for (int ci = 0; ci < 16; ++ci)
+                                if (ci < cin0) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
                             v[j] = a;
                         }
-                        write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
+                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
                     }
                 }
             } else if (epi == CE_BIAS) {
                 // ---- conv (+bias via the GEMM) (+ residual from a shared-memory slot)
-                for (int t = 0; t < geo.n_mtiles; ++t) {
-                    const RowInfo ri = make_row(geo, t, r, b0);
-                    const int b = b0 + ri.s;
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
+                    const int b = b0 + ri[t].s;
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16];
                         tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
-                        if (!ri.valid) continue;
+                        if (!ri[t].valid) continue;
                         if (res_mode == 2) {
                             float rr[16];
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
                             unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
                             unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += rr[j];
                         }
-                        write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
+                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
                     }
                 }
             } else {
                 // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
-                const int G = p.st[i].groups, cpg = C / G, silu = p.st[i].silu, film_off = p.st[i].film_off;
+                const int G = p.st[i].groups, cpg = C / G, silu = p.st[i].silu;
                 // pass 1: per-row (sum, sumsq) per group
-                for (int t = 0; t < geo.n_mtiles; ++t) {
-                    const RowInfo ri = make_row(geo, t, r, b0);
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
                     float2* rs_row = rowstat + (size_t)(t * 128 + r) * G;
+                    const bool valid = ri[t].valid;
                     if (cpg >= 16) {
                         for (int gi = 0; gi < G; ++gi) {
                             float sx = 0.f, sq = 0.f;
@@ -413,7 +446,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) { sx += v[j]; sq = fmaf(v[j], v[j], sq); }
                             }
-                            rs_row[gi] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                            rs_row[gi] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                         }
                     } else {
                         for (int c16 = 0; c16 < C; c16 += 16) {
@@ -425,7 +458,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
                                     for (int j = 0; j < 4; ++j) { const float xv = v[q * 4 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
-                                    rs_row[(c16 >> 2) + q] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                                    rs_row[(c16 >> 2) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             } else {   // cpg == 8
 #pragma unroll
@@ -433,49 +466,33 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) { const float xv = v[q * 8 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
-                                    rs_row[(c16 >> 3) + q] = ri.valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                                    rs_row[(c16 >> 3) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             }
                         }
                     }
                 }
                 if (dbg && r == 0) dbg[i * 8 + 3] = clock64();
-                reduce_stats(geo, rowstat, partial, stat, G, (float)(cpg * HW), r);
-                // collapse GroupNorm affine and FiLM into one (scale, offset) per (sample, channel)
-                {
-                    const float* gamma = fblob + p.st[i].gamma_off;
-                    const float* beta = fblob + p.st[i].beta_off;
-                    for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
-                        const int s = idx / C, c = idx - s * C;
-                        const float2 ms = stat[s * G + c / cpg];
-                        float a = ms.y * gamma[c], bb = beta[c] - ms.x * a;
-                        if (film_off >= 0 && b0 + s < geo.B) {
-                            const int row = film_per_sample ? (b0 + s) : sg.film_row;
-                            const float* film = film_tab + (size_t)row * film_dim + film_off;
-                            const float sc = film[c] + 1.0f, sh = film[C + c];      // x*(scale+1)+shift, unet.py:70
-                            a *= sc; bb = bb * sc + sh;
-                        }
-                        coef[idx] = make_float2(a, bb);
-                    }
-                }
-                epi_sync();
+                film.off = p.st[i].film_off;
+                stats_to_coef(geo, MT * 128, b0, rowstat, coef, G, C, HW, fblob + p.st[i].gamma_off, fblob + p.st[i].beta_off, film, r);
                 if (dbg && r == 0) dbg[i * 8 + 4] = clock64();
                 // pass 2: y = x*scale + offset, SiLU, + residual, write
-                for (int t = 0; t < geo.n_mtiles; ++t) {
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
                     float kacc[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) kacc[j] = 0.f;
-                    const RowInfo ri = make_row(geo, t, r, b0);
-                    const int b = b0 + ri.s;
-                    const float2* cf = coef + (ri.valid ? ri.s : 0) * C;
+                    const bool valid = ri[t].valid;
+                    const int b = b0 + ri[t].s;
+                    const float2* cf = coef + (valid ? ri[t].s : 0) * C;
                     float psx = 0.f, psq = 0.f;
                     for (int c16 = 0; c16 < C; c16 += 16) {
                         float v[16], rr[16];
                         tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
                         if (res_mode == 1) tmem_ld16(tlane + (uint32_t)(res_col + t * C + c16), rr);
-                        if (!ri.valid) continue;
+                        if (!valid) continue;
                         if (res_mode == 2) {
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri.pp * 16u;
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
                             unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
                             unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
                         }
@@ -500,11 +517,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                                 }
                             }
                         } else {
-                            write_outputs(od, geo, smem, plane_bytes, ri, b, c16, v, fmt);
+                            write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
                         }
                     }
-                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = ri.valid ? make_float2(psx, psq) : make_float2(0.f, 0.f);
-                    if (is_final && ri.valid) {
+                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = valid ? make_float2(psx, psq) : make_float2(0.f, 0.f);
+                    if (is_final && valid) {
                         // ---- final_conv bias + RK4 / Euler / CFG stage update (sampling.py:43-48,69-74)
                         const int nch = p.channels, dim = p.dim;
                         const size_t plane = (size_t)geo.B * nch * HW;
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                         for (int co = 0; co < 16; ++co) {
                             if (co >= nch) continue;
                             float k = kacc[co] + cpar[nch * dim + co];
-                            const size_t o = ((size_t)b * nch + co) * HW + ri.px;
+                            const size_t o = ((size_t)b * nch + co) * HW + ri[t].px;
                             if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(ctrl->cfg, __fsub_rn(ctrl->vcond[o], k)));
                             if (ctrl->vtrace && sg.eval_idx >= 0) ctrl->vtrace[(size_t)sg.eval_idx * plane + o] = k;
                             switch (sg.kind) {
@@ -545,29 +562,23 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                 }
                 if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
-                    reduce_stats(geo, rowstat, partial, stat, 1, (float)(C * HW), r);
-                    const float* g2 = fblob + p.st[i].pn_gamma_off;
-                    const float* b2 = fblob + p.st[i].pn_beta_off;
-                    for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
-                        const int s = idx / C, c = idx - s * C;
-                        const float2 ms = stat[s];
-                        const float a = ms.y * g2[c];
-                        coef[idx] = make_float2(a, b2[c] - ms.x * a);
-                    }
-                    epi_sync();
+                    FilmSrc nofilm = film;
+                    nofilm.off = -1;
+                    stats_to_coef(geo, MT * 128, b0, rowstat, coef, 1, C, HW, fblob + p.st[i].pn_gamma_off, fblob + p.st[i].pn_beta_off,
+                                  nofilm, r);
                     uint4* dst = reinterpret_cast<uint4*>(gt[pn_g]);
                     const int out_slot = od.slot_off;
-                    for (int t = 0; t < geo.n_mtiles; ++t) {
-                        const RowInfo ri = make_row(geo, t, r, b0);
-                        if (!ri.valid) continue;
-                        const int b = b0 + ri.s;
-                        const float2* cf = coef + ri.s * C;
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        if (!ri[t].valid) continue;
+                        const int b = b0 + ri[t].s;
+                        const float2* cf = coef + ri[t].s * C;
                         for (int cb = 0; cb < (C >> 3); ++cb) {
                             float xv[8];
-                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u), xv, fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)cb * plane_bytes + (uint32_t)ri[t].pp * 16u), xv, fmt);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { const float2 ab = cf[cb * 8 + j]; xv[j] = fmaf(xv[j], ab.x, ab.y); }
-                            dst[(size_t)(cb * geo.B + b) * HW + ri.px] = pack8(xv, fmt);
+                            dst[(size_t)(cb * geo.B + b) * HW + ri[t].px] = pack8(xv, fmt);
                         }
                     }
                 }
@@ -599,13 +610,22 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
 
 cudaError_t attn_configure();
 cudaError_t fused_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     return attn_configure();
 }
 
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
-    k_chain<<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    switch (p.n_mtiles) {
+        case 1: k_chain<1><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
+        case 2: k_chain<2><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
+        case 3: k_chain<3><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
+        case 4: k_chain<4><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
