@@ -267,6 +267,7 @@ struct AttnFusedParams {
     const float* fblob;
     const void* x2;                         // residual input (16-bit blocked, global)
     void* out; void* out_un; void* out_up;  // outputs (16-bit blocked); un/up may be null
+    long long* dbg;                         // optional clock64 timeline of CTA 0 (null in production)
 };
 
 cudaError_t fused_configure();

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+    if (dbg && tid == 0) dbg[64] = clock64();
     const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
 
     if (warp == 4) {
@@ -133,10 +135,12 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             RingA rs{0};
             mbar_wait(bar_load, 0);
             tc_fence_after();
+            if (dbg && lane == 0) dbg[0] = clock64();
             // ---- phase 0: K and V convolutions (and Q for the mid attention)
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_k, p.qkv_chunks, p.qkv_S);
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_v, p.qkv_chunks, p.qkv_S);
             if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+            if (dbg && lane == 0) dbg[1] = clock64();
             if (elect_one()) umma_commit(bar_mma);
             __syncwarp();
             int ph = 0;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                 // ---- phase 1: context per sample (both operands MN-major, K = pixels), then the Q convolution
                 mbar_wait(bar_epi, ph & 1); ++ph;
                 tc_fence_after();
+                if (dbg && lane == 0) dbg[8] = clock64();
                 const uint32_t idesc_ctx = make_idesc16(128, 144, p.fmt, 1, 1);
                 {
                     const int nb = p.nb, col_ctx = p.col_ctx;
@@ -158,11 +163,13 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     __syncwarp();
                 }
                 attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+                if (dbg && lane == 0) dbg[9] = clock64();
                 if (elect_one()) umma_commit(bar_mma);
                 __syncwarp();
                 // ---- phase 2: out[n][(h,e)] per (sample, tile, head)
                 mbar_wait(bar_epi, ph & 1); ++ph;
                 tc_fence_after();
+                if (dbg && lane == 0) dbg[16] = clock64();
                 const uint32_t idesc_out = make_idesc16(128, 32, p.fmt, 0, 0);
                 {
                     const int nb = p.nb, col_out = p.col_out;
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             // ---- last phase: to_out convolution over the O slot
             mbar_wait(bar_epi, ph & 1); ++ph;
             tc_fence_after();
+            if (dbg && lane == 0) dbg[24] = clock64();
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, p.col_proj,
                       p.o_chunks, p.o_S);
             if (elect_one()) umma_commit(bar_mma);
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
         mbar_wait(bar_load, 0);
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
+        if (dbg && r == 0) dbg[2] = clock64();
         if (!p.full) {
             // ================= EPI 0: column softmax numerators of K, V to shared memory =================
             const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
@@ -213,11 +222,14 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     const bool valid = s < p.nb && b0 + s < p.B;
                     float v[16];
                     tmem_ld16(tlane + (uint32_t)(p.col_k + t * 128 + c16), v);
+                    if (!valid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float m = valid ? v[j] : -INFINITY;
-                        for (int o = seg >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        v[j] = m;
+                        for (int j = 0; j < 16; ++j) v[j] = -INFINITY;
+                    }
+                    // butterfly over the lanes of one sample; every step runs over all 16 channels at once (ILP)
+                    for (int o = seg >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
                     }
                     if (n >= 32) {
                         if (lane == 0) {
@@ -230,6 +242,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     }
                 }
             }
+            if (dbg && r == 0) dbg[3] = clock64();
             epi_sync();
             if (n >= 32) {
                 const int wps = n / 32;                      // warp-rows per sample
@@ -264,12 +277,14 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     *reinterpret_cast<uint4*>(smem + p.v_off + 16u * plane + row_off) = pack8(ones, p.fmt);
                 }
             }
+            if (dbg && r == 0) dbg[4] = clock64();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_epi);
             // ================= EPI 1: context normalisation -> B operand; softmax_d(q) -> A operand =================
             mbar_wait(bar_mma, ph & 1); ++ph;
             tc_fence_after();
+            if (dbg && r == 0) dbg[10] = clock64();
             {
                 const int h = warp, d = lane;                // TMEM row r = (h, d)
                 for (int s = 0; s < p.nb; ++s) {
@@ -310,12 +325,14 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, p.fmt);
                 }
             }
+            if (dbg && r == 0) dbg[11] = clock64();
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_epi);
             // ================= EPI 2: attention output -> O slot (dense rows), reuses the V slot =================
             mbar_wait(bar_mma, ph & 1); ++ph;
             tc_fence_after();
+            if (dbg && r == 0) dbg[18] = clock64();
             for (int s = 0; s < p.nb; ++s)
                 for (int t = 0; t < mtS; ++t) {
                     const int px = t * 128 + r;
@@ -404,9 +421,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             tc_fence_before();
             mbar_arrive(bar_epi);
         }
+        if (dbg && r == 0) dbg[19] = clock64();
         // ================= last EPI: to_out bias -> GroupNorm(1,C) -> + x2 -> global =================
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
+        if (dbg && r == 0) dbg[26] = clock64();
         const float* bias = p.fblob + p.bo_off;
         if (!p.full) {
             for (int t = 0; t < p.n_mtiles; ++t) {
@@ -470,6 +489,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (dbg && tid == 0) dbg[65] = clock64();
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 

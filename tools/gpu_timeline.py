@@ -25,6 +25,12 @@ for i, name in enumerate(names):
     if start == 0:
         continue
     print(f"== stage {i} {name}: kernel body {end - start} cycles")
+    if not name.startswith("S_"):
+        d = lambda k: (tl[k] - start) if tl[k] else -1   # noqa: E731
+        print(f"   attn: load+mma0_start +{d(0)} kvconv_issued +{d(1)} | epi0_start +{d(2)} maxpass_done +{d(3)} epi0_end +{d(4)} | "
+              f"mma1_start +{d(8)} ctx+q_issued +{d(9)} | epi1_start +{d(10)} epi1_end +{d(11)} | mma2_start +{d(16)} | "
+              f"epi2_start +{d(18)} epi2_end +{d(19)} | mma3_start +{d(24)} | epi3_start +{d(26)} end +{end - start}")
+        continue
     for s in range(8):
         row = tl[s * 8: s * 8 + 8]
         if row[2] == 0:
