@@ -234,7 +234,8 @@ struct ChainParams {
     int n_loads, load_off[CH_MAX_LOADS], load_ncb[CH_MAX_LOADS];
     int zero_off, zero_bytes;               // shared-memory range to clear at start (epilogue-written slots)
     int ones_off;                           // 4 KB constant A tile [1,0,...] that multiplies the bias slice
-    int g_max, coef_n;                      // stats region layout: rowstat[rows*g_max] partial[128] stat[128] coef[coef_n] cpar[256]
+    int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
+                                            // gpar[C] (float2)
     int ring_off, ring_slot_bytes, n_ring;
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16

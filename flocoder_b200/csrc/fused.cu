@@ -138,7 +138,10 @@ __device__ __forceinline__ void stream_weights(uint32_t smem_base, uint32_t ring
         const int slot = cc % n_ring;
         if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, ((cc / n_ring) - 1) & 1);
         mbar_expect_tx(bar_full + 8 * slot, bytes);
-        bulk_load_1d(smem_base + ring_off + (uint32_t)slot * ring_slot_bytes, src, bytes, bar_full + 8 * slot);
+        // several concurrent bulk copies per chunk: more requests in flight towards L2
+        const uint32_t dst = smem_base + ring_off + (uint32_t)slot * ring_slot_bytes;
+        const uint32_t piece = bytes >= 8192 ? ((bytes / 4 + 15) & ~15u) : bytes;
+        for (uint32_t o = 0; o < bytes; o += piece) bulk_load_1d(dst + o, src + o, min(piece, bytes - o), bar_full + 8 * slot);
         src += bytes;
         ++cc;
     }
@@ -181,11 +184,12 @@ __device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uin
 //   strided share of the rows in a fixed order, a shuffle tree combines them (deterministic), and the same lanes
 //   then write the group's channels of coef[s*C + c].  Two named barriers per call.
 struct FilmSrc {
-    const float* tab;       // FiLM table or null
-    int per_sample, row, dim, off;   // off < 0: no FiLM
+    const float* tab;       // FiLM table
+    int per_sample, row, dim;
 };
-__device__ void stats_to_coef(const Geo& g, int R, int b0, const float2* rowstat, float2* coef, int G, int C, int HW,
-                              const float* gamma, const float* beta, const FilmSrc& film, int tid) {
+// `gpar[c]` = (gamma, beta); with `has_film`, coef[s*C+c] holds (1+scale, shift) on entry.
+__device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int C, int HW,
+                              bool has_film, int tid) {
     const int combos = g.nb * G, cpg = C / G;
     const int cpw = (combos + 3) >> 2;
     int seg = 32;
@@ -213,13 +217,12 @@ __device__ void stats_to_coef(const Geo& g, int R, int b0, const float2* rowstat
         const float mean = sx / cnt;
         const float var = fmaxf(sq / cnt - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        const float* fl = nullptr;
-        if (film.off >= 0 && b0 + s < g.B) fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + film.off;
         for (int c = gi * cpg + li; c < (gi + 1) * cpg; c += seg) {
-            float a = rstd * gamma[c], bb = beta[c] - mean * a;
-            if (fl) {
-                const float sc = fl[c] + 1.0f, sh = fl[C + c];          // x*(scale+1)+shift, unet.py:70
-                a *= sc; bb = bb * sc + sh;
+            const float2 gb = gpar[c];
+            float a = rstd * gb.x, bb = gb.y - mean * a;
+            if (has_film) {
+                const float2 f = coef[s * C + c];
+                a *= f.x; bb = bb * f.x + f.y;
             }
             coef[s * C + c] = make_float2(a, bb);
         }
@@ -231,7 +234,7 @@ __device__ void stats_to_coef(const Geo& g, int R, int b0, const float2* rowstat
 // k_chain
 // ------------------------------------------------------------------------------------------------
 template <int MT>
-__global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__ CUtensorMap tm0,
+__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
                                                          const __grid_constant__ CUtensorMap tm3,
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);
         float2* coef = rowstat + MT * 128 * p.g_max;          // [nb][C] (scale, offset)
         float* cpar = reinterpret_cast<float*>(coef + p.coef_n);   // small per-step constants (init / final conv weights)
+        const int cpar_n = p.cpar_n;
         Ctrl* ctrl = p.ctrl;
         const float* fblob = p.fblob;
         const int HW = geo.H * geo.W;
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
         const int step_idx = ctrl->step;
         const Stage sg = ctrl->stages[step_idx];
         FilmSrc film;
-        film.tab = ctrl->film; film.per_sample = ctrl->film_per_sample; film.row = sg.film_row; film.dim = p.film_dim; film.off = -1;
+        film.tab = ctrl->film; film.per_sample = ctrl->film_per_sample; film.row = sg.film_row; film.dim = p.film_dim;
         RowInfo ri[MT];
 #pragma unroll
         for (int t = 0; t < MT; ++t) ri[t] = make_row(geo, t, r, b0);
@@ -380,6 +384,24 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                 const int nch = p.channels, dim = p.dim;
                 for (int k = r; k < nch * dim; k += EPI_THREADS) cpar[k] = w[k];
                 for (int k = r; k < nch; k += EPI_THREADS) cpar[nch * dim + k] = bias[k];
+            }
+            if (epi == CE_GN) {
+                // per-channel GroupNorm affine and per-(sample, channel) FiLM factors, fetched while the MMAs run
+                epi_sync();           // every thread is done reading the previous step's coef / gpar
+                const float* gamma = fblob + p.st[i].gamma_off;
+                const float* beta = fblob + p.st[i].beta_off;
+                float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
+                for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c], beta[c]);
+                const int foff = p.st[i].film_off;
+                for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
+                    const int s = idx / C, c = idx - s * C;
+                    float2 f = make_float2(1.0f, 0.0f);
+                    if (foff >= 0 && b0 + s < geo.B) {
+                        const float* fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + foff;
+                        f = make_float2(fl[c] + 1.0f, fl[C + c]);          // x*(scale+1)+shift, unet.py:70
+                    }
+                    coef[idx] = f;
+                }
             }
             mbar_wait(bar_mma, i & 1);
             tc_fence_after();
@@ -432,32 +454,42 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
             } else {
                 // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
                 const int G = p.st[i].groups, cpg = C / G, silu = p.st[i].silu;
-                // pass 1: per-row (sum, sumsq) per group
+                // pass 1: per-row (sum, sumsq) per group; the TMEM loads of all tiles are issued before one wait
+                if (cpg >= 16) {
+                    for (int gi = 0; gi < G; ++gi) {
+                        float sx[MT], sq[MT];
 #pragma unroll
-                for (int t = 0; t < MT; ++t) {
-                    float2* rs_row = rowstat + (size_t)(t * 128 + r) * G;
-                    const bool valid = ri[t].valid;
-                    if (cpg >= 16) {
-                        for (int gi = 0; gi < G; ++gi) {
-                            float sx = 0.f, sq = 0.f;
-                            for (int c16 = gi * cpg; c16 < (gi + 1) * cpg; c16 += 16) {
-                                float v[16];
-                                tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
+                        for (int t = 0; t < MT; ++t) { sx[t] = 0.f; sq[t] = 0.f; }
+                        for (int c16 = gi * cpg; c16 < (gi + 1) * cpg; c16 += 16) {
+                            uint32_t v[MT][16];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) { sx += v[j]; sq = fmaf(v[j], v[j], sq); }
-                            }
-                            rs_row[gi] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                            for (int t = 0; t < MT; ++t) tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), v[t]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int t = 0; t < MT; ++t)
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { const float xv = __uint_as_float(v[t][j]); sx[t] += xv; sq[t] = fmaf(xv, xv, sq[t]); }
                         }
-                    } else {
-                        for (int c16 = 0; c16 < C; c16 += 16) {
-                            float v[16];
-                            tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
+#pragma unroll
+                        for (int t = 0; t < MT; ++t)
+                            rowstat[(size_t)(t * 128 + r) * G + gi] = ri[t].valid ? make_float2(sx[t], sq[t]) : make_float2(0.f, 0.f);
+                    }
+                } else {
+                    for (int c16 = 0; c16 < C; c16 += 16) {
+                        uint32_t v[MT][16];
+#pragma unroll
+                        for (int t = 0; t < MT; ++t) tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), v[t]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int t = 0; t < MT; ++t) {
+                            float2* rs_row = rowstat + (size_t)(t * 128 + r) * G;
+                            const bool valid = ri[t].valid;
                             if (cpg == 4) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) { const float xv = v[q * 4 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
+                                    for (int j = 0; j < 4; ++j) { const float xv = __uint_as_float(v[t][q * 4 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
                                     rs_row[(c16 >> 2) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             } else {   // cpg == 8
@@ -465,7 +497,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                                 for (int q = 0; q < 2; ++q) {
                                     float sx = 0.f, sq = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) { const float xv = v[q * 8 + j]; sx += xv; sq = fmaf(xv, xv, sq); }
+                                    for (int j = 0; j < 8; ++j) { const float xv = __uint_as_float(v[t][q * 8 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
                                     rs_row[(c16 >> 3) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
                                 }
                             }
@@ -473,54 +505,70 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                     }
                 }
                 if (dbg && r == 0) dbg[i * 8 + 3] = clock64();
-                film.off = p.st[i].film_off;
-                stats_to_coef(geo, MT * 128, b0, rowstat, coef, G, C, HW, fblob + p.st[i].gamma_off, fblob + p.st[i].beta_off, film, r);
+                stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), G, C, HW, true, r);
                 if (dbg && r == 0) dbg[i * 8 + 4] = clock64();
-                // pass 2: y = x*scale + offset, SiLU, + residual, write
+                // pass 2: y = x*scale + offset, SiLU, + residual, write.  Chunk-major so that the TMEM loads of all
+                // tiles are in flight together and the per-element chains of MT*16 values interleave.
+                float kacc[MT][16];
+                float psx[MT], psq[MT];
 #pragma unroll
                 for (int t = 0; t < MT; ++t) {
-                    float kacc[16];
+                    psx[t] = 0.f; psq[t] = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) kacc[j] = 0.f;
-                    const bool valid = ri[t].valid;
-                    const int b = b0 + ri[t].s;
-                    const float2* cf = coef + (valid ? ri[t].s : 0) * C;
-                    float psx = 0.f, psq = 0.f;
-                    for (int c16 = 0; c16 < C; c16 += 16) {
+                    for (int j = 0; j < 16; ++j) kacc[t][j] = 0.f;
+                }
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    uint32_t av[MT][16], rv[MT][16];
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), av[t]);
+                        if (res_mode == 1) tmem_ld16_issue(tlane + (uint32_t)(res_col + t * C + c16), rv[t]);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        if (!ri[t].valid) continue;
+                        const int b = b0 + ri[t].s;
+                        const float2* cf = coef + ri[t].s * C + c16;
                         float v[16], rr[16];
-                        tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
-                        if (res_mode == 1) tmem_ld16(tlane + (uint32_t)(res_col + t * C + c16), rr);
-                        if (!valid) continue;
                         if (res_mode == 2) {
                             const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
                             unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
                             unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
+                        } else if (res_mode == 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rr[j] = __uint_as_float(rv[t][j]);
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float2 ab = cf[c16 + j];
-                            float y = fmaf(v[j], ab.x, ab.y);
-                            if (silu) y = __fdividef(y, 1.0f + __expf(-y));
+                            const float2 ab = cf[j];
+                            float y = fmaf(__uint_as_float(av[t][j]), ab.x, ab.y);
+                            if (silu) y = fast_silu(y);
                             if (res_mode) y += rr[j];
                             v[j] = y;
-                            psx += y; psq = fmaf(y, y, psq);
+                            psx[t] += y; psq[t] = fmaf(y, y, psq[t]);
                         }
                         if (is_final) {
                             const int nch = p.channels, dim = p.dim;
 #pragma unroll
                             for (int co = 0; co < 16; ++co) {
                                 if (co < nch) {
-                                    float a = kacc[co];
+                                    float a = kacc[t][co];
 #pragma unroll
                                     for (int j = 0; j < 16; ++j) a = fmaf(v[j], cpar[co * dim + c16 + j], a);
-                                    kacc[co] = a;
+                                    kacc[t][co] = a;
                                 }
                             }
                         } else {
                             write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
                         }
                     }
-                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = valid ? make_float2(psx, psq) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int t = 0; t < MT; ++t) {
+                    const bool valid = ri[t].valid;
+                    const int b = b0 + ri[t].s;
+                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = valid ? make_float2(psx[t], psq[t]) : make_float2(0.f, 0.f);
                     if (is_final && valid) {
                         // ---- final_conv bias + RK4 / Euler / CFG stage update (sampling.py:43-48,69-74)
                         const int nch = p.channels, dim = p.dim;
@@ -528,7 +576,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
 #pragma unroll
                         for (int co = 0; co < 16; ++co) {
                             if (co >= nch) continue;
-                            float k = kacc[co] + cpar[nch * dim + co];
+                            float k = kacc[t][co] + cpar[nch * dim + co];
                             const size_t o = ((size_t)b * nch + co) * HW + ri[t].px;
                             if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(ctrl->cfg, __fsub_rn(ctrl->vcond[o], k)));
                             if (ctrl->vtrace && sg.eval_idx >= 0) ctrl->vtrace[(size_t)sg.eval_idx * plane + o] = k;
@@ -562,10 +610,14 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_chain(const __grid_constant__
                 }
                 if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
-                    FilmSrc nofilm = film;
-                    nofilm.off = -1;
-                    stats_to_coef(geo, MT * 128, b0, rowstat, coef, 1, C, HW, fblob + p.st[i].pn_gamma_off, fblob + p.st[i].pn_beta_off,
-                                  nofilm, r);
+                    {
+                        const float* g2 = fblob + p.st[i].pn_gamma_off;
+                        const float* b2 = fblob + p.st[i].pn_beta_off;
+                        float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
+                        epi_sync();                                   // everyone is done with the block-norm gpar/coef
+                        for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c], b2[c]);
+                    }
+                    stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), 1, C, HW, false, r);
                     uint4* dst = reinterpret_cast<uint4*>(gt[pn_g]);
                     const int out_slot = od.slot_off;
 #pragma unroll

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     tmem_ld16(tlane + (uint32_t)(p.col_v + t * 128 + c16), vv);
                     if (!valid) continue;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) kv[j] = __expf(kv[j] - kmax[s * 128 + c16 + j]);
+                    for (int j = 0; j < 16; ++j) kv[j] = fast_exp(kv[j] - kmax[s * 128 + c16 + j]);
                     uint8_t* pd = smem + p.p_off + (uint32_t)(c16 >> 3) * plane + row_off;
                     uint8_t* vd = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
                     *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     for (int j = 1; j < 32; ++j) m = fmaxf(m, q[j]);
                     float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { q[j] = __expf(q[j] - m); sum += q[j]; }
+                    for (int j = 0; j < 32; ++j) { q[j] = fast_exp(q[j] - m); sum += q[j]; }
                     const float inv = 1.0f / sum;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) q[j] *= inv;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                 }
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { sim[j] = (j < n && valid) ? __expf(sim[j] - m) : 0.f; sum += sim[j]; }
+                for (int j = 0; j < 16; ++j) { sim[j] = (j < n && valid) ? fast_exp(sim[j] - m) : 0.f; sum += sim[j]; }
                 const float inv = valid ? 1.0f / sum : 0.f;
 #pragma unroll
                 for (int e = 0; e < 32; ++e) o[h * 32 + e] = 0.f;

@@ -34,4 +34,17 @@ __device__ __forceinline__ void unpack8(uint4 u, float* v, int fmt) {
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, EPI_THREADS); }
 
 
+
+// Branch-free MUFU forms: the CUDA intrinsics add denormal-range fix-ups (predicated code and reconvergence
+// points) that serialise the per-element chains of an unrolled epilogue loop.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+__device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+// SiLU (unet.py:67 nn.SiLU): y * sigmoid(y)
+__device__ __forceinline__ float fast_silu(float y) { return y * fast_rcp(1.0f + fast_exp(-y)); }
+
 }  // namespace flo
