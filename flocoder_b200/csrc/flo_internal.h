@@ -215,6 +215,7 @@ struct ChainStep {
     unsigned w_off; int slices, slices_per_chunk;              // weight stream (16-bit elements into wblob): K16 slices
                                                                // incl. the trailing bias slice, slices per ring chunk
     int has_res, res_col; unsigned wres_off; int res_slices, res_slices_per_chunk;   // 1x1 res_conv on the same A
+    int tab_idx, res_tab_idx;               // first entry of this conv's A-address table (ChainParams::tab_off)
     // ---- epilogue part
     int epi;                                // ChainEpi
     int C, groups, silu, film_off;          // film_off < 0: no FiLM
@@ -238,6 +239,7 @@ struct ChainParams {
                                             // gpar[C] (float2)
     int ring_off, ring_slot_bytes, n_ring;
     int stats_off, bar_off, smem_bytes, tmem_cols;
+    int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start
     int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16
     int film_dim;
     int cin0, dim, channels;                // init conv / final conv shapes

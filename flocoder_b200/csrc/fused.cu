@@ -66,16 +66,15 @@ __device__ __forceinline__ RowInfo make_row(const Geo& g, int t, int r, int b0) 
 // MMA issue: one convolution = taps x channel-pair slices (+ 1 bias slice), weights from the ring
 // ------------------------------------------------------------------------------------------------
 struct ConvIssue {
-    uint32_t a0_lo, a1_lo;     // (smem address >> 4) of plane 0 of each operand slot
-    int a0_pairs, a1_pairs;    // channel-block pairs (K16 slices per tap) in each slot
-    int ksize, n, col, slices, S;
+    const int32_t* tab;        // per-slice A start address (>>4, tile row offset not included); entries [0, slices)
+    int n, col, slices, S;
 };
 template <int MT>
 struct IssueCtx {
     uint32_t tmem_base, bar_full, bar_empty, ring_lo, ring_slot16, ones_lo;
     uint32_t plane16;          // plane stride >> 4
     uint32_t desc_hi_a, desc_hi_ones;
-    int n_ring, fmt, Wp;
+    int n_ring, fmt;
     uint32_t row0[MT];
     int cc;                    // global ring chunk counter
 };
@@ -84,6 +83,8 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
+// The A operand of K16 slice ks = two channel-block planes of one input slot, shifted by the 3x3 tap: its start
+// address comes from the table built at kernel start, so the issuing thread runs load / add / tcgen05.mma only.
 template <int MT>
 __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) {
     const uint32_t idesc = make_idesc16(128, c.n, x.fmt, 0, 0);
@@ -91,8 +92,6 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
     const uint32_t b_lbo = ((uint32_t)c.n & 0x3FFFu) << 16;      // n*16 bytes >> 4 in the LBO field
     const uint32_t a_lbo = (x.plane16 & 0x3FFFu) << 16;
     const uint32_t slice16 = (uint32_t)c.n * 2u;                 // n*32 bytes >> 4
-    const uint32_t two_planes = 2u * x.plane16;
-    const int pairs = c.a0_pairs + c.a1_pairs;
     const int conv_slices = c.slices - 1;                        // the last slice is the bias
     for (int ks0 = 0; ks0 < c.slices; ks0 += c.S) {
         const int cnt = min(c.S, c.slices - ks0);
@@ -101,31 +100,41 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
         tc_fence_after();
         if (elect_one()) {
             uint32_t b_lo = (x.ring_lo + (uint32_t)slot * x.ring_slot16) | b_lbo;
-            int tap = ks0 / pairs, cp = ks0 - tap * pairs;
+            const int32_t* tp = c.tab + ks0;
+            int32_t cur = tp[0];
             for (int s = 0; s < cnt; ++s) {
-                const int ks = ks0 + s;
+                const int32_t nxt = tp[s + 1];                   // the table has one spare entry per conv
                 const uint64_t bdesc = desc64(b_lo, b_hi);
-                if (ks == conv_slices) {
+                if (ks0 + s == conv_slices) {
                     const uint64_t adesc = desc64(x.ones_lo | (8u << 16), x.desc_hi_ones);     // rows [1,1,0..]; K half 1 = zeros
 #pragma unroll
                     for (int t = 0; t < MT; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
                 } else {
-                    const int shift = (c.ksize == 3) ? ((tap / 3 - 1) * x.Wp + (tap % 3 - 1)) : 0;
-                    const uint32_t plane_lo = (cp < c.a0_pairs) ? c.a0_lo + (uint32_t)cp * two_planes
-                                                                : c.a1_lo + (uint32_t)(cp - c.a0_pairs) * two_planes;
-                    const uint32_t a_base = (plane_lo + (uint32_t)shift) | a_lbo;
-                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    const uint32_t a_base = (uint32_t)cur | a_lbo;
+                    const uint32_t acc = (ks0 + s) > 0 ? 1u : 0u;
 #pragma unroll
                     for (int t = 0; t < MT; ++t)
                         umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), desc64(a_base + x.row0[t], x.desc_hi_a), bdesc, idesc, acc);
-                    if (++cp == pairs) { cp = 0; ++tap; }
                 }
+                cur = nxt;
                 b_lo += slice16;
             }
             umma_commit(x.bar_empty + 8 * slot);
         }
         __syncwarp();
         ++x.cc;
+    }
+}
+// Table of A start addresses for one conv: slice ks = (tap, channel-block pair cp); pairs [0, a0_pairs) come from
+// slot a0, the rest from slot a1 (the channel concat of the up path, unet.py:349,353).
+__device__ __forceinline__ void build_conv_table(int32_t* tab, int conv_slices, int ksize, int a0_16, int a0_pairs, int a1_16,
+                                                 int a1_pairs, int two_planes, int Wp, int tid) {
+    const int pairs = a0_pairs + a1_pairs;
+    for (int ks = tid; ks < conv_slices; ks += FUSED_THREADS) {
+        const int tap = ks / pairs, cp = ks - tap * pairs;
+        const int shift = (ksize == 3) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
+        const int plane = (cp < a0_pairs) ? a0_16 + cp * two_planes : a1_16 + (cp - a0_pairs) * two_planes;
+        tab[ks] = plane + shift;
     }
 }
 // producer side of the same chunk sequence
@@ -272,6 +281,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,1,0,0,0,0,0,0] per row (bias hi + lo); plane 1: zeros
             *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? ones2 : 0u, 0, 0, 0);
     }
+    int32_t* atab = reinterpret_cast<int32_t*>(smem + p.tab_off);
+    for (int i = 0; i < n_steps; ++i) {
+        if (!p.st[i].has_conv) continue;
+        const int a0_16 = (int)((smem_base + p.st[i].a0_off) >> 4), a1_16 = (int)((smem_base + p.st[i].a1_off) >> 4);
+        const int two_planes = (int)(plane_bytes >> 4) * 2;
+        build_conv_table(atab + p.st[i].tab_idx, p.st[i].slices - 1, p.st[i].ksize, a0_16, p.st[i].a0_ncb >> 1, a1_16,
+                         p.st[i].a1_ncb >> 1, two_planes, geo.Wp, tid);
+        if (p.st[i].has_res)
+            build_conv_table(atab + p.st[i].res_tab_idx, p.st[i].res_slices - 1, 1, a0_16, p.st[i].a0_ncb >> 1, a1_16,
+                             p.st[i].a1_ncb >> 1, two_planes, geo.Wp, tid);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         x.plane16 = plane_bytes >> 4;
         x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
         x.desc_hi_ones = (128u >> 4) | (1u << 14);
-        x.n_ring = n_ring; x.fmt = fmt; x.Wp = geo.Wp; x.cc = 0;
+        x.n_ring = n_ring; x.fmt = fmt; x.cc = 0;
 #pragma unroll
         for (int t = 0; t < MT; ++t) x.row0[t] = (uint32_t)tile_row0(geo, t);
         if (n_loads > 0) mbar_wait(bar_load, 0);
@@ -321,13 +341,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
             if (p.st[i].has_conv) {
                 ConvIssue c;
-                c.a0_lo = (smem_base + p.st[i].a0_off) >> 4; c.a1_lo = (smem_base + p.st[i].a1_off) >> 4;
-                c.a0_pairs = p.st[i].a0_ncb >> 1; c.a1_pairs = p.st[i].a1_ncb >> 1;
-                c.ksize = p.st[i].ksize; c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
+                c.tab = atab + p.st[i].tab_idx;
+                c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
                 c.S = p.st[i].slices_per_chunk;
                 issue_conv<MT>(x, c);
                 if (p.st[i].has_res) {
-                    c.ksize = 1; c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
+                    c.tab = atab + p.st[i].res_tab_idx;
+                    c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
                     issue_conv<MT>(x, c);
                 }
                 if (dbg && lane == 0) dbg[i * 8 + 1] = clock64();
