@@ -24,6 +24,7 @@
 // The kernel is templated on the number of 128-row M tiles per CTA so tile loops and row bookkeeping are static.
 #include <cuda_fp16.h>
 
+#include <cstring>
 #include "flo_internal.h"
 #include "umma_common.cuh"
 #include "fused_common.cuh"
@@ -137,23 +138,37 @@ __device__ __forceinline__ void build_conv_table(int32_t* tab, int conv_slices, 
         tab[ks] = plane + shift;
     }
 }
-// producer side of the same chunk sequence
-__device__ __forceinline__ void stream_weights(uint32_t smem_base, uint32_t ring_off, uint32_t ring_slot_bytes, int n_ring,
-                                               uint32_t bar_full, uint32_t bar_empty, int& cc, const uint16_t* w, int slices, int S,
-                                               int n) {
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(w);
-    for (int done = 0; done < slices; done += S) {
-        const uint32_t bytes = (uint32_t)min(S, slices - done) * (uint32_t)n * 32u;
-        const int slot = cc % n_ring;
-        if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, ((cc / n_ring) - 1) & 1);
-        mbar_expect_tx(bar_full + 8 * slot, bytes);
-        // several concurrent bulk copies per chunk: more requests in flight towards L2
-        const uint32_t dst = smem_base + ring_off + (uint32_t)slot * ring_slot_bytes;
-        const uint32_t piece = bytes >= 8192 ? ((bytes / 4 + 15) & ~15u) : bytes;
-        for (uint32_t o = 0; o < bytes; o += piece) bulk_load_1d(dst + o, src + o, min(piece, bytes - o), bar_full + 8 * slot);
-        src += bytes;
-        ++cc;
+// producer side of the same chunk sequence: a resumable walk over (step, conv | res_conv, chunk)
+struct WIter { int i, part, done; };
+__device__ __forceinline__ bool witer_next(const ChainParams& p, WIter& it, const uint8_t*& src, uint32_t& bytes) {
+    while (it.i < p.n_steps) {
+        const ChainStep& st = p.st[it.i];
+        if (st.has_conv) {
+            const int slices = it.part ? st.res_slices : st.slices;
+            const int S = it.part ? st.res_slices_per_chunk : st.slices_per_chunk;
+            if (it.done < slices) {
+                const int cnt = min(S, slices - it.done);
+                const uint16_t* w = p.wblob + (it.part ? st.wres_off : st.w_off);
+                src = reinterpret_cast<const uint8_t*>(w) + (size_t)it.done * (size_t)st.n * 32u;
+                bytes = (uint32_t)cnt * (uint32_t)st.n * 32u;
+                it.done += cnt;
+                return true;
+            }
+            if (it.part == 0 && st.has_res) { it.part = 1; it.done = 0; continue; }
+        }
+        ++it.i; it.part = 0; it.done = 0;
     }
+    return false;
+}
+__device__ __forceinline__ void issue_chunk(uint32_t smem_base, uint32_t ring_off, uint32_t ring_slot_bytes, int n_ring, uint32_t bar_full,
+                                            uint32_t bar_empty, int cc, const uint8_t* src, uint32_t bytes) {
+    const int slot = cc % n_ring;
+    if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, ((cc / n_ring) - 1) & 1);
+    mbar_expect_tx(bar_full + 8 * slot, bytes);
+    // several concurrent bulk copies per chunk: more requests in flight towards L2
+    const uint32_t dst = smem_base + ring_off + (uint32_t)slot * ring_slot_bytes;
+    const uint32_t piece = bytes >= 8192 ? ((bytes / 4 + 15) & ~15u) : bytes;
+    for (uint32_t o = 0; o < bytes; o += piece) bulk_load_1d(dst + o, src + o, min(piece, bytes - o), bar_full + 8 * slot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -265,6 +280,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
     const int ones_off = p.ones_off;
     long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+    if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
 
     if (warp == 4 && lane == 0) {
         for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -298,28 +314,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8] = clock64();
+    if (dbg && tid == 0) dbg[101] = global_ns();
 
     if (warp == 4) {
         // ============================ producer ============================
         if (lane == 0) {
+            const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
+            WIter it{0, 0, 0};
+            int cc = 0;
+            const uint8_t* src; uint32_t bytes;
+            bool more = true;
+            // the weights do not depend on the previous kernel: fill the ring before waiting for it
+            while (cc < n_ring && (more = witer_next(p, it, src, bytes))) {
+                issue_chunk(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, src, bytes);
+                ++cc;
+            }
+            griddep_wait();
+            griddep_launch();
             if (n_loads > 0) {
-                uint32_t bytes = 0;
-                for (int i = 0; i < n_loads; ++i) bytes += (uint32_t)p.load_ncb[i] * plane_bytes;
-                mbar_expect_tx(bar_load, bytes);
+                uint32_t lbytes = 0;
+                for (int i = 0; i < n_loads; ++i) lbytes += (uint32_t)p.load_ncb[i] * plane_bytes;
+                mbar_expect_tx(bar_load, lbytes);
                 const CUtensorMap* maps[4] = {&tm0, &tm1, &tm2, &tm3};
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
-            const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
-            const uint16_t* wblob = p.wblob;
-            int cc = 0;
-            for (int i = 0; i < n_steps; ++i) {
-                if (!p.st[i].has_conv) continue;
-                const int n = p.st[i].n;
-                stream_weights(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, wblob + p.st[i].w_off,
-                               p.st[i].slices, p.st[i].slices_per_chunk, n);
-                if (p.st[i].has_res)
-                    stream_weights(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, wblob + p.st[i].wres_off,
-                                   p.st[i].res_slices, p.st[i].res_slices_per_chunk, n);
+            while (more && witer_next(p, it, src, bytes)) {
+                issue_chunk(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, src, bytes);
+                ++cc;
             }
         }
     } else if (warp == 5) {
@@ -368,6 +389,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         Ctrl* ctrl = p.ctrl;
         const float* fblob = p.fblob;
         const int HW = geo.H * geo.W;
+        griddep_wait();              // ctrl, the FiLM table and every activation come from earlier kernels
+        griddep_launch();
         void* gt[CH_MAX_GT];
 #pragma unroll
         for (int i = 0; i < CH_MAX_GT; ++i) gt[i] = p.gt[i];
@@ -677,6 +700,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     tc_fence_before();
     __syncthreads();
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8 + 1] = clock64();
+    if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -690,15 +714,30 @@ cudaError_t fused_configure() {
     return attn_configure();
 }
 
+static bool g_pdl = false;
+void fused_set_pdl(bool on) { g_pdl = on; }
+cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
+    const void* fn;
     switch (p.n_mtiles) {
-        case 1: k_chain<1><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
-        case 2: k_chain<2><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
-        case 3: k_chain<3><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
-        case 4: k_chain<4><<<grid, FUSED_THREADS, p.smem_bytes, s>>>(maps[0], maps[1], maps[2], maps[3], p); break;
+        case 1: fn = (const void*)k_chain<1>; break;
+        case 2: fn = (const void*)k_chain<2>; break;
+        case 3: fn = (const void*)k_chain<3>; break;
+        case 4: fn = (const void*)k_chain<4>; break;
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
+    void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
+    return launch_pdl(fn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args);
 }
 
 }  // namespace flo

@@ -22,16 +22,20 @@ namespace flo {
 
 struct RingA { int cc; };
 
-__device__ __forceinline__ void attn_stream(const AttnFusedParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
-                                            RingA& rs, const uint16_t* w, int n_chunks, int chunk_bytes) {
-    for (int ci = 0; ci < n_chunks; ++ci) {
-        const int slot = rs.cc % p.n_ring;
-        if (rs.cc >= p.n_ring) mbar_wait(bar_empty + 8 * slot, ((rs.cc / p.n_ring) - 1) & 1);
-        mbar_expect_tx(bar_full + 8 * slot, (uint32_t)chunk_bytes);
-        bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes,
-                     reinterpret_cast<const uint8_t*>(w) + (size_t)ci * chunk_bytes, (uint32_t)chunk_bytes, bar_full + 8 * slot);
-        ++rs.cc;
-    }
+// weight chunk g of the stage: K, V, Q projections (qkv_chunks each), then to_out (o_chunks)
+__device__ __forceinline__ void attn_issue_chunk(const AttnFusedParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
+                                                 int g, int qkv_bytes, int o_bytes) {
+    const int qc = p.qkv_chunks;
+    const uint16_t* w; int ci, bytes;
+    if (g < qc) { w = p.wblob + p.wk_off; ci = g; bytes = qkv_bytes; }
+    else if (g < 2 * qc) { w = p.wblob + p.wv_off; ci = g - qc; bytes = qkv_bytes; }
+    else if (g < 3 * qc) { w = p.wblob + p.wq_off; ci = g - 2 * qc; bytes = qkv_bytes; }
+    else { w = p.wblob + p.wo_off; ci = g - 3 * qc; bytes = o_bytes; }
+    const int slot = g % p.n_ring;
+    if (g >= p.n_ring) mbar_wait(bar_empty + 8 * slot, ((g / p.n_ring) - 1) & 1);
+    mbar_expect_tx(bar_full + 8 * slot, (uint32_t)bytes);
+    bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes, reinterpret_cast<const uint8_t*>(w) + (size_t)ci * bytes,
+                 (uint32_t)bytes, bar_full + 8 * slot);
 }
 // 1x1 conv over a K-major operand slot: A rows = tile t rows [128t, 128t+128), planes at `a_plane` stride
 __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t smem_base, uint32_t tmem_base, uint32_t bar_full,
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     const uint32_t tmem_slot = bar_epi + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
     const int b0 = blockIdx.x * p.nb;
+    if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
     const int n = p.n, n_pad = p.n_pad, C = p.C;
     const uint32_t plane = (uint32_t)p.plane_bytes;
     const uint32_t xh_plane = (uint32_t)(p.nb * n) * 16u;
@@ -118,17 +123,18 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_ptr;
     long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
     if (dbg && tid == 0) dbg[64] = clock64();
+    if (dbg && tid == 0) dbg[101] = global_ns();
     const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
 
     if (warp == 4) {
         if (lane == 0) {
+            const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(p.n_ring, total);
+            for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
+            griddep_wait();          // weights are constants; the activations come from the previous kernel
+            griddep_launch();
             mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * xh_plane);
             tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
-            RingA rs{0};
-            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wk_off, p.qkv_chunks, qkv_bytes);
-            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wv_off, p.qkv_chunks, qkv_bytes);
-            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wq_off, p.qkv_chunks, qkv_bytes);
-            attn_stream(p, smem_base, bar_full, bar_empty, rs, p.wblob + p.wo_off, p.o_chunks, o_bytes);
+            for (int g = pre; g < total; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
         }
     } else if (warp == 5) {
         {   // whole warp, warp-uniform; one elected lane issues the tcgen05 instructions
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
         float2* partial = rowstat + p.n_mtiles * 128;
         float2* stat = partial + EPI_THREADS;
         int ph = 0;
+        griddep_wait();
         mbar_wait(bar_load, 0);
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (dbg && tid == 0) dbg[65] = clock64();
+    if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -497,9 +505,10 @@ cudaError_t attn_configure() {
     return cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
+cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
-    k_attn<<<grid, FUSED_THREADS, p.smem_bytes, s>>>(xh_map, p);
-    return cudaGetLastError();
+    void* args[2] = {(void*)&xh_map, (void*)&p};
+    return launch_pdl((const void*)k_attn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args);
 }
 
 }  // namespace flo

@@ -129,4 +129,13 @@ __host__ __device__ constexpr uint32_t make_idesc16(int m, int n, int fmt, int a
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+
+// Programmatic dependent launch: the next kernel of the stream may start its prologue (barrier init, TMEM
+// allocation, weight prefetch) while this one still runs; griddep_wait() blocks until every earlier kernel has
+// completed and its global writes are visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
 }  // namespace flo

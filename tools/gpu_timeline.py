@@ -19,6 +19,17 @@ for _ in range(3):
 torch.cuda.synchronize()
 eng = m.engine(16, 16)
 names = eng.op_names()
+prev_end = None
+print("stage                 entry-after-prev-end  prologue   body(cta0)  last-cta-end-after-cta0-end   [us, globaltimer]")
+for i, name in enumerate(names):
+    tl = eng.read_timeline(B, i)
+    if tl[100] == 0:
+        continue
+    gap = (tl[100] - prev_end) / 1e3 if prev_end else float("nan")
+    print(f"{i:3d} {name:18s} {gap:10.2f} {(tl[101]-tl[100])/1e3:10.2f} {(tl[102]-tl[101])/1e3:10.2f} {(tl[103]-tl[102])/1e3:10.2f}")
+    prev_end = tl[103]
+if "gaps" in sys.argv:
+    sys.exit(0)
 for i, name in enumerate(names):
     tl = eng.read_timeline(B, i)
     start, end = tl[64], tl[65]
