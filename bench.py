@@ -223,7 +223,8 @@ def run_gpu_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            flush.zero_()
+            if not os.environ.get("FLO_BENCH_NOFLUSH"):
+                flush.zero_()
             fn()
         e1.record()
         barrier()
@@ -232,11 +233,15 @@ def run_gpu_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # the sampler starts before the warm-up (NVML initialisation and its first query are slow and would otherwise
+    # land inside the timed region); only the samples taken during the timed region are kept
+    clocks = ClockSampler(local)
+    if rank == 0 and not os.environ.get("FLO_BENCH_NOCLOCK"):
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    torch.cuda.synchronize()
+    clocks.samples.clear(); clocks.reasons.clear()
     l0 = eng.launch_count()
     ms = timed(step_resident, args.steps)
     launches = eng.launch_count() - l0
