@@ -218,7 +218,8 @@ def test_16bit_final_latent_vs_fp32_reference(goldens, name, compute_dtype, laye
 @pytest.mark.parametrize("compute_dtype,prec,tol", [("bf16", FUSED_BF16, 3e-2), ("fp16", FUSED_FP16, 4e-3)])
 def test_fused_per_stage_tensors_vs_emulating_oracle(goldens, compute_dtype, prec, tol):
     """Every stage-boundary tensor of the fused path (and, in debug mode, every ResnetBlock output) against the
-    oracle that rounds at the same points; the first block must agree to accumulation-order noise."""
+    oracle that rounds at the same points; the first block must agree to accumulation-order / MUFU-approximation
+    noise (a handful of flipped 16-bit roundings: ex2.approx + rcp.approx in the kernel's SiLU vs exact in the oracle)."""
     g = goldens["midi_vqgan"]
     m = gpu_model(0, compute_dtype)
     _, sd = seeded_state_dict(0)
@@ -226,7 +227,7 @@ def test_fused_per_stage_tensors_vs_emulating_oracle(goldens, compute_dtype, pre
     assert len(rows) > 40
     for name, e in rows.items():
         print(f"{name:40s} {e:.3e}")
-    assert rows["init_conv"] <= 1e-6 and rows["downs.0.0"] <= 1e-4
+    assert rows["init_conv"] <= 1e-6 and rows["downs.0.0"] <= (5e-4 if compute_dtype == "bf16" else 1e-4)
     worst = max(rows.items(), key=lambda r: r[1])
     assert worst[1] <= tol, worst
 
