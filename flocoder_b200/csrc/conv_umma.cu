@@ -429,4 +429,60 @@ cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, f
     return cudaGetLastError();
 }
 
+
+// Back-to-back tcgen05.mma throughput probe: one elected thread issues `n_mma` M=128 x N x K=16 MMAs on zeroed no-swizzle
+// operands (A start address cycling through 4 tiles), one commit, then waits.  cycles[0] = issue loop, cycles[1] = until done.
+__global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int n_mma, int n_acc) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tslot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid * 16; i < 96 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int cols = 32;
+    while (cols < N * n_acc) cols <<= 1;
+    if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(&tslot);
+    long long t0 = 0, t1 = 0;
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint32_t base = smem_u32(smem);
+        const uint64_t ad0 = make_smem_desc(base, 2048u, 128u);                  // A: LBO = 2 KB plane, SBO = 128 B
+        const uint64_t bd0 = make_smem_desc(base + 64 * 1024, (uint32_t)N * 16u, 128u);
+        t0 = clock64();
+        if (elect_one()) {
+            const uint32_t acc_mask = (uint32_t)(n_acc - 1);
+#pragma unroll 4
+            for (int i = 0; i < n_mma; ++i)
+                umma_bf16(tbase + ((uint32_t)i & acc_mask) * (uint32_t)N, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
+            umma_commit(smem_u32(&bar));
+        }
+        __syncwarp();
+        t1 = clock64();
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    if (warp == 1 && lane == 0) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, cols);
+}
+cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    k_umma_rate<<<1, 128, 200 * 1024, s>>>(cycles, N, n_mma, n_acc);
+    return cudaGetLastError();
+}
+
 }  // namespace flo

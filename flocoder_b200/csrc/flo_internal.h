@@ -174,6 +174,7 @@ cudaError_t simt_configure();
 cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, int N, int K, int a_lbo,
                               int a_sbo, int a_shift, int b_lbo, int b_sbo, cudaStream_t s);
 
+cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cudaStream_t s);
 cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, long long* cycles, int N, int K, int layout,
                                int row_bytes, int a_sbo, int a_shift, int a_lbo, int use_base_offset, int reps, cudaStream_t s);
 
@@ -216,6 +217,7 @@ struct ChainStep {
                                                                // incl. the trailing bias slice, slices per ring chunk
     int has_res, res_col; unsigned wres_off; int res_slices, res_slices_per_chunk;   // 1x1 res_conv on the same A
     int tab_idx, res_tab_idx;               // first entry of this conv's A-address table (ChainParams::tab_off)
+    int chunk0, res_chunk0;                 // first weight-ring chunk of the conv / res_conv in the stage's chunk list
     // ---- epilogue part
     int epi;                                // ChainEpi
     int C, groups, silu, film_off;          // film_off < 0: no FiLM
@@ -240,6 +242,7 @@ struct ChainParams {
     int ring_off, ring_slot_bytes, n_ring;
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start
+    int wtab_off, n_chunks;                 // weight chunk list (byte offset into wblob, bytes), built at kernel start
     int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16
     int film_dim;
     int cin0, dim, channels;                // init conv / final conv shapes

@@ -66,6 +66,10 @@ __device__ __forceinline__ RowInfo make_row(const Geo& g, int t, int r, int b0) 
 // ------------------------------------------------------------------------------------------------
 // MMA issue: one convolution = taps x channel-pair slices (+ 1 bias slice), weights from the ring
 // ------------------------------------------------------------------------------------------------
+struct RingPos {               // ring slot and mbarrier phase, advanced without integer division
+    int slot; uint32_t phase;
+    __device__ __forceinline__ void next(int n_ring) { if (++slot == n_ring) { slot = 0; phase ^= 1u; } }
+};
 struct ConvIssue {
     const int32_t* tab;        // per-slice A start address (>>4, tile row offset not included); entries [0, slices)
     int n, col, slices, S;
@@ -78,6 +82,8 @@ struct IssueCtx {
     int n_ring, fmt;
     uint32_t row0[MT];
     int cc;                    // global ring chunk counter
+    RingPos rp;
+    long long* dbg;
 };
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
     uint64_t d;
@@ -96,9 +102,10 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
     const int conv_slices = c.slices - 1;                        // the last slice is the bias
     for (int ks0 = 0; ks0 < c.slices; ks0 += c.S) {
         const int cnt = min(c.S, c.slices - ks0);
-        const int slot = x.cc % x.n_ring;
-        mbar_wait(x.bar_full + 8 * slot, (x.cc / x.n_ring) & 1);
+        const int slot = x.rp.slot;
+        mbar_wait(x.bar_full + 8 * slot, x.rp.phase);
         tc_fence_after();
+        if (x.dbg && x.cc >= 8 && x.cc < 16 && (threadIdx.x & 31) == 0) x.dbg[104 + (x.cc - 8) * 3 + 2] = clock64();   // chunk seen full
         if (elect_one()) {
             uint32_t b_lo = (x.ring_lo + (uint32_t)slot * x.ring_slot16) | b_lbo;
             const int32_t* tp = c.tab + ks0;
@@ -124,6 +131,7 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
         }
         __syncwarp();
         ++x.cc;
+        x.rp.next(x.n_ring);
     }
 }
 // Table of A start addresses for one conv: slice ks = (tap, channel-block pair cp); pairs [0, a0_pairs) come from
@@ -138,37 +146,11 @@ __device__ __forceinline__ void build_conv_table(int32_t* tab, int conv_slices, 
         tab[ks] = plane + shift;
     }
 }
-// producer side of the same chunk sequence: a resumable walk over (step, conv | res_conv, chunk)
-struct WIter { int i, part, done; };
-__device__ __forceinline__ bool witer_next(const ChainParams& p, WIter& it, const uint8_t*& src, uint32_t& bytes) {
-    while (it.i < p.n_steps) {
-        const ChainStep& st = p.st[it.i];
-        if (st.has_conv) {
-            const int slices = it.part ? st.res_slices : st.slices;
-            const int S = it.part ? st.res_slices_per_chunk : st.slices_per_chunk;
-            if (it.done < slices) {
-                const int cnt = min(S, slices - it.done);
-                const uint16_t* w = p.wblob + (it.part ? st.wres_off : st.w_off);
-                src = reinterpret_cast<const uint8_t*>(w) + (size_t)it.done * (size_t)st.n * 32u;
-                bytes = (uint32_t)cnt * (uint32_t)st.n * 32u;
-                it.done += cnt;
-                return true;
-            }
-            if (it.part == 0 && st.has_res) { it.part = 1; it.done = 0; continue; }
-        }
-        ++it.i; it.part = 0; it.done = 0;
-    }
-    return false;
-}
-__device__ __forceinline__ void issue_chunk(uint32_t smem_base, uint32_t ring_off, uint32_t ring_slot_bytes, int n_ring, uint32_t bar_full,
-                                            uint32_t bar_empty, int cc, const uint8_t* src, uint32_t bytes) {
-    const int slot = cc % n_ring;
-    if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, ((cc / n_ring) - 1) & 1);
-    mbar_expect_tx(bar_full + 8 * slot, bytes);
-    // several concurrent bulk copies per chunk: more requests in flight towards L2
-    const uint32_t dst = smem_base + ring_off + (uint32_t)slot * ring_slot_bytes;
-    const uint32_t piece = bytes >= 8192 ? ((bytes / 4 + 15) & ~15u) : bytes;
-    for (uint32_t o = 0; o < bytes; o += piece) bulk_load_1d(dst + o, src + o, min(piece, bytes - o), bar_full + 8 * slot);
+// producer side of the same chunk sequence: (byte offset into wblob, bytes) per chunk, built at kernel start
+__device__ __forceinline__ void build_chunk_table(uint2* wtab, unsigned w_off, int slices, int S, int n, int tid) {
+    const int nchunks = (slices + S - 1) / S;
+    for (int c = tid; c < nchunks; c += FUSED_THREADS)
+        wtab[c] = make_uint2(w_off * 2u + (uint32_t)(c * S) * (uint32_t)n * 32u, (uint32_t)min(S, slices - c * S) * (uint32_t)n * 32u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -298,8 +280,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? ones2 : 0u, 0, 0, 0);
     }
     int32_t* atab = reinterpret_cast<int32_t*>(smem + p.tab_off);
+    uint2* wtab_w = reinterpret_cast<uint2*>(smem + p.wtab_off);
     for (int i = 0; i < n_steps; ++i) {
         if (!p.st[i].has_conv) continue;
+        build_chunk_table(wtab_w + p.st[i].chunk0, p.st[i].w_off, p.st[i].slices, p.st[i].slices_per_chunk, p.st[i].n, tid);
+        if (p.st[i].has_res)
+            build_chunk_table(wtab_w + p.st[i].res_chunk0, p.st[i].wres_off, p.st[i].res_slices, p.st[i].res_slices_per_chunk,
+                              p.st[i].n, tid);
         const int a0_16 = (int)((smem_base + p.st[i].a0_off) >> 4), a1_16 = (int)((smem_base + p.st[i].a1_off) >> 4);
         const int two_planes = (int)(plane_bytes >> 4) * 2;
         build_conv_table(atab + p.st[i].tab_idx, p.st[i].slices - 1, p.st[i].ksize, a0_16, p.st[i].a0_ncb >> 1, a1_16,
@@ -319,16 +306,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     if (warp == 4) {
         // ============================ producer ============================
         if (lane == 0) {
-            const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
-            WIter it{0, 0, 0};
-            int cc = 0;
-            const uint8_t* src; uint32_t bytes;
-            bool more = true;
+            const uint32_t ring_base = smem_base + p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
+            const uint2* wtab = reinterpret_cast<const uint2*>(smem + p.wtab_off);
+            const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.wblob);
+            const int n_chunks = p.n_chunks;
+            RingPos rp{0, 0};
+            auto issue = [&](int cc) {
+                const uint2 e = wtab[cc];
+                const uint32_t full = bar_full + 8 * rp.slot;
+                if (cc >= n_ring) mbar_wait(bar_empty + 8 * rp.slot, rp.phase ^ 1u);
+                if (dbg && cc >= 8 && cc < 16) dbg[104 + (cc - 8) * 3 + 1] = clock64();
+                mbar_expect_tx(full, e.y);
+                // several concurrent bulk copies per chunk: more requests in flight towards L2
+                const uint32_t dst = ring_base + (uint32_t)rp.slot * ring_slot_bytes;
+                const uint8_t* src = wbase + e.x;
+                if (e.y >= 8192u) {
+                    const uint32_t piece = ((e.y >> 2) + 15u) & ~15u;
+                    bulk_load_1d(dst, src, piece, full);
+                    bulk_load_1d(dst + piece, src + piece, piece, full);
+                    bulk_load_1d(dst + 2 * piece, src + 2 * piece, piece, full);
+                    bulk_load_1d(dst + 3 * piece, src + 3 * piece, e.y - 3 * piece, full);
+                } else {
+                    bulk_load_1d(dst, src, e.y, full);
+                }
+                rp.next(n_ring);
+            };
             // the weights do not depend on the previous kernel: fill the ring before waiting for it
-            while (cc < n_ring && (more = witer_next(p, it, src, bytes))) {
-                issue_chunk(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, src, bytes);
-                ++cc;
-            }
+            const int pre = min(n_ring, n_chunks);
+            for (int cc = 0; cc < pre; ++cc) issue(cc);
             griddep_wait();
             griddep_launch();
             if (n_loads > 0) {
@@ -338,10 +343,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 const CUtensorMap* maps[4] = {&tm0, &tm1, &tm2, &tm3};
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
-            while (more && witer_next(p, it, src, bytes)) {
-                issue_chunk(smem_base, ring_off, ring_slot_bytes, n_ring, bar_full, bar_empty, cc, src, bytes);
-                ++cc;
-            }
+            for (int cc = pre; cc < n_chunks; ++cc) issue(cc);
         }
     } else if (warp == 5) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         x.plane16 = plane_bytes >> 4;
         x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
         x.desc_hi_ones = (128u >> 4) | (1u << 14);
-        x.n_ring = n_ring; x.fmt = fmt; x.cc = 0;
+        x.n_ring = n_ring; x.fmt = fmt; x.cc = 0; x.rp.slot = 0; x.rp.phase = 0; x.dbg = dbg;
 #pragma unroll
         for (int t = 0; t < MT; ++t) x.row0[t] = (uint32_t)tile_row0(geo, t);
         if (n_loads > 0) mbar_wait(bar_load, 0);

@@ -233,6 +233,23 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
     micro2_case(rep, st, "sw32 shift19 bo=0", 16, 16, 6, 32, 256, 19 * 32, 0, 0, 1);
     micro2_case(rep, st, "sw32 strip sbo=576 bo=0", 16, 16, 6, 32, 18 * 32, 19 * 32, 0, 0, 1);
     micro2_case(rep, st, "sw64 shift5 bo=0", 32, 32, 4, 64, 512, 5 * 64, 0, 0, 1);
+    {   // back-to-back MMA throughput (informational)
+        long long* dc; long long hc[2];
+        ST_CUDA(cudaMalloc(&dc, 16));
+        const int Ns[4] = {16, 32, 64, 128}, counts[4] = {1, 8, 32, 128};
+        for (int acc = 1; acc <= 2; ++acc)
+            for (int ni = 0; ni < 4; ++ni) {
+                char buf[256]; int o = snprintf(buf, sizeof(buf), "INFO umma_rate N=%-3d acc=%d :", Ns[ni], acc);
+                for (int ci = 0; ci < 4; ++ci) {
+                    ST_CUDA(launch_umma_rate(dc, Ns[ni], counts[ci], acc, st));
+                    ST_CUDA(cudaStreamSynchronize(st));
+                    ST_CUDA(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
+                    o += snprintf(buf + o, sizeof(buf) - o, "  n=%d issue %lld done %lld", counts[ci], hc[0], hc[1]);
+                }
+                rep.text += buf; rep.text += "\n";
+            }
+        cudaFree(dc);
+    }
     auto flush = [&]() { if (report && report_cap > 0) snprintf(report, report_cap, "%s", rep.text.c_str()); };
     if (rc) { flush(); return -1; }
     // ---- tcgen05 convolution vs CUDA-core convolution

@@ -42,6 +42,9 @@ for i, name in enumerate(names):
               f"mma1_start +{d(8)} ctx+q_issued +{d(9)} | epi1_start +{d(10)} epi1_end +{d(11)} | mma2_start +{d(16)} | "
               f"epi2_start +{d(18)} epi2_end +{d(19)} | mma3_start +{d(24)} | epi3_start +{d(26)} end +{end - start}")
         continue
+    if tl[105]:
+        print("   weight chunks 8..15 (cycles rel. kernel start): " + " | ".join(
+            f"wait {tl[104+3*k]-start} issue {tl[105+3*k]-start} full {tl[106+3*k]-start}" for k in range(8) if tl[105+3*k]))
     for s in range(8):
         row = tl[s * 8: s * 8 + 8]
         if row[2] == 0:
