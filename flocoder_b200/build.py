@@ -24,6 +24,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += [f for f in os.environ.get("FLO_NVCC_EXTRA", "").split() if f]     # e.g. -DFLO_DBG_... for experiments
+
+
 def find_nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.isfile(cand):

@@ -1195,9 +1195,9 @@ int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap) {
             const FStage& st = h.fstages[i];
             if (st.kind == 0) {
                 const ChainParams& c = st.cp;
-                snprintf(line, sizeof(line), "stage %2zu chain %-12s %dx%d nb=%d mt=%d strips=%d steps=%d loads=%d smem=%d (slots %d, ring %dx%d) tmem=%d ctas=%d\n",
+                snprintf(line, sizeof(line), "stage %2zu chain %-12s %dx%d nb=%d mt=%d strips=%d steps=%d loads=%d smem=%d (slots %d, ring %dx%d) tmem=%d nsplit=%d ctas=%d\n",
                          i, st.name.c_str(), c.H, c.W, c.nb, c.n_mtiles, c.strips, c.n_steps, c.n_loads, c.smem_bytes, c.ring_off,
-                         c.n_ring, c.ring_slot_bytes, c.tmem_cols, (B + c.nb - 1) / c.nb);
+                         c.n_ring, c.ring_slot_bytes, c.tmem_cols, c.nsplit, c.nsplit * ((B + c.nb - 1) / c.nb));
                 t += line;
                 for (int k = 0; k < c.n_steps; ++k) {
                     const ChainStep& cs = c.st[k];

@@ -160,6 +160,7 @@ struct OutDst {                 // destinations of one step's result, in registe
     int slot_off;               // shared-memory slot or -1
     uint4* g; uint4* g_un; uint4* g_up;
     int ncb;
+    uint32_t smem_base; int nsplit;      // nsplit > 1: the slot is replicated in every CTA of the cluster (DSMEM stores)
 };
 __device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uint8_t* smem, uint32_t plane_bytes, const RowInfo& ri,
                                               int b, int c16, const float* v, int fmt) {
@@ -168,7 +169,16 @@ __device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uin
     for (int hb = 0; hb < 2; ++hb) {
         const int cb = (c16 >> 3) + hb;
         const uint4 u = pack8(v + hb * 8, fmt);
-        if (o.slot_off >= 0) *reinterpret_cast<uint4*>(smem + o.slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u) = u;
+        if (o.slot_off >= 0) {
+            const uint32_t soff = (uint32_t)o.slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u;
+#ifdef FLO_DBG_LOCAL_ONLY
+            if (true) *reinterpret_cast<uint4*>(smem + soff) = u;
+#else
+            if (o.nsplit == 1) *reinterpret_cast<uint4*>(smem + soff) = u;
+#endif
+            else
+                for (int q = 0; q < o.nsplit; ++q) st_cluster_v4(mapa_shared(o.smem_base + soff, (uint32_t)q), u);
+        }
         if (o.g) o.g[(size_t)(cb * g.B + b) * HW + ri.px] = u;
         if (o.g_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)  (unet.py:52)
             const int plane = ((ri.h & 1) * 2 + (ri.w & 1)) * o.ncb + cb;
@@ -194,8 +204,11 @@ struct FilmSrc {
     int per_sample, row, dim;
 };
 // `gpar[c]` = (gamma, beta); with `has_film`, coef[s*C+c] holds (1+scale, shift) on entry.
+struct XChg {                    // cross-CTA (cluster) reduction of per-sample statistics; nsplit == 1: unused
+    int nsplit; uint32_t rank, smem_base, bar_x; int xpart_off; uint32_t* phase; uint8_t* smem;
+};
 __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int C, int HW,
-                              bool has_film, int tid) {
+                              bool has_film, int tid, const XChg* xc = nullptr) {
     const int combos = g.nb * G, cpg = C / G;
     const int cpw = (combos + 3) >> 2;
     int seg = 32;
@@ -218,8 +231,26 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
+    int n_parts = 1;
+    if (xc && xc->nsplit > 1) {
+        // G == 1 here: every CTA of the cluster holds the sums over ITS channels; publish them to all CTAs, then
+        // add the parts in rank order (deterministic, identical in every CTA)
+        n_parts = xc->nsplit;
+        if (active && li == 0)
+            for (int q = 0; q < n_parts; ++q)
+                st_cluster_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
+                              make_float2(sx, sq));
+        for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
+        mbar_wait_cluster(xc->bar_x, *xc->phase & 1u);
+        ++*xc->phase;
+        if (active) {
+            const float2* xp = reinterpret_cast<const float2*>(xc->smem + xc->xpart_off);
+            sx = 0.f; sq = 0.f;
+            for (int q = 0; q < n_parts; ++q) { const float2 v = xp[q * g.nb + s]; sx += v.x; sq += v.y; }
+        }
+    }
     if (active) {
-        const float cnt = (float)(cpg * HW);
+        const float cnt = (float)(cpg * HW * n_parts);
         const float mean = sx / cnt;
         const float var = fmaxf(sq / cnt - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
@@ -255,9 +286,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     const uint32_t bar_mma = bar_load + 8;
     const uint32_t bar_epi = bar_mma + 8;
     const uint32_t tmem_slot = bar_epi + 8;
+    const uint32_t bar_x = tmem_slot + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 24);
     const Geo geo = make_geo(p);
-    const int b0 = blockIdx.x * geo.nb;
+    // N-split: the Q CTAs of a cluster own the same samples and 1/Q of every step's output channels
+    const int Q = p.nsplit;
+#ifdef FLO_DBG_SAMEW
+    const uint32_t qrank = 0u;
+#else
+    const uint32_t qrank = Q > 1 ? cluster_ctarank() : 0u;
+#endif
+    const int b0 = ((int)blockIdx.x / Q) * geo.nb;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
     const int ones_off = p.ones_off;
@@ -268,7 +307,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
-        mbar_init(bar_epi, EPI_THREADS);
+        mbar_init(bar_epi, EPI_THREADS * Q);
+        mbar_init(bar_x, EPI_THREADS * Q);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -283,11 +323,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     uint2* wtab_w = reinterpret_cast<uint2*>(smem + p.wtab_off);
     for (int i = 0; i < n_steps; ++i) {
         if (!p.st[i].has_conv) continue;
-        build_chunk_table(wtab_w + p.st[i].chunk0, p.st[i].w_off, p.st[i].slices, p.st[i].slices_per_chunk, p.st[i].n, tid);
+        // each CTA of an N-split cluster streams its own contiguous [slices][n] weight stream
+        build_chunk_table(wtab_w + p.st[i].chunk0, p.st[i].w_off + qrank * (unsigned)(p.st[i].slices * p.st[i].n * 16), p.st[i].slices,
+                          p.st[i].slices_per_chunk, p.st[i].n, tid);
         if (p.st[i].has_res)
-            build_chunk_table(wtab_w + p.st[i].res_chunk0, p.st[i].wres_off, p.st[i].res_slices, p.st[i].res_slices_per_chunk,
-                              p.st[i].n, tid);
-        const int a0_16 = (int)((smem_base + p.st[i].a0_off) >> 4), a1_16 = (int)((smem_base + p.st[i].a1_off) >> 4);
+            build_chunk_table(wtab_w + p.st[i].res_chunk0, p.st[i].wres_off + qrank * (unsigned)(p.st[i].res_slices * p.st[i].n * 16),
+                              p.st[i].res_slices, p.st[i].res_slices_per_chunk, p.st[i].n, tid);
+        // descriptor address field: 14 bits of (CTA-local address >> 4); in a cluster the shared window address carries the CTA rank
+        // in its upper bits, which must not leak into the LBO field
+        const int a0_16 = (int)(((smem_base + p.st[i].a0_off) >> 4) & 0x3FFFu), a1_16 = (int)(((smem_base + p.st[i].a1_off) >> 4) & 0x3FFFu);
         const int two_planes = (int)(plane_bytes >> 4) * 2;
         build_conv_table(atab + p.st[i].tab_idx, p.st[i].slices - 1, p.st[i].ksize, a0_16, p.st[i].a0_ncb >> 1, a1_16,
                          p.st[i].a1_ncb >> 1, two_planes, geo.Wp, tid);
@@ -297,7 +341,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    if (Q > 1) cluster_sync_all();       // barriers initialised and slots cleared in EVERY CTA before any remote store / arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8] = clock64();
@@ -344,13 +389,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
             for (int cc = pre; cc < n_chunks; ++cc) issue(cc);
+#ifdef FLO_DBG_PRINT
+            if (blockIdx.x < 2 && Q > 1 && geo.H == 4) {
+                mbar_wait(bar_full, 0);
+                const uint16_t* rs = reinterpret_cast<const uint16_t*>(smem + p.ring_off);
+                const uint16_t* gs = reinterpret_cast<const uint16_t*>(wbase + wtab[0].x);
+                printf("blk %d rank %u w_off %u wtab0 (%u,%u) ring: %04x %04x %04x %04x | glob: %04x %04x %04x %04x | st.n %d slices %d\n", blockIdx.x, qrank,
+                       p.st[0].w_off, wtab[0].x, wtab[0].y, rs[0], rs[1], rs[2], rs[3], gs[0], gs[1], gs[2], gs[3], p.st[0].n, p.st[0].slices);
+            }
+#endif
         }
     } else if (warp == 5) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
         IssueCtx<MT> x;
         x.tmem_base = tmem_base; x.bar_full = bar_full; x.bar_empty = bar_empty;
-        x.ring_lo = (smem_base + p.ring_off) >> 4; x.ring_slot16 = (uint32_t)p.ring_slot_bytes >> 4;
-        x.ones_lo = (smem_base + ones_off) >> 4;
+        x.ring_lo = ((smem_base + p.ring_off) >> 4) & 0x3FFFu; x.ring_slot16 = (uint32_t)p.ring_slot_bytes >> 4;
+        x.ones_lo = ((smem_base + ones_off) >> 4) & 0x3FFFu;
         x.plane16 = plane_bytes >> 4;
         x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
         x.desc_hi_ones = (128u >> 4) | (1u << 14);
@@ -359,7 +413,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int t = 0; t < MT; ++t) x.row0[t] = (uint32_t)tile_row0(geo, t);
         if (n_loads > 0) mbar_wait(bar_load, 0);
         for (int i = 0; i < n_steps; ++i) {
-            if (i > 0) mbar_wait(bar_epi, (i - 1) & 1);
+            if (i > 0) {
+                if (Q > 1) { mbar_wait_cluster(bar_epi, (i - 1) & 1); fence_proxy_async_all(); }
+                else mbar_wait(bar_epi, (i - 1) & 1);
+            }
             tc_fence_after();
             if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
             if (p.st[i].has_conv) {
@@ -404,14 +461,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
 #pragma unroll
         for (int t = 0; t < MT; ++t) ri[t] = make_row(geo, t, r, b0);
         if (n_loads > 0) mbar_wait(bar_load, 0);
+        uint32_t xphase = 0;
+        XChg xc;
+        xc.nsplit = Q; xc.rank = qrank; xc.smem_base = smem_base; xc.bar_x = bar_x; xc.xpart_off = p.xpart_off; xc.phase = &xphase;
+        xc.smem = smem;
 
         for (int i = 0; i < n_steps; ++i) {
             // ---- step parameters into registers
-            const int epi = p.st[i].epi, C = p.st[i].C, acc_col = p.st[i].acc_col, res_col = p.st[i].res_col;
+            const int epi = p.st[i].epi, Ctot = p.st[i].C, acc_col = p.st[i].acc_col, res_col = p.st[i].res_col;
+            const int C = Ctot / Q, c0 = (int)qrank * C;      // this CTA's channels [c0, c0 + C) of the step's Ctot
             const int res_mode = p.st[i].res_mode, res_slot_off = p.st[i].res_slot_off;
             const int is_final = p.st[i].final, pn_g = p.st[i].pn_g;
             OutDst od;
-            od.slot_off = p.st[i].out_slot_off; od.ncb = C >> 3;
+            od.slot_off = p.st[i].out_slot_off; od.ncb = Ctot >> 3; od.smem_base = smem_base; od.nsplit = Q;
             od.g = p.st[i].out_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_g]) : nullptr;
             od.g_un = p.st[i].out_un_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_un_g]) : nullptr;
             od.g_up = p.st[i].out_up_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_up_g]) : nullptr;
@@ -436,14 +498,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 const float* gamma = fblob + p.st[i].gamma_off;
                 const float* beta = fblob + p.st[i].beta_off;
                 float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
-                for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c], beta[c]);
+                for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c0 + c], beta[c0 + c]);
                 const int foff = p.st[i].film_off;
                 for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
                     const int s = idx / C, c = idx - s * C;
                     float2 f = make_float2(1.0f, 0.0f);
                     if (foff >= 0 && b0 + s < geo.B) {
                         const float* fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + foff;
-                        f = make_float2(fl[c] + 1.0f, fl[C + c]);          // x*(scale+1)+shift, unet.py:70
+                        f = make_float2(fl[c0 + c] + 1.0f, fl[Ctot + c0 + c]);          // x*(scale+1)+shift, unet.py:70
                     }
                     coef[idx] = f;
                 }
@@ -487,18 +549,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         if (!ri[t].valid) continue;
                         if (res_mode == 2) {
                             float rr[16];
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + c16) >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
                             unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
                             unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += rr[j];
                         }
-                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
+#ifdef FLO_DBG_PRINT
+                        if (Q > 1 && geo.H == 4 && b == 0 && ri[t].px == 0 && c16 == 0)
+                        {
+                            const uint16_t* a16 = reinterpret_cast<const uint16_t*>(smem + p.st[i].a0_off + ri[t].pp * 16);
+                            const uint16_t* a16b = reinterpret_cast<const uint16_t*>(smem + p.st[i].a0_off + 7 * plane_bytes + ri[t].pp * 16);
+                            printf("epi blk %d rank %u c0 %d: acc %f %f %f %f  (slot %d) smem_base %x tmem %x A[pl0] %04x %04x %04x %04x A[pl7] %04x %04x %04x %04x pp %d a0_off %d\n", blockIdx.x, qrank, c0, v[0], v[1], v[2], v[3], od.slot_off, smem_base, tmem_base,
+                                   a16[0], a16[1], a16[2], a16[3], a16b[0], a16b[1], a16b[2], a16b[3], ri[t].pp, p.st[i].a0_off);
+                        }
+#endif
+                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c0 + c16, v, fmt);
                     }
                 }
             } else {
                 // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
-                const int G = p.st[i].groups, cpg = C / G, silu = p.st[i].silu;
+                const int G = p.st[i].groups / Q, cpg = C / G, silu = p.st[i].silu;       // this CTA's groups
                 // pass 1: per-row (sum, sumsq) per group; the TMEM loads of all tiles are issued before one wait
                 if (cpg >= 16) {
                     for (int gi = 0; gi < G; ++gi) {
@@ -577,7 +648,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         const float2* cf = coef + ri[t].s * C + c16;
                         float v[16], rr[16];
                         if (res_mode == 2) {
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c16 >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + c16) >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
                             unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
                             unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
                         } else if (res_mode == 1) {
@@ -605,7 +676,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                                 }
                             }
                         } else {
-                            write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
+                            write_outputs(od, geo, smem, plane_bytes, ri[t], b, c0 + c16, v, fmt);
                         }
                     }
                 }
@@ -660,9 +731,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         const float* b2 = fblob + p.st[i].pn_beta_off;
                         float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
                         epi_sync();                                   // everyone is done with the block-norm gpar/coef
-                        for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c], b2[c]);
+                        for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c0 + c], b2[c0 + c]);
                     }
-                    stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), 1, C, HW, false, r);
+                    stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), 1, C, HW, false, r, &xc);
                     uint4* dst = reinterpret_cast<uint4*>(gt[pn_g]);
                     const int out_slot = od.slot_off;
 #pragma unroll
@@ -671,11 +742,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         const int b = b0 + ri[t].s;
                         const float2* cf = coef + ri[t].s * C;
                         for (int cb = 0; cb < (C >> 3); ++cb) {
+                            const int gcb = (c0 >> 3) + cb;
                             float xv[8];
-                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)cb * plane_bytes + (uint32_t)ri[t].pp * 16u), xv, fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)gcb * plane_bytes + (uint32_t)ri[t].pp * 16u), xv, fmt);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { const float2 ab = cf[cb * 8 + j]; xv[j] = fmaf(xv[j], ab.x, ab.y); }
-                            dst[(size_t)(cb * geo.B + b) * HW + ri[t].px] = pack8(xv, fmt);
+                            dst[(size_t)(gcb * geo.B + b) * HW + ri[t].px] = pack8(xv, fmt);
                         }
                     }
                 }
@@ -694,13 +766,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 }
             }
             if (dbg && r == 0) dbg[i * 8 + 5] = clock64();
-            fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
             tc_fence_before();
-            mbar_arrive(bar_epi);
+            if (Q > 1) {
+                fence_proxy_async_all();     // local and remote shared-memory results -> visible to every CTA's next tcgen05.mma
+                for (int q = 0; q < Q; ++q) mbar_arrive_cluster(mapa_shared(bar_epi, (uint32_t)q));
+            } else {
+                fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
+                mbar_arrive(bar_epi);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (Q > 1) cluster_sync_all();       // no CTA may exit while a peer can still store into its shared memory
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8 + 1] = clock64();
     if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
@@ -718,14 +796,23 @@ cudaError_t fused_configure() {
 
 static bool g_pdl = false;
 void fused_set_pdl(bool on) { g_pdl = on; }
-cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args) {
+cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (g_pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
@@ -739,7 +826,7 @@ cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid
         default: return cudaErrorInvalidValue;
     }
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
-    return launch_pdl(fn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args);
+    return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);
 }
 
 }  // namespace flo

@@ -505,10 +505,10 @@ cudaError_t attn_configure() {
     return cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args);
+cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
     void* args[2] = {(void*)&xh_map, (void*)&p};
-    return launch_pdl((const void*)k_attn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args);
+    return launch_pdl((const void*)k_attn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args, 1);
 }
 
 }  // namespace flo
