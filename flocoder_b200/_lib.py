@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "libflocoder_b200.so")
+LIB_PATH = os.environ.get("FLO_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "libflocoder_b200.so")   # FLO_LIB: A/B-test another build of the same ABI
 
 FLO_OK, FLO_ERR_INVALID, FLO_ERR_UNSUPPORTED, FLO_ERR_CUDA, FLO_ERR_NOMEM = 0, -1, -2, -3, -4
 FLO_F32, FLO_BF16, FLO_F16 = 0, 1, 2

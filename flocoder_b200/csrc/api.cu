@@ -257,6 +257,7 @@ struct Plan {
     // fused path
     uint8_t* farena = nullptr;
     std::vector<CUtensorMap> fstage_maps;
+    int fvar = 0;                           // which Handle::stages() variant this plan runs
     std::vector<ChainParams> fchain;
     std::vector<AttnFusedParams> fattn;
     long long* dbg = nullptr;
@@ -288,7 +289,10 @@ struct Handle {
     int64_t launches = 0;
     Val r_val;
     std::vector<FTensor> ftensors;
-    std::vector<FStage> fstages;
+    std::vector<FStage> fstages;            // variant 0: N-split of the low-resolution chain stages up to 4 CTAs
+    std::vector<FStage> fstages_alt[2];     // variants 1, 2: N-split capped at 2 / none (picked per batch size so the
+                                            // split stages still fit the GPU in one wave)
+    const std::vector<FStage>& stages(int variant) const { return variant == 0 ? fstages : fstages_alt[variant - 1]; }
     size_t farena_ps = 0;
 };
 
@@ -919,9 +923,15 @@ int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const
     if (rc) return rc;
     allocate_arena(*h);
     if (h->spec.fused) {
-        FusedBuilder fb(*h, h->ftensors, h->fstages);
+        FusedBuilder fb(*h, h->ftensors, h->fstages, 4);
         rc = fb.build();
         if (rc) return rc;
+        for (int v = 0; v < 2; ++v) {
+            std::vector<FTensor> scratch;              // same tensors in the same order as variant 0
+            FusedBuilder fa(*h, scratch, h->fstages_alt[v], v == 0 ? 2 : 1);
+            rc = fa.build();
+            if (rc) return rc;
+        }
     }
     h->host.clear();
     CUDA_TRY(cudaMalloc((void**)&h->d_f32, h->blob_f32.size() * sizeof(float)));
@@ -1185,7 +1195,7 @@ int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap) {
         t += line;
     }
     if (h.spec.fused) {
-        FusedBuilder fb(h, h.ftensors, h.fstages);
+        FusedBuilder fb(h, h.ftensors, h.fstages, 4);
         rc = fb.build();
         if (rc) return rc;
         snprintf(line, sizeof(line), "fused: %d stages, %d boundary tensors, %zu bytes/sample\n", (int)h.fstages.size(),
