@@ -171,11 +171,7 @@ __device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uin
         const uint4 u = pack8(v + hb * 8, fmt);
         if (o.slot_off >= 0) {
             const uint32_t soff = (uint32_t)o.slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u;
-#ifdef FLO_DBG_LOCAL_ONLY
-            if (true) *reinterpret_cast<uint4*>(smem + soff) = u;
-#else
             if (o.nsplit == 1) *reinterpret_cast<uint4*>(smem + soff) = u;
-#endif
             else
                 for (int q = 0; q < o.nsplit; ++q) st_cluster_v4(mapa_shared(o.smem_base + soff, (uint32_t)q), u);
         }
@@ -270,7 +266,8 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
 // ------------------------------------------------------------------------------------------------
 // k_chain
 // ------------------------------------------------------------------------------------------------
-template <int MT>
+// SPLIT: the N-split (cluster) variant; false compiles every cluster / DSMEM path out (Q == 1, c0 == 0 fold away)
+template <int MT, bool SPLIT>
 __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
@@ -290,12 +287,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 24);
     const Geo geo = make_geo(p);
     // N-split: the Q CTAs of a cluster own the same samples and 1/Q of every step's output channels
-    const int Q = p.nsplit;
-#ifdef FLO_DBG_SAMEW
-    const uint32_t qrank = 0u;
-#else
-    const uint32_t qrank = Q > 1 ? cluster_ctarank() : 0u;
-#endif
+    const int Q = SPLIT ? p.nsplit : 1;
+    const uint32_t qrank = SPLIT ? cluster_ctarank() : 0u;
     const int b0 = ((int)blockIdx.x / Q) * geo.nb;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
@@ -389,15 +382,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
             for (int cc = pre; cc < n_chunks; ++cc) issue(cc);
-#ifdef FLO_DBG_PRINT
-            if (blockIdx.x < 2 && Q > 1 && geo.H == 4) {
-                mbar_wait(bar_full, 0);
-                const uint16_t* rs = reinterpret_cast<const uint16_t*>(smem + p.ring_off);
-                const uint16_t* gs = reinterpret_cast<const uint16_t*>(wbase + wtab[0].x);
-                printf("blk %d rank %u w_off %u wtab0 (%u,%u) ring: %04x %04x %04x %04x | glob: %04x %04x %04x %04x | st.n %d slices %d\n", blockIdx.x, qrank,
-                       p.st[0].w_off, wtab[0].x, wtab[0].y, rs[0], rs[1], rs[2], rs[3], gs[0], gs[1], gs[2], gs[3], p.st[0].n, p.st[0].slices);
-            }
-#endif
         }
     } else if (warp == 5) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
@@ -555,15 +539,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += rr[j];
                         }
-#ifdef FLO_DBG_PRINT
-                        if (Q > 1 && geo.H == 4 && b == 0 && ri[t].px == 0 && c16 == 0)
-                        {
-                            const uint16_t* a16 = reinterpret_cast<const uint16_t*>(smem + p.st[i].a0_off + ri[t].pp * 16);
-                            const uint16_t* a16b = reinterpret_cast<const uint16_t*>(smem + p.st[i].a0_off + 7 * plane_bytes + ri[t].pp * 16);
-                            printf("epi blk %d rank %u c0 %d: acc %f %f %f %f  (slot %d) smem_base %x tmem %x A[pl0] %04x %04x %04x %04x A[pl7] %04x %04x %04x %04x pp %d a0_off %d\n", blockIdx.x, qrank, c0, v[0], v[1], v[2], v[3], od.slot_off, smem_base, tmem_base,
-                                   a16[0], a16[1], a16[2], a16[3], a16b[0], a16b[1], a16b[2], a16b[3], ri[t].pp, p.st[i].a0_off);
-                        }
-#endif
                         write_outputs(od, geo, smem, plane_bytes, ri[t], b, c0 + c16, v, fmt);
                     }
                 }
@@ -786,10 +761,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
 
 cudaError_t attn_configure();
 cudaError_t fused_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_chain<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     return attn_configure();
 }
@@ -819,12 +795,13 @@ cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStr
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
     const void* fn;
     switch (p.n_mtiles) {
-        case 1: fn = (const void*)k_chain<1>; break;
-        case 2: fn = (const void*)k_chain<2>; break;
-        case 3: fn = (const void*)k_chain<3>; break;
-        case 4: fn = (const void*)k_chain<4>; break;
+        case 1: fn = p.nsplit > 1 ? (const void*)k_chain<1, true> : (const void*)k_chain<1, false>; break;
+        case 2: fn = (const void*)k_chain<2, false>; break;
+        case 3: fn = (const void*)k_chain<3, false>; break;
+        case 4: fn = (const void*)k_chain<4, false>; break;
         default: return cudaErrorInvalidValue;
     }
+    if (p.nsplit > 1 && p.n_mtiles != 1) return cudaErrorInvalidValue;
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
     return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);
 }
