@@ -109,23 +109,38 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
         if (elect_one()) {
             uint32_t b_lo = (x.ring_lo + (uint32_t)slot * x.ring_slot16) | b_lbo;
             const int32_t* tp = c.tab + ks0;
-            int32_t cur = tp[0];
-            for (int s = 0; s < cnt; ++s) {
-                const int32_t nxt = tp[s + 1];                   // the table has one spare entry per conv
+            const int n_conv = min(cnt, conv_slices - ks0);      // slices of this chunk that are convolution slices
+            uint32_t acc = ks0 > 0 ? 1u : 0u;                    // the very first slice overwrites the accumulator
+            auto mma_slice = [&](int32_t e) {
                 const uint64_t bdesc = desc64(b_lo, b_hi);
-                if (ks0 + s == conv_slices) {
-                    const uint64_t adesc = desc64(x.ones_lo | (8u << 16), x.desc_hi_ones);     // rows [1,1,0..]; K half 1 = zeros
+                const uint32_t a_base = (uint32_t)e | a_lbo;
 #pragma unroll
-                    for (int t = 0; t < MT; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
-                } else {
-                    const uint32_t a_base = (uint32_t)cur | a_lbo;
-                    const uint32_t acc = (ks0 + s) > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int t = 0; t < MT; ++t)
-                        umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), desc64(a_base + x.row0[t], x.desc_hi_a), bdesc, idesc, acc);
-                }
-                cur = nxt;
+                for (int t = 0; t < MT; ++t)
+                    umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), desc64(a_base + x.row0[t], x.desc_hi_a), bdesc, idesc, acc);
+                acc = 1u;
                 b_lo += slice16;
+            };
+            // groups of GRP slices: the table entries of the next group are loaded before this group's MMAs are issued
+            constexpr int GRP = MT == 1 ? 4 : 2;
+            int s = 0;
+            int32_t e[GRP], f[GRP];
+#pragma unroll
+            for (int k = 0; k < GRP; ++k) e[k] = (n_conv >= GRP) ? tp[k] : 0;
+            for (; s + GRP <= n_conv; s += GRP) {
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) f[k] = (s + 2 * GRP <= n_conv) ? tp[s + GRP + k] : 0;
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) mma_slice(e[k]);
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) e[k] = f[k];
+            }
+            for (; s < n_conv; ++s) mma_slice(tp[s]);
+            if (ks0 + cnt == c.slices) {
+                // bias slice: rows [1,1,0..] x (bias hi, bias lo); K half 1 = zeros
+                const uint64_t bdesc = desc64(b_lo, b_hi);
+                const uint64_t adesc = desc64(x.ones_lo | (8u << 16), x.desc_hi_ones);
+#pragma unroll
+                for (int t = 0; t < MT; ++t) umma_bf16(x.tmem_base + (uint32_t)(c.col + t * c.n), adesc, bdesc, idesc, 1u);
             }
             umma_commit(x.bar_empty + 8 * slot);
         }
