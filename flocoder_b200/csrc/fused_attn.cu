@@ -87,6 +87,40 @@ __device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, 
     }
 }
 
+
+// Column maximum over the lanes of a segment for 16 channels held per lane.  A butterfly would move all 16 values at
+// every step (16 shuffles x log2(seg)); here every step also halves the channels a lane is responsible for, so the
+// exchange costs 8 + 4 + 2 + 1 (+1) shuffles.  On return lane L holds `CNT` channels starting at channel `chan`.
+template <int M>
+__device__ __forceinline__ void colmax_halve(float (&v)[16], bool upper, int o) {
+#pragma unroll
+    for (int j = 0; j < M / 2; ++j) {
+        const float send = upper ? v[j] : v[j + M / 2];
+        const float keep = upper ? v[j + M / 2] : v[j];
+        v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+}
+template <int SEG>
+__device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
+    int chan = 0;
+    if (SEG == 32) {
+        colmax_halve<16>(v, lane & 16, 16); chan += (lane & 16) ? 8 : 0;
+        colmax_halve<8>(v, lane & 8, 8);    chan += (lane & 8) ? 4 : 0;
+        colmax_halve<4>(v, lane & 4, 4);    chan += (lane & 4) ? 2 : 0;
+        colmax_halve<2>(v, lane & 2, 2);    chan += (lane & 2) ? 1 : 0;
+        v[0] = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
+    } else if (SEG == 16) {
+        colmax_halve<16>(v, lane & 8, 8); chan += (lane & 8) ? 8 : 0;
+        colmax_halve<8>(v, lane & 4, 4);  chan += (lane & 4) ? 4 : 0;
+        colmax_halve<4>(v, lane & 2, 2);  chan += (lane & 2) ? 2 : 0;
+        colmax_halve<2>(v, lane & 1, 1);  chan += (lane & 1) ? 1 : 0;
+    } else {   // SEG == 4: four channels per lane remain
+        colmax_halve<16>(v, lane & 2, 2); chan += (lane & 2) ? 8 : 0;
+        colmax_halve<8>(v, lane & 1, 1);  chan += (lane & 1) ? 4 : 0;
+    }
+    return chan;
+}
+
 __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -233,19 +267,28 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = -INFINITY;
                     }
-                    // butterfly over the lanes of one sample; every step runs over all 16 channels at once (ILP)
-                    for (int o = seg >> 1; o > 0; o >>= 1) {
+                    if (seg == 32) {
+                        const int chan = colmax16<32>(v, lane);
+                        if ((lane & 1) == 0) kpart[(t * 4 + warp) * 128 + c16 + chan] = v[0];
+                    } else if (seg == 16) {
+                        const int chan = colmax16<16>(v, lane);
+                        if (s < p.nb) kmax[s * 128 + c16 + chan] = v[0];
+                    } else if (seg == 4) {
+                        const int chan = colmax16<4>(v, lane);
+                        if (s < p.nb) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
-                    }
-                    if (n >= 32) {
-                        if (lane == 0) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) kpart[(t * 4 + warp) * 128 + c16 + j] = v[j];
+                            for (int j = 0; j < 4; ++j) kmax[s * 128 + c16 + chan + j] = v[j];
                         }
-                    } else if ((lane & (seg - 1)) == 0 && s < p.nb) {
+                    } else {
+                        // generic butterfly over the lanes of one sample
+                        for (int o = seg >> 1; o > 0; o >>= 1) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) kmax[s * 128 + c16 + j] = v[j];
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
+                        }
+                        if ((lane & (seg - 1)) == 0 && s < p.nb) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) kmax[s * 128 + c16 + j] = v[j];
+                        }
                     }
                 }
             }
