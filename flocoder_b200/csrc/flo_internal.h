@@ -259,6 +259,7 @@ struct ChainParams {
 // linear-attention block  Residual(PreNorm(dim, LinearAttention(dim)))  (unet.py:33-39,125-161) and the
 // mid-block full attention (unet.py:99-122), one kernel, `nb` samples per CTA
 struct AttnFusedParams {
+    int epi_warps;                          // 4, or 8 when a sample spans two M tiles (one tile per warp group)
     int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
                                             // n_mtiles = 128-row tiles of the dense rows (s*n + p)
     int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)

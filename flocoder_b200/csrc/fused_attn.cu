@@ -121,10 +121,14 @@ __device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
     return chan;
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
+__global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    // Warp roles: [0, EW) epilogue (EW = 4, or 8 when a sample spans two M tiles: one tile per warp group, both groups
+    // share the TMEM lane quadrants), EW = TMA producer, EW + 1 = MMA issuer.
+    const int EW = p.epi_warps, n_epi = EW * 32, n_thr = (int)blockDim.x;
+    const int w_prod = EW, w_mma = EW + 1;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_base + p.bar_off;
     const uint32_t bar_empty = bar_full + 8 * MAX_WSTAGES;
@@ -140,15 +144,15 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     const uint32_t xh_plane = (uint32_t)(p.nb * n) * 16u;
     const int mtS = (n + 127) / 128;                    // 128-row tiles per sample in the out contraction
 
-    if (warp == 4 && lane == 0) {
+    if (warp == w_prod && lane == 0) {
         for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
-        mbar_init(bar_epi, EPI_THREADS);
+        mbar_init(bar_epi, n_epi);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    for (int i = tid * 16; i < p.zero_bytes; i += FUSED_THREADS * 16)
+    if (warp == w_mma) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    for (int i = tid * 16; i < p.zero_bytes; i += n_thr * 16)
         *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     if (dbg && tid == 0) dbg[101] = global_ns();
     const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
 
-    if (warp == 4) {
+    if (warp == w_prod) {
         if (lane == 0) {
             const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(p.n_ring, total);
             for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
             for (int g = pre; g < total; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
         }
-    } else if (warp == 5) {
+    } else if (warp == w_mma) {
         {   // whole warp, warp-uniform; one elected lane issues the tcgen05 instructions
             RingA rs{0};
             mbar_wait(bar_load, 0);
@@ -241,13 +245,17 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             __syncwarp();
         }
     } else {
-        const int r = warp * 32 + lane;
-        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int quad = warp & 3, half = warp >> 2;           // TMEM lane quadrant; which warp group
+        const int r = quad * 32 + lane;                        // row inside an M tile == TMEM lane
+        const int et = half * 128 + r;                         // epilogue thread index
+        const int t0 = half, tstep = EW >> 2;                  // M tiles / samples are dealt round-robin to the warp groups
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        auto esync = [&]() { named_bar_sync(1, n_epi); };
         float* kmax = reinterpret_cast<float*>(smem + p.kmax_off);          // [nb][128]
         float* kpart = kmax + p.nb * 128;                                   // [n_mtiles*4][128]
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);    // [n_mtiles*128]
         float2* partial = rowstat + p.n_mtiles * 128;
-        float2* stat = partial + EPI_THREADS;
+        float2* stat = partial + 256;
         int ph = 0;
         griddep_wait();
         mbar_wait(bar_load, 0);
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             // ================= EPI 0: column softmax numerators of K, V to shared memory =================
             const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
             for (int c16 = 0; c16 < 128; c16 += 16) {
-                for (int t = 0; t < p.n_mtiles; ++t) {
+                for (int t = t0; t < p.n_mtiles; t += tstep) {
                     const int rd = t * 128 + r, s = rd / n;
                     const bool valid = s < p.nb && b0 + s < p.B;
                     float v[16];
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     }
                     if (seg == 32) {
                         const int chan = colmax16<32>(v, lane);
-                        if ((lane & 1) == 0) kpart[(t * 4 + warp) * 128 + c16 + chan] = v[0];
+                        if ((lane & 1) == 0) kpart[(t * 4 + quad) * 128 + c16 + chan] = v[0];
                     } else if (seg == 16) {
                         const int chan = colmax16<16>(v, lane);
                         if (s < p.nb) kmax[s * 128 + c16 + chan] = v[0];
@@ -293,18 +301,18 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                 }
             }
             if (dbg && r == 0) dbg[3] = clock64();
-            epi_sync();
+            esync();
             if (n >= 32) {
                 const int wps = n / 32;                      // warp-rows per sample
-                for (int idx = r; idx < p.nb * 128; idx += EPI_THREADS) {
+                for (int idx = et; idx < p.nb * 128; idx += n_epi) {
                     const int s = idx >> 7, c = idx & 127;
                     float m = -INFINITY;
                     for (int w = 0; w < wps; ++w) m = fmaxf(m, kpart[(s * wps + w) * 128 + c]);
                     kmax[idx] = m;
                 }
-                epi_sync();
+                esync();
             }
-            for (int t = 0; t < p.n_mtiles; ++t) {
+            for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
@@ -336,8 +344,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             tc_fence_after();
             if (dbg && r == 0) dbg[10] = clock64();
             {
-                const int h = warp, d = lane;                // TMEM row r = (h, d)
-                for (int s = 0; s < p.nb; ++s) {
+                const int h = quad, d = lane;                // TMEM row r = (h, d)
+                for (int s = t0; s < p.nb; s += tstep) {
                     float c0[16], c1[16], sm[16];
                     tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32), c0);
                     tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32 + 16), c1);
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     }
                 }
             }
-            for (int t = 0; t < p.n_mtiles; ++t) {
+            for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
@@ -384,7 +392,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             tc_fence_after();
             if (dbg && r == 0) dbg[18] = clock64();
             for (int s = 0; s < p.nb; ++s)
-                for (int t = 0; t < mtS; ++t) {
+                for (int t = (mtS > 1 ? t0 : 0); t < mtS; t += (mtS > 1 ? tstep : 1)) {
+                    if (mtS == 1 && half != (s % tstep)) continue;      // one-tile samples: round-robin over the warp groups
                     const int px = t * 128 + r;
                     const bool valid = px < n && b0 + s < p.B;
                     const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                 *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
                 *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, p.fmt);
             }
-            epi_sync();
+            esync();
             float o[128];
             for (int h = 0; h < 4; ++h) {
                 float q[32];
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
                     }
                 }
             }
-            epi_sync();                                      // everyone is done reading K/V rows
+            esync();                                      // everyone is done reading K/V rows
             (void)i;
 #pragma unroll
             for (int cb = 0; cb < 16; ++cb)
@@ -478,7 +487,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
         if (dbg && r == 0) dbg[26] = clock64();
         const float* bias = p.fblob + p.bo_off;
         if (!p.full) {
-            for (int t = 0; t < p.n_mtiles; ++t) {
+            for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd / n;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 float sx = 0.f, sq = 0.f;
@@ -492,30 +501,30 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
             }
             // per-sample totals in a fixed order (deterministic)
             int parts = 1;
-            while (parts * 2 * p.nb <= EPI_THREADS && parts < 16) parts *= 2;
-            epi_sync();
-            if (r < p.nb * parts) {
-                const int part = r % parts, s = r / parts;
+            while (parts * 2 * p.nb <= 128 && parts < 16) parts *= 2;
+            esync();
+            if (et < p.nb * parts) {
+                const int part = et % parts, s = et / parts;
                 const int per = (n + parts - 1) / parts;
                 const int a = s * n + part * per, bnd = min((s + 1) * n, a + per);
                 float sx = 0.f, sq = 0.f;
                 for (int k = a; k < bnd; ++k) { sx += rowstat[k].x; sq += rowstat[k].y; }
-                partial[r] = make_float2(sx, sq);
+                partial[et] = make_float2(sx, sq);
             }
-            epi_sync();
-            if (r < p.nb) {
+            esync();
+            if (et < p.nb) {
                 float sx = 0.f, sq = 0.f;
-                for (int k = 0; k < parts; ++k) { sx += partial[r * parts + k].x; sq += partial[r * parts + k].y; }
+                for (int k = 0; k < parts; ++k) { sx += partial[et * parts + k].x; sq += partial[et * parts + k].y; }
                 const float cnt = (float)(C * n);
                 const float mean = sx / cnt;
                 const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-                stat[r] = make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
+                stat[et] = make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
             }
-            epi_sync();
+            esync();
         }
         const float* gamma = p.fblob + p.gamma_off;
         const float* beta = p.fblob + p.beta_off;
-        for (int t = 0; t < p.n_mtiles; ++t) {
+        for (int t = t0; t < p.n_mtiles; t += tstep) {
             const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
             const bool valid = s < p.nb && b0 + s < p.B;
             const int b = b0 + s;
@@ -541,7 +550,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_attn(const __grid_constant__ 
     __syncthreads();
     if (dbg && tid == 0) dbg[65] = clock64();
     if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
-    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == w_mma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 cudaError_t attn_configure() {
@@ -551,7 +560,7 @@ cudaError_t attn_configure() {
 cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
     void* args[2] = {(void*)&xh_map, (void*)&p};
-    return launch_pdl((const void*)k_attn, grid, FUSED_THREADS, (size_t)p.smem_bytes, s, args, 1);
+    return launch_pdl((const void*)k_attn, grid, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, 1);
 }
 
 }  // namespace flo

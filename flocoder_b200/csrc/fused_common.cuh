@@ -31,6 +31,7 @@ __device__ __forceinline__ void unpack8(uint4 u, float* v, int fmt) {
     float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt), c = unpack2(u.z, fmt), d = unpack2(u.w, fmt);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+constexpr int ATTN_MAX_THREADS = 320;   // k_attn with 8 epilogue warps
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, EPI_THREADS); }
 
 
