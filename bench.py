@@ -218,17 +218,20 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_ms = {}
+
+    def timed(fn, steps, tag):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
             if not os.environ.get("FLO_BENCH_NOFLUSH"):
                 flush.zero_()
             fn()
-        e1.record()
+            ev[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        step_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]
+        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -239,18 +242,20 @@ def run_gpu_arm(args):
     if rank == 0 and not os.environ.get("FLO_BENCH_NOCLOCK"):
         clocks.start()
     for _ in range(max(args.warmup, 3)):
+        flush.zero_()                    # also warms torch's fill kernel (its lazy first load cost 10-230 ms inside step 1)
         step_resident()
     torch.cuda.synchronize()
     clocks.samples.clear(); clocks.reasons.clear()
     l0 = eng.launch_count()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps, "resident")
     launches = eng.launch_count() - l0
     clk = clocks.stop() if rank == 0 else {}
     value = world * B * args.steps / (ms * 1e-3)
 
     for _ in range(2):
+        flush.zero_()
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, "e2e")
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -300,7 +305,8 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.dtype], "data": "synthetic",
-        "config": dict(workload_config(world, B, args.dtype), kernels="layerwise" if args.layerwise else "fused-stage"),
+        "config": dict(workload_config(world, B, args.dtype), kernels="layerwise" if args.layerwise else "fused-stage",
+                       step_ms=step_ms),
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
                    "samples": clk.get("samples", 0)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 4 * LATENT[0] * LATENT[1] * LATENT[2],
