@@ -42,6 +42,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def traffic_per_launch(kernel, args, batch):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json); only
+    quoted when the run matches the captured configuration (fused path, bf16/fp16, batch 256), else null."""
+    if args.layerwise or args.dtype == "fp32" or batch != 256:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def workload_config(n_gpus, per_gpu_batch, dtype):
     return {
         "workload": f"flowers_sd latent U-Net (dim=16, mults 1-2-4-8, n_classes={N_CLASSES}, random init seed 1234), "
@@ -284,7 +296,7 @@ def run_gpu_arm(args):
     roofline = {
         "bound": "tensor", "kernel": f"{KIND[dom]}, {gd['n']} launches/forward",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": (achieved / peak) if peak else None, "traffic": None,
+        "frac": (achieved / peak) if peak else None, "traffic": traffic_per_launch(KIND[dom].split(" ")[0], args, B),
         "peak_source": f"{peaks['source']} burst bf16 cuBLAS (kernel timed alone)",
         "share_of_forward": gd["ms"] / fwd_ms if fwd_ms > 0 else None,
         "end_to_end_tensor_frac_of_sustained": value / world * NFE * CONV_FLOP_PER_SAMPLE_FORWARD / 1e12 / peaks["bf16_tflops_sustained"],
