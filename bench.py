@@ -115,7 +115,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * PER_GPU_BATCH / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, PER_GPU_BATCH, "fp32"),
+        # the same workload label as the GPU arm at this N; the host's cores process it sample by sample, so the
+        # throughput of the bounded sample (one shard-sized batch) is the throughput of the whole job
+        "config": workload_config(max(1, args.gpus), PER_GPU_BATCH, "fp32"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
