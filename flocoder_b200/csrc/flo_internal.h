@@ -242,7 +242,8 @@ struct ChainParams {
     int ring_off, ring_slot_bytes, n_ring;
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start
-    int wtab_off, n_chunks;                 // weight chunk list (byte offset into wblob, bytes), built at kernel start
+    int wtab_off, n_chunks;                 // weight chunk list (byte offset into wblob, bytes)
+    int tabs_off;                           // both tables, host-built, in fblob: int32 atab[tab_n], then uint2 wtab[nsplit][n_chunks]
     int nsplit;                             // output channels split over this many CTAs of a cluster (1 = none)
     int xpart_off;                          // [nsplit][nb] float2 partial PreNorm statistics exchanged through DSMEM
     int fmt;                                // 16-bit operand format: 1 = bf16, 0 = fp16

@@ -149,25 +149,6 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
         x.rp.next(x.n_ring);
     }
 }
-// Table of A start addresses for one conv: slice ks = (tap, channel-block pair cp); pairs [0, a0_pairs) come from
-// slot a0, the rest from slot a1 (the channel concat of the up path, unet.py:349,353).
-__device__ __forceinline__ void build_conv_table(int32_t* tab, int conv_slices, int ksize, int a0_16, int a0_pairs, int a1_16,
-                                                 int a1_pairs, int two_planes, int Wp, int tid) {
-    const int pairs = a0_pairs + a1_pairs;
-    for (int ks = tid; ks < conv_slices; ks += FUSED_THREADS) {
-        const int tap = ks / pairs, cp = ks - tap * pairs;
-        const int shift = (ksize == 3) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
-        const int plane = (cp < a0_pairs) ? a0_16 + cp * two_planes : a1_16 + (cp - a0_pairs) * two_planes;
-        tab[ks] = plane + shift;
-    }
-}
-// producer side of the same chunk sequence: (byte offset into wblob, bytes) per chunk, built at kernel start
-__device__ __forceinline__ void build_chunk_table(uint2* wtab, unsigned w_off, int slices, int S, int n, int tid) {
-    const int nchunks = (slices + S - 1) / S;
-    for (int c = tid; c < nchunks; c += FUSED_THREADS)
-        wtab[c] = make_uint2(w_off * 2u + (uint32_t)(c * S) * (uint32_t)n * 32u, (uint32_t)min(S, slices - c * S) * (uint32_t)n * 32u);
-}
-
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
@@ -327,25 +308,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,1,0,0,0,0,0,0] per row (bias hi + lo); plane 1: zeros
             *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? ones2 : 0u, 0, 0, 0);
     }
+    // the host-built tables (fused_plan.inc, end_chain) into shared memory; descriptor address field = 14 bits of
+    // (CTA-local address >> 4): in a cluster the shared window address carries the CTA rank in its upper bits,
+    // which must not leak into the LBO field
     int32_t* atab = reinterpret_cast<int32_t*>(smem + p.tab_off);
-    uint2* wtab_w = reinterpret_cast<uint2*>(smem + p.wtab_off);
-    for (int i = 0; i < n_steps; ++i) {
-        if (!p.st[i].has_conv) continue;
-        // each CTA of an N-split cluster streams its own contiguous [slices][n] weight stream
-        build_chunk_table(wtab_w + p.st[i].chunk0, p.st[i].w_off + qrank * (unsigned)(p.st[i].slices * p.st[i].n * 16), p.st[i].slices,
-                          p.st[i].slices_per_chunk, p.st[i].n, tid);
-        if (p.st[i].has_res)
-            build_chunk_table(wtab_w + p.st[i].res_chunk0, p.st[i].wres_off + qrank * (unsigned)(p.st[i].res_slices * p.st[i].n * 16),
-                              p.st[i].res_slices, p.st[i].res_slices_per_chunk, p.st[i].n, tid);
-        // descriptor address field: 14 bits of (CTA-local address >> 4); in a cluster the shared window address carries the CTA rank
-        // in its upper bits, which must not leak into the LBO field
-        const int a0_16 = (int)(((smem_base + p.st[i].a0_off) >> 4) & 0x3FFFu), a1_16 = (int)(((smem_base + p.st[i].a1_off) >> 4) & 0x3FFFu);
-        const int two_planes = (int)(plane_bytes >> 4) * 2;
-        build_conv_table(atab + p.st[i].tab_idx, p.st[i].slices - 1, p.st[i].ksize, a0_16, p.st[i].a0_ncb >> 1, a1_16,
-                         p.st[i].a1_ncb >> 1, two_planes, geo.Wp, tid);
-        if (p.st[i].has_res)
-            build_conv_table(atab + p.st[i].res_tab_idx, p.st[i].res_slices - 1, 1, a0_16, p.st[i].a0_ncb >> 1, a1_16,
-                             p.st[i].a1_ncb >> 1, two_planes, geo.Wp, tid);
+    {
+        const int32_t* gtab = reinterpret_cast<const int32_t*>(p.fblob + p.tabs_off);
+        const int base16 = (int)((smem_base >> 4) & 0x3FFFu);
+        const int tab_n = p.tab_n, n_chunks = p.n_chunks;
+        for (int i = tid; i < tab_n; i += FUSED_THREADS) atab[i] = gtab[i] + base16;
+        const uint2* gw = reinterpret_cast<const uint2*>(gtab + tab_n) + (size_t)qrank * n_chunks;
+        uint2* wtab_w = reinterpret_cast<uint2*>(smem + p.wtab_off);
+        for (int i = tid; i < n_chunks; i += FUSED_THREADS) wtab_w[i] = gw[i];
     }
     fence_proxy_async();
     tc_fence_before();
