@@ -257,6 +257,15 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         float2* partial = rowstat + p.n_mtiles * 128;
         float2* stat = partial + 256;
         int ph = 0;
+        // to_out bias and GroupNorm affine into shared memory while the first MMAs run (they are read per channel chunk
+        // in the last epilogue, where a cold global line per chunk was 1k cycles on the critical path)
+        float* par = reinterpret_cast<float*>(stat + 128);                  // [3][128]: bias, gamma, beta
+        for (int c = et; c < C; c += n_epi) {
+            par[c] = p.fblob[p.bo_off + c];
+            par[128 + c] = p.full ? 1.0f : p.fblob[p.gamma_off + c];
+            par[256 + c] = p.full ? 0.0f : p.fblob[p.beta_off + c];
+        }
+        esync();
         griddep_wait();
         mbar_wait(bar_load, 0);
         mbar_wait(bar_mma, ph & 1); ++ph;
@@ -410,41 +419,65 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             tc_fence_before();
             mbar_arrive(bar_epi);
         } else {
-            // ================= mid attention: softmax(q k^T) v per row on CUDA cores =================
-            // K rows -> p_off region [row][128], V rows -> v_off region [row][128] (16-bit)
-            const int rd = r, s = rd / n, i = rd - s * n;
-            const bool valid = s < p.nb && b0 + s < p.B;
-            for (int c16 = 0; c16 < 128; c16 += 16) {
-                float kv[16], vv[16];
-                tmem_ld16(tlane + (uint32_t)(p.col_k + c16), kv);
-                tmem_ld16(tlane + (uint32_t)(p.col_v + c16), vv);
-                uint8_t* kd = smem + p.p_off + (uint32_t)rd * 256u + (uint32_t)c16 * 2u;
-                uint8_t* vd = smem + p.v_off + (uint32_t)rd * 256u + (uint32_t)c16 * 2u;
-                *reinterpret_cast<uint4*>(kd) = pack8(kv, p.fmt);
-                *reinterpret_cast<uint4*>(kd + 16) = pack8(kv + 8, p.fmt);
-                *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
-                *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, p.fmt);
+            // ================= mid attention: softmax(q k^T) v on CUDA cores (unet.py:99-122) =================
+            // A CTA owns nb = 32/n samples = 32 rows (TMEM lane quadrant 0).  Warp 0 moves K, V (16-bit) and Q (fp32)
+            // from TMEM to shared memory; then thread (row = lane, head = warp) does one head of one query row.
+            // Bank-conflict-free strides: K/V rows are stored key-pixel-major (index j*nb + s) with a 272-byte pitch, so the
+            // 8 samples a warp reads for one key pixel j are 272 bytes apart; Q rows have a 528-byte pitch.
+            constexpr uint32_t KP = 272u;
+            constexpr int QP = 132;
+            uint8_t* kbuf = smem + p.v_off;                    // [n][nb] rows of 128 16-bit values
+            uint8_t* vbuf = kbuf + 32 * KP;
+            float* qbuf = reinterpret_cast<float*>(vbuf + 32 * KP);      // [32] rows of 128 fp32
+            if (warp == 0) {
+                for (int c16 = 0; c16 < 128; c16 += 16) {
+                    uint32_t ku[16], vu[16], qu[16];
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + c16), ku);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_v + c16), vu);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_q + c16), qu);
+                    tmem_ld_wait();
+                    float kv[16], vv[16], qv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); qv[j] = __uint_as_float(qu[j]); }
+                    const uint32_t kvrow = (uint32_t)((lane % n) * p.nb + lane / n);
+                    uint8_t* kd = kbuf + kvrow * KP + (uint32_t)c16 * 2u;
+                    uint8_t* vd = vbuf + kvrow * KP + (uint32_t)c16 * 2u;
+                    *reinterpret_cast<uint4*>(kd) = pack8(kv, p.fmt);
+                    *reinterpret_cast<uint4*>(kd + 16) = pack8(kv + 8, p.fmt);
+                    *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
+                    *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, p.fmt);
+                    float4* qd = reinterpret_cast<float4*>(qbuf + lane * QP + c16);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) qd[k4] = make_float4(qv[4 * k4], qv[4 * k4 + 1], qv[4 * k4 + 2], qv[4 * k4 + 3]);
+                }
             }
             esync();
-            float o[128];
-            for (int h = 0; h < 4; ++h) {
+            {
+                const int row = lane, h = warp;
+                const int s = row / n;
+                const bool valid = b0 + s < p.B;
                 float q[32];
-                tmem_ld16(tlane + (uint32_t)(p.col_q + h * 32), q);
-                tmem_ld16(tlane + (uint32_t)(p.col_q + h * 32 + 16), q + 16);
+                const float4* qs = reinterpret_cast<const float4*>(qbuf + row * QP + h * 32);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 t4 = qs[k4];
+                    q[4 * k4] = t4.x * 0.17677669529663687f; q[4 * k4 + 1] = t4.y * 0.17677669529663687f;
+                    q[4 * k4 + 2] = t4.z * 0.17677669529663687f; q[4 * k4 + 3] = t4.w * 0.17677669529663687f;
+                }
                 float sim[16];
                 float m = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     sim[j] = -INFINITY;
-                    if (j < n && valid) {
-                        const uint8_t* kr = smem + p.p_off + (uint32_t)(s * n + j) * 256u + (uint32_t)h * 64u;
+                    if (j < n) {
+                        const uint8_t* kr = kbuf + (uint32_t)(j * p.nb + s) * KP + (uint32_t)h * 64u;
                         float a = 0.f;
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) {
                             float kk[8];
                             unpack8(*reinterpret_cast<const uint4*>(kr + cb * 16), kk, p.fmt);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) a = fmaf(q[cb * 8 + e] * 0.17677669529663687f, kk[e], a);
+                            for (int e = 0; e < 8; ++e) a = fmaf(q[cb * 8 + e], kk[e], a);
                         }
                         sim[j] = a;
                         m = fmaxf(m, a);
@@ -452,30 +485,34 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
                 float sum = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { sim[j] = (j < n && valid) ? fast_exp(sim[j] - m) : 0.f; sum += sim[j]; }
-                const float inv = valid ? 1.0f / sum : 0.f;
+                for (int j = 0; j < 16; ++j) { sim[j] = (j < n) ? fast_exp(sim[j] - m) : 0.f; sum += sim[j]; }
+                const float inv = 1.0f / sum;
+                float o[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) o[h * 32 + e] = 0.f;
+                for (int e = 0; e < 32; ++e) o[e] = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    if (j < n && valid) {
-                        const uint8_t* vr = smem + p.v_off + (uint32_t)(s * n + j) * 256u + (uint32_t)h * 64u;
+                    if (j < n) {
+                        const uint8_t* vr = vbuf + (uint32_t)(j * p.nb + s) * KP + (uint32_t)h * 64u;
                         const float a = sim[j] * inv;
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) {
                             float vv[8];
                             unpack8(*reinterpret_cast<const uint4*>(vr + cb * 16), vv, p.fmt);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) o[h * 32 + cb * 8 + e] = fmaf(a, vv[e], o[h * 32 + cb * 8 + e]);
+                            for (int e = 0; e < 8; ++e) o[cb * 8 + e] = fmaf(a, vv[e], o[cb * 8 + e]);
                         }
                     }
                 }
-            }
-            esync();                                      // everyone is done reading K/V rows
-            (void)i;
+                if (!valid) {
 #pragma unroll
-            for (int cb = 0; cb < 16; ++cb)
-                *reinterpret_cast<uint4*>(smem + p.p_off + (uint32_t)cb * plane + (uint32_t)rd * 16u) = pack8(o + cb * 8, p.fmt);
+                    for (int e = 0; e < 32; ++e) o[e] = 0.f;
+                }
+                // 'b h (x y) d -> b (h d) x y' (unet.py:121): channel = h*32 + d, as the A operand of the to_out conv
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+                    *reinterpret_cast<uint4*>(smem + p.p_off + (uint32_t)(4 * h + cb) * plane + (uint32_t)row * 16u) = pack8(o + cb * 8, p.fmt);
+            }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_epi);
@@ -485,7 +522,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
         if (dbg && r == 0) dbg[26] = clock64();
-        const float* bias = p.fblob + p.bo_off;
+        const float* bias = par;
         if (!p.full) {
             for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd / n;
@@ -522,27 +559,71 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
             esync();
         }
-        const float* gamma = p.fblob + p.gamma_off;
-        const float* beta = p.fblob + p.beta_off;
-        for (int t = t0; t < p.n_mtiles; t += tstep) {
-            const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
-            const bool valid = s < p.nb && b0 + s < p.B;
-            const int b = b0 + s;
-            const float2 ms = (!p.full && s < p.nb) ? stat[s] : make_float2(0.f, 1.f);
-            for (int c16 = 0; c16 < C; c16 += 16) {
-                float v[16], x2[16];
-                tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
-                if (!valid) continue;
-                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
-                unpack8(xsrc[(size_t)((c16 >> 3) * p.B + b) * n + px], x2, p.fmt);
-                unpack8(xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * n + px], x2 + 8, p.fmt);
+        const float* gamma = par + 128;
+        const float* beta = par + 256;
+        if (p.full) {
+            // 32 valid rows (TMEM quadrant 0): warp 0 moves the projection to shared memory, then every warp finishes a
+            // quarter of the channels: + bias + x (unet.py:122, Residual)
+            constexpr int QP = 132;
+            float* ybuf = reinterpret_cast<float*>(smem + p.v_off);          // the K/V/Q staging is dead by now
+            if (warp == 0) {
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + c16), v);
+                    float4* yd = reinterpret_cast<float4*>(ybuf + lane * QP + c16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float y = v[j] + bias[c16 + j];
-                    if (!p.full) y = (y - ms.x) * ms.y * gamma[c16 + j] + beta[c16 + j];
-                    v[j] = y + x2[j];
+                    for (int k4 = 0; k4 < 4; ++k4) yd[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
                 }
-                attn_write_out(p, b, px, c16, v);
+            }
+            esync();
+            const int row = lane, s = row / n, px = row - s * n, b = b0 + s;
+            const int cq = C >> 2;                                           // channels per warp
+            if (b < p.B) {
+                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+                for (int c16 = warp * cq; c16 < (warp + 1) * cq; c16 += 16) {
+                    const uint4 xa = xsrc[(size_t)((c16 >> 3) * p.B + b) * n + px];
+                    const uint4 xb = xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * n + px];
+                    float v[16], x2[16];
+                    const float4* ys = reinterpret_cast<const float4*>(ybuf + row * QP + c16);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) { const float4 t4 = ys[k4]; v[4 * k4] = t4.x; v[4 * k4 + 1] = t4.y; v[4 * k4 + 2] = t4.z; v[4 * k4 + 3] = t4.w; }
+                    unpack8(xa, x2, p.fmt);
+                    unpack8(xb, x2 + 8, p.fmt);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] + bias[c16 + j] + x2[j];
+                    attn_write_out(p, b, px, c16, v);
+                }
+            }
+        } else {
+            for (int t = t0; t < p.n_mtiles; t += tstep) {
+                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const bool valid = s < p.nb && b0 + s < p.B;
+                const int b = b0 + s;
+                const float2 ms = s < p.nb ? stat[s] : make_float2(0.f, 1.f);
+                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+                // the residual rows of the NEXT channel chunk are requested before this chunk is processed
+                uint4 xa = make_uint4(0, 0, 0, 0), xb = xa;
+                if (valid) { xa = xsrc[(size_t)(0 * p.B + b) * n + px]; xb = xsrc[(size_t)(1 * p.B + b) * n + px]; }
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    uint4 na = make_uint4(0, 0, 0, 0), nb4 = na;
+                    if (valid && c16 + 16 < C) {
+                        na = xsrc[(size_t)(((c16 >> 3) + 2) * p.B + b) * n + px];
+                        nb4 = xsrc[(size_t)(((c16 >> 3) + 3) * p.B + b) * n + px];
+                    }
+                    float v[16], x2[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+                    if (valid) {
+                        unpack8(xa, x2, p.fmt);
+                        unpack8(xb, x2 + 8, p.fmt);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float y = (v[j] + bias[c16 + j] - ms.x) * ms.y * gamma[c16 + j] + beta[c16 + j];
+                            v[j] = y + x2[j];
+                        }
+                        attn_write_out(p, b, px, c16, v);
+                    }
+                    xa = na; xb = nb4;
+                }
             }
         }
     }
