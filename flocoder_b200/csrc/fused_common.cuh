@@ -46,6 +46,14 @@ __device__ __forceinline__ float fast_rcp(float x) {
     float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
 // SiLU (unet.py:67 nn.SiLU): y * sigmoid(y)
+#ifdef FLO_SILU_TANH
+// one MUFU instead of two: sigmoid(y) = 0.5 + 0.5 tanh(y/2)
+__device__ __forceinline__ float fast_silu(float y) {
+    float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+    return y * fmaf(0.5f, t, 0.5f);
+}
+#else
 __device__ __forceinline__ float fast_silu(float y) { return y * fast_rcp(1.0f + fast_exp(-y)); }
+#endif
 
 }  // namespace flo
