@@ -441,28 +441,31 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
     for (int i = tid * 16; i < 96 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) {
-        mbar_init(smem_u32(&bar), 1);
+        mbar_init(smem_u32(&bar), n_acc < 0 ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int cols = 32;
-    while (cols < N * n_acc) cols <<= 1;
+    while (cols < N * (n_acc < 0 ? 2 : n_acc)) cols <<= 1;
     if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(&tslot);
     long long t0 = 0, t1 = 0;
-    if (warp == 1) {
+    const bool dual = n_acc < 0;                 // two issuing warps (1 and 2), one accumulator each, barrier count 2
+    const int nacc = dual ? 1 : n_acc;
+    if (warp == 1 || (dual && warp == 2)) {
         const uint32_t idesc = make_idesc_bf16(128, N);
         const uint32_t base = smem_u32(smem);
         const uint64_t ad0 = make_smem_desc(base, 2048u, 128u);                  // A: LBO = 2 KB plane, SBO = 128 B
         const uint64_t bd0 = make_smem_desc(base + 64 * 1024, (uint32_t)N * 16u, 128u);
+        const uint32_t tcol = tbase + (uint32_t)((warp - 1) * N);
         t0 = clock64();
         if (elect_one()) {
-            const uint32_t acc_mask = (uint32_t)(n_acc - 1);
+            const uint32_t acc_mask = (uint32_t)(nacc - 1);
 #pragma unroll 4
             for (int i = 0; i < n_mma; ++i)
-                umma_bf16(tbase + ((uint32_t)i & acc_mask) * (uint32_t)N, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
+                umma_bf16(tcol + ((uint32_t)i & acc_mask) * (uint32_t)N, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
             umma_commit(smem_u32(&bar));
         }
         __syncwarp();

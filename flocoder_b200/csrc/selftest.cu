@@ -237,7 +237,7 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
         long long* dc; long long hc[2];
         ST_CUDA(cudaMalloc(&dc, 16));
         const int Ns[4] = {16, 32, 64, 128}, counts[4] = {1, 8, 32, 128};
-        for (int acc = 1; acc <= 2; ++acc)
+        for (int acc = -1; acc <= 1; acc += 2)       // -1: two issuing warps, one accumulator each; 1: one issuer
             for (int ni = 0; ni < 4; ++ni) {
                 char buf[256]; int o = snprintf(buf, sizeof(buf), "INFO umma_rate N=%-3d acc=%d :", Ns[ni], acc);
                 for (int ci = 0; ci < 4; ++ci) {
