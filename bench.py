@@ -101,15 +101,23 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     batch, intervals = PER_GPU_BATCH, 1
-    for _ in range(args.warmup):
-        cpu_sample(batch, intervals, threads)
-    vals, secs = [], 0.0
-    for _ in range(args.steps):
+    # Bounded sample: one RK4 interval of the workload batch per step; if (warmup + steps) of those would not finish in
+    # about 2.5 minutes on this host, the later steps use a proportionally smaller batch (throughput is per sample).
+    budget_s, t_used, n_left = 150.0, 0.0, args.warmup + args.steps
+    vals, secs, batches = [], 0.0, []
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         v, s = cpu_sample(batch, intervals, threads)
-        vals.append(v)
-        secs += s
+        t_used += time.perf_counter() - t0
+        n_left -= 1
+        if k >= args.warmup:
+            vals.append(v); secs += s; batches.append(batch)
+        if n_left > 0:
+            per_sample = (time.perf_counter() - t0) / batch
+            fit = int((budget_s - t_used) / n_left / per_sample) if per_sample > 0 else batch
+            batch = max(8, min(PER_GPU_BATCH, (fit // 8) * 8))
     value = sum(vals) / len(vals)
-    sample = (f"per step: B={batch}, {intervals} of 49 RK4 intervals ({4 * intervals} of {NFE} evaluations) of the "
+    sample = (f"per step: B={batches if len(set(batches)) > 1 else batches[0]}, {intervals} of 49 RK4 intervals ({4 * intervals} of {NFE} evaluations) of the "
               f"CPU oracle (PyTorch fp32, test-proven equal to the reference), scaled by 49/{intervals}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
