@@ -95,7 +95,9 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
     if (c->n_classes < 0) { set_error("n_classes < 0"); return FLO_ERR_INVALID; }
     s.dim = c->dim; s.channels = c->channels; s.n_levels = c->n_mults; s.groups = c->groups;
     s.n_classes = c->n_classes; s.H = c->height; s.W = c->width; s.bf16 = c->compute_dtype != FLO_F32;
-    s.f16 = c->compute_dtype == FLO_F16; s.fused = s.bf16 && !(c->flags & FLO_FLAG_LAYERWISE);
+    s.f16 = c->compute_dtype == FLO_F16;
+    // fused stage kernels: latent channels <= 4 (registers of the final epilogue); otherwise the layer-wise tcgen05 path
+    s.fused = s.bf16 && !(c->flags & FLO_FLAG_LAYERWISE) && c->channels <= 4;
     s.flags = c->flags; s.device = c->device;
     s.dims.clear();
     s.dims.push_back(c->dim);

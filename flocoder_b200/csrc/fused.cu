@@ -120,19 +120,28 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
                 acc = 1u;
                 b_lo += slice16;
             };
-            // groups of GRP slices: the table entries of the next group are loaded before this group's MMAs are issued
-            constexpr int GRP = MT == 1 ? 4 : 2;
             int s = 0;
-            int32_t e[GRP], f[GRP];
+            if constexpr (MT == 1) {
+                // groups of four slices: the table entries of the next group are loaded before this group's MMAs are issued
+                int32_t e[4], f[4];
 #pragma unroll
-            for (int k = 0; k < GRP; ++k) e[k] = (n_conv >= GRP) ? tp[k] : 0;
-            for (; s + GRP <= n_conv; s += GRP) {
+                for (int k = 0; k < 4; ++k) e[k] = (n_conv >= 4) ? tp[k] : 0;
+                for (; s + 4 <= n_conv; s += 4) {
 #pragma unroll
-                for (int k = 0; k < GRP; ++k) f[k] = (s + 2 * GRP <= n_conv) ? tp[s + GRP + k] : 0;
+                    for (int k = 0; k < 4; ++k) f[k] = (s + 8 <= n_conv) ? tp[s + 4 + k] : 0;
 #pragma unroll
-                for (int k = 0; k < GRP; ++k) mma_slice(e[k]);
+                    for (int k = 0; k < 4; ++k) mma_slice(e[k]);
 #pragma unroll
-                for (int k = 0; k < GRP; ++k) e[k] = f[k];
+                    for (int k = 0; k < 4; ++k) e[k] = f[k];
+                }
+            } else {
+                // several M tiles per slice: one entry ahead is enough (and keeps the register count of the kernel down)
+                int32_t cur = n_conv > 0 ? tp[0] : 0;
+                for (; s < n_conv; ++s) {
+                    const int32_t nxt = tp[s + 1];               // the table has one spare entry per conv
+                    mma_slice(cur);
+                    cur = nxt;
+                }
             }
             for (; s < n_conv; ++s) mma_slice(tp[s]);
             if (ks0 + cnt == c.slices) {
@@ -263,6 +272,7 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
 // k_chain
 // ------------------------------------------------------------------------------------------------
 // SPLIT: the N-split (cluster) variant; false compiles every cluster / DSMEM path out (Q == 1, c0 == 0 fold away)
+constexpr int FINAL_MAX_CH = 4;     // latent channels the fused final epilogue handles (api.cu routes more to the layer-wise path)
 template <int MT, bool SPLIT>
 __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
@@ -589,13 +599,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 if (dbg && r == 0) dbg[i * 8 + 4] = clock64();
                 // pass 2: y = x*scale + offset, SiLU, + residual, write.  Chunk-major so that the TMEM loads of all
                 // tiles are in flight together and the per-element chains of MT*16 values interleave.
-                float kacc[MT][16];
+                float kacc[MT][FINAL_MAX_CH];       // final 1x1 conv accumulators (latent channels; fused path: <= 4)
                 float psx[MT], psq[MT];
 #pragma unroll
                 for (int t = 0; t < MT; ++t) {
                     psx[t] = 0.f; psq[t] = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) kacc[t][j] = 0.f;
+                    for (int j = 0; j < FINAL_MAX_CH; ++j) kacc[t][j] = 0.f;
                 }
                 for (int c16 = 0; c16 < C; c16 += 16) {
                     uint32_t av[MT][16], rv[MT][16];
@@ -631,7 +641,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         if (is_final) {
                             const int nch = p.channels, dim = p.dim;
 #pragma unroll
-                            for (int co = 0; co < 16; ++co) {
+                            for (int co = 0; co < FINAL_MAX_CH; ++co) {
                                 if (co < nch) {
                                     float a = kacc[t][co];
 #pragma unroll
@@ -644,6 +654,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         }
                     }
                 }
+                // the integrator state this thread will update in the last epilogue is requested in one batch (8 independent
+                // loads in flight instead of a dependent chain per element); the control block's pointers are read once
+                float fy[MT][4], fa[MT][4], fc[MT][4];
+                float *Y = nullptr, *ACC = nullptr, *XS = nullptr, *VOUT = nullptr, *VC = nullptr, *VT = nullptr;
+                float cfg_s = 0.f;
+                const bool fast_final = is_final && p.channels <= 4;
+                if (is_final) {
+                    Y = ctrl->y; ACC = ctrl->acc; XS = ctrl->xs; VOUT = ctrl->vout; VC = ctrl->vcond; VT = ctrl->vtrace; cfg_s = ctrl->cfg;
+                }
+                if (fast_final) {
+                    const int nch = p.channels;
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)
+#pragma unroll
+                        for (int co = 0; co < 4; ++co) {
+                            fy[t][co] = 0.f; fa[t][co] = 0.f; fc[t][co] = 0.f;
+                            if (ri[t].valid && co < nch) {
+                                const size_t o = ((size_t)(b0 + ri[t].s) * nch + co) * HW + ri[t].px;
+                                if (sg.kind != ST_PLAIN && sg.kind != ST_CFG_COND) fy[t][co] = Y[o];
+                                if (sg.kind == ST_RK2 || sg.kind == ST_RK3 || sg.kind == ST_RK4) fa[t][co] = ACC[o];
+                                if (sg.flags & SF_CFG_COMBINE) fc[t][co] = VC[o];
+                            }
+                        }
+                }
 #pragma unroll
                 for (int t = 0; t < MT; ++t) {
                     const bool valid = ri[t].valid;
@@ -654,34 +688,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                         const int nch = p.channels, dim = p.dim;
                         const size_t plane = (size_t)geo.B * nch * HW;
 #pragma unroll
-                        for (int co = 0; co < 16; ++co) {
+                        for (int co = 0; co < FINAL_MAX_CH; ++co) {
                             if (co >= nch) continue;
                             float k = kacc[t][co] + cpar[nch * dim + co];
                             const size_t o = ((size_t)b * nch + co) * HW + ri[t].px;
-                            if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(ctrl->cfg, __fsub_rn(ctrl->vcond[o], k)));
-                            if (ctrl->vtrace && sg.eval_idx >= 0) ctrl->vtrace[(size_t)sg.eval_idx * plane + o] = k;
+                            // prefetched operands on the common (channels <= 4) path, direct loads otherwise
+                            const bool pre = fast_final;
+                            if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(cfg_s, __fsub_rn(pre ? fc[t][co & 3] : VC[o], k)));
+                            if (VT && sg.eval_idx >= 0) VT[(size_t)sg.eval_idx * plane + o] = k;
                             switch (sg.kind) {
-                                case ST_PLAIN: ctrl->vout[o] = k; break;
-                                case ST_CFG_COND: ctrl->vcond[o] = k; break;
+                                case ST_PLAIN: VOUT[o] = k; break;
+                                case ST_CFG_COND: VC[o] = k; break;
                                 case ST_RK1:
-                                    ctrl->acc[o] = k;
-                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
+                                    ACC[o] = k;
+                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
                                     break;
                                 case ST_RK2:
-                                    ctrl->acc[o] = __fadd_rn(ctrl->acc[o], __fmul_rn(2.0f, k));
-                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
+                                    ACC[o] = __fadd_rn(pre ? fa[t][co & 3] : ACC[o], __fmul_rn(2.0f, k));
+                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
                                     break;
                                 case ST_RK3:
-                                    ctrl->acc[o] = __fadd_rn(ctrl->acc[o], __fmul_rn(2.0f, k));
-                                    ctrl->xs[o] = __fadd_rn(ctrl->y[o], __fmul_rn(sg.dt, k));
+                                    ACC[o] = __fadd_rn(pre ? fa[t][co & 3] : ACC[o], __fmul_rn(2.0f, k));
+                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(sg.dt, k));
                                     break;
                                 case ST_RK4: {
-                                    const float yn = __fadd_rn(ctrl->y[o], __fmul_rn(sg.dt6, __fadd_rn(ctrl->acc[o], k)));
-                                    ctrl->y[o] = yn; ctrl->xs[o] = yn;
+                                    const float yn = __fadd_rn(pre ? fy[t][co & 3] : Y[o],
+                                                               __fmul_rn(sg.dt6, __fadd_rn(pre ? fa[t][co & 3] : ACC[o], k)));
+                                    Y[o] = yn; XS[o] = yn;
                                 } break;
                                 case ST_EULER: {
-                                    const float yn = __fadd_rn(ctrl->y[o], __fmul_rn(k, sg.dt));
-                                    ctrl->y[o] = yn; ctrl->xs[o] = yn;
+                                    const float yn = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(k, sg.dt));
+                                    Y[o] = yn; XS[o] = yn;
                                 } break;
                                 default: break;
                             }
