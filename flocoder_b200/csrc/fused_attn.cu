@@ -274,37 +274,52 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         if (!p.full) {
             // ================= EPI 0: column softmax numerators of K, V to shared memory =================
             const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
-            for (int c16 = 0; c16 < 128; c16 += 16) {
-                for (int t = t0; t < p.n_mtiles; t += tstep) {
-                    const int rd = t * 128 + r, s = rd / n;
-                    const bool valid = s < p.nb && b0 + s < p.B;
-                    float v[16];
-                    tmem_ld16(tlane + (uint32_t)(p.col_k + t * 128 + c16), v);
-                    if (!valid) {
+            // two 16-channel chunks per iteration: both TMEM loads are in flight together and the two shuffle
+            // reductions are independent, so their latencies overlap
+            for (int t = t0; t < p.n_mtiles; t += tstep) {
+                const int rd = t * 128 + r, s = rd / n;
+                const bool valid = s < p.nb && b0 + s < p.B;
+                for (int c32 = 0; c32 < 128; c32 += 32) {
+                    uint32_t ua[16], ub[16];
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c32), ua);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c32 + 16), ub);
+                    tmem_ld_wait();
+                    float va[16], vb[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = -INFINITY;
+                    for (int j = 0; j < 16; ++j) {
+                        va[j] = valid ? __uint_as_float(ua[j]) : -INFINITY;
+                        vb[j] = valid ? __uint_as_float(ub[j]) : -INFINITY;
                     }
                     if (seg == 32) {
-                        const int chan = colmax16<32>(v, lane);
-                        if ((lane & 1) == 0) kpart[(t * 4 + quad) * 128 + c16 + chan] = v[0];
+                        const int ca = colmax16<32>(va, lane);
+                        const int cb = colmax16<32>(vb, lane);
+                        if ((lane & 1) == 0) {
+                            kpart[(t * 4 + quad) * 128 + c32 + ca] = va[0];
+                            kpart[(t * 4 + quad) * 128 + c32 + 16 + cb] = vb[0];
+                        }
                     } else if (seg == 16) {
-                        const int chan = colmax16<16>(v, lane);
-                        if (s < p.nb) kmax[s * 128 + c16 + chan] = v[0];
+                        const int ca = colmax16<16>(va, lane);
+                        const int cb = colmax16<16>(vb, lane);
+                        if (s < p.nb) { kmax[s * 128 + c32 + ca] = va[0]; kmax[s * 128 + c32 + 16 + cb] = vb[0]; }
                     } else if (seg == 4) {
-                        const int chan = colmax16<4>(v, lane);
+                        const int ca = colmax16<4>(va, lane);
+                        const int cb = colmax16<4>(vb, lane);
                         if (s < p.nb) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) kmax[s * 128 + c16 + chan + j] = v[j];
+                            for (int j = 0; j < 4; ++j) { kmax[s * 128 + c32 + ca + j] = va[j]; kmax[s * 128 + c32 + 16 + cb + j] = vb[j]; }
                         }
                     } else {
                         // generic butterfly over the lanes of one sample
                         for (int o = seg >> 1; o > 0; o >>= 1) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], o));
+                            for (int j = 0; j < 16; ++j) {
+                                va[j] = fmaxf(va[j], __shfl_xor_sync(0xffffffffu, va[j], o));
+                                vb[j] = fmaxf(vb[j], __shfl_xor_sync(0xffffffffu, vb[j], o));
+                            }
                         }
                         if ((lane & (seg - 1)) == 0 && s < p.nb) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) kmax[s * 128 + c16 + j] = v[j];
+                            for (int j = 0; j < 16; ++j) { kmax[s * 128 + c32 + j] = va[j]; kmax[s * 128 + c32 + 16 + j] = vb[j]; }
                         }
                     }
                 }
@@ -326,10 +341,14 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 for (int c16 = 0; c16 < 128; c16 += 16) {
-                    float kv[16], vv[16];
-                    tmem_ld16(tlane + (uint32_t)(p.col_k + t * 128 + c16), kv);
-                    tmem_ld16(tlane + (uint32_t)(p.col_v + t * 128 + c16), vv);
+                    uint32_t ku[16], vu[16];
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c16), ku);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_v + t * 128 + c16), vu);
+                    tmem_ld_wait();
                     if (!valid) continue;
+                    float kv[16], vv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) kv[j] = fast_exp(kv[j] - kmax[s * 128 + c16 + j]);
                     uint8_t* pd = smem + p.p_off + (uint32_t)(c16 >> 3) * plane + row_off;
@@ -374,10 +393,14 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 for (int h = 0; h < 4; ++h) {
-                    float q[32];
-                    tmem_ld16(tlane + (uint32_t)(p.col_q + t * 128 + h * 32), q);
-                    tmem_ld16(tlane + (uint32_t)(p.col_q + t * 128 + h * 32 + 16), q + 16);
+                    uint32_t qa[16], qb[16];
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + h * 32), qa);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + h * 32 + 16), qb);
+                    tmem_ld_wait();
                     if (!valid) continue;
+                    float q[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { q[j] = __uint_as_float(qa[j]); q[16 + j] = __uint_as_float(qb[j]); }
                     float m = q[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) m = fmaxf(m, q[j]);
