@@ -349,8 +349,13 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     float kv[16], vv[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); }
+                    const float4* km4 = reinterpret_cast<const float4*>(kmax + s * 128 + c16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) kv[j] = fast_exp(kv[j] - kmax[s * 128 + c16 + j]);
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 m4 = km4[k4];
+                        kv[4 * k4] = fast_exp(kv[4 * k4] - m4.x); kv[4 * k4 + 1] = fast_exp(kv[4 * k4 + 1] - m4.y);
+                        kv[4 * k4 + 2] = fast_exp(kv[4 * k4 + 2] - m4.z); kv[4 * k4 + 3] = fast_exp(kv[4 * k4 + 3] - m4.w);
+                    }
                     uint8_t* pd = smem + p.p_off + (uint32_t)(c16 >> 3) * plane + row_off;
                     uint8_t* vd = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
                     *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
@@ -429,13 +434,18 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const int px = t * 128 + r;
                     const bool valid = px < n && b0 + s < p.B;
                     const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
-                    for (int c16 = 0; c16 < 128; c16 += 16) {
-                        float v[16];
-                        tmem_ld16(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c16), v);
+                    for (int c32 = 0; c32 < 128; c32 += 32) {
+                        uint32_t ua[16], ub[16];
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c32), ua);
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c32 + 16), ub);
+                        tmem_ld_wait();
                         if (!valid) continue;
-                        uint8_t* od = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
-                        *reinterpret_cast<uint4*>(od) = pack8(v, p.fmt);
-                        *reinterpret_cast<uint4*>(od + plane) = pack8(v + 8, p.fmt);
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(ua[j]); v[16 + j] = __uint_as_float(ub[j]); }
+                        uint8_t* od = smem + p.v_off + (uint32_t)(c32 >> 3) * plane + row_off;
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(od + (uint32_t)k8 * plane) = pack8(v + 8 * k8, p.fmt);
                     }
                 }
             fence_proxy_async();
