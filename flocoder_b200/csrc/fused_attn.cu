@@ -379,11 +379,15 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             {
                 const int h = quad, d = lane;                // TMEM row r = (h, d)
                 for (int s = t0; s < p.nb; s += tstep) {
-                    float c0[16], c1[16], sm[16];
-                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32), c0);
-                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32 + 16), c1);
-                    tmem_ld16(tlane + (uint32_t)(p.col_ctx + s * 144 + 128), sm);
-                    const float inv = 0.17677669529663687f / sm[0];      // 32^-0.5 / sum_n exp(k - max)
+                    uint32_t u0[16], u1[16], us[16];
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32), u0);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32 + 16), u1);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + 128), us);
+                    tmem_ld_wait();
+                    float c0[16], c1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { c0[j] = __uint_as_float(u0[j]); c1[j] = __uint_as_float(u1[j]); }
+                    const float inv = 0.17677669529663687f / __uint_as_float(us[0]);      // 32^-0.5 / sum_n exp(k - max)
                     uint8_t* base = smem + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
@@ -397,27 +401,36 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
-                for (int h = 0; h < 4; ++h) {
-                    uint32_t qa[16], qb[16];
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + h * 32), qa);
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + h * 32 + 16), qb);
+                // two heads per iteration (four TMEM loads in flight, two independent softmax chains); max and sum as
+                // 4-way trees instead of 32-long dependent chains
+                for (int h2 = 0; h2 < 4; h2 += 2) {
+                    uint32_t qu[2][32];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + (h2 + k) * 32), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][0]));
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + (h2 + k) * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][16]));
+                    }
                     tmem_ld_wait();
                     if (!valid) continue;
-                    float q[32];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { q[j] = __uint_as_float(qa[j]); q[16 + j] = __uint_as_float(qb[j]); }
-                    float m = q[0];
+                    for (int k = 0; k < 2; ++k) {
+                        float q[32];
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, q[j]);
-                    float sum = 0.f;
+                        for (int j = 0; j < 32; ++j) q[j] = __uint_as_float(qu[k][j]);
+                        float m4[4] = {q[0], q[1], q[2], q[3]};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { q[j] = fast_exp(q[j] - m); sum += q[j]; }
-                    const float inv = 1.0f / sum;
+                        for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], q[j]);
+                        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) q[j] *= inv;
-                    uint8_t* qd = smem + p.p_off + (uint32_t)(4 * h) * plane + row_off;
+                        for (int j = 0; j < 32; ++j) { q[j] = fast_exp(q[j] - m); s4[j & 3] += q[j]; }
+                        const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, p.fmt);
+                        for (int j = 0; j < 32; ++j) q[j] *= inv;
+                        uint8_t* qd = smem + p.p_off + (uint32_t)(4 * (h2 + k)) * plane + row_off;
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, p.fmt);
+                    }
                 }
             }
             if (dbg && r == 0) dbg[11] = clock64();
@@ -561,12 +574,21 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int rd = t * 128 + r, s = rd / n;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 float sx = 0.f, sq = 0.f;
-                for (int c16 = 0; c16 < C; c16 += 16) {
-                    float v[16];
-                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+                float sx2 = 0.f, sq2 = 0.f;
+                for (int c16 = 0; c16 < C; c16 += 32) {
+                    uint32_t ua[16], ub[16];
+                    const bool two = c16 + 16 < C;
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_proj + t * C + c16), ua);
+                    if (two) tmem_ld16_issue(tlane + (uint32_t)(p.col_proj + t * C + c16 + 16), ub);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float x = v[j] + bias[c16 + j]; sx += x; sq += x * x; }
+                    for (int j = 0; j < 16; ++j) { const float x = __uint_as_float(ua[j]) + bias[c16 + j]; sx += x; sq += x * x; }
+                    if (two) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { const float x = __uint_as_float(ub[j]) + bias[c16 + 16 + j]; sx2 += x; sq2 += x * x; }
+                    }
                 }
+                sx += sx2; sq += sq2;
                 rowstat[rd] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
             }
             // per-sample totals in a fixed order (deterministic)
