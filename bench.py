@@ -301,14 +301,22 @@ def run_gpu_arm(args):
     fwd_ms = sum(ms_ops)
     dom = max((k for k in groups if k in (1, 6, 7)), key=lambda k: groups[k]["ms"])
     gd = groups[dom]
-    achieved = gd["flop"] / (gd["ms"] * 1e-3) / 1e12 if gd["ms"] > 0 else 0.0
-    peak = peaks["bf16_tflops"] if args.dtype in ("bf16", "fp16") else None
+    # Event records between launches add ~6 us per launch that the graph replay of the timed region does not have, so the
+    # kernel's duration inside the step is taken as (its share of the event-timed forward) x (the forward time of the
+    # timed region); the raw event-timed figure is reported next to it.
+    fwd_ms_in_step = ms / args.steps / NFE
+    share = gd["ms"] / fwd_ms if fwd_ms > 0 else 0.0
+    ms_in_step = share * fwd_ms_in_step
+    achieved = gd["flop"] / (ms_in_step * 1e-3) / 1e12 if ms_in_step > 0 else 0.0
+    achieved_event = gd["flop"] / (gd["ms"] * 1e-3) / 1e12 if gd["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"] if args.dtype in ("bf16", "fp16") else None      # kernel timed inside a long step
     roofline = {
         "bound": "tensor", "kernel": f"{KIND[dom]}, {gd['n']} launches/forward",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if peak else None, "traffic": traffic_per_launch(KIND[dom].split(" ")[0], args, B),
-        "peak_source": f"{peaks['source']} burst bf16 cuBLAS (kernel timed alone)",
-        "share_of_forward": gd["ms"] / fwd_ms if fwd_ms > 0 else None,
+        "peak_source": f"{peaks['source']} sustained bf16 cuBLAS (kernel duration taken inside the timed step)",
+        "share_of_forward": share, "kernel_ms_per_forward_in_step": ms_in_step, "forward_ms_in_step": fwd_ms_in_step,
+        "achieved_event_timed_alone": achieved_event,
         "end_to_end_tensor_frac_of_sustained": value / world * NFE * CONV_FLOP_PER_SAMPLE_FORWARD / 1e12 / peaks["bf16_tflops_sustained"],
         "forward_ms_sum_of_kernels": fwd_ms,
         "kernels": {KIND[k].split(" ")[0]: {"launches": g["n"], "ms": g["ms"], "conv_tflops": g["flop"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0,
