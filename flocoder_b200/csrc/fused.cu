@@ -513,9 +513,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = cpar[C * cin0 + c16 + j];
+                            if (cin0 == 4) {          // the usual latent: one 16-byte weight row per output channel
+                                const float4 w4 = *reinterpret_cast<const float4*>(cpar + (c16 + j) * 4);
+                                a = fmaf(xin[0], w4.x, a); a = fmaf(xin[1], w4.y, a); a = fmaf(xin[2], w4.z, a); a = fmaf(xin[3], w4.w, a);
+                            } else {
 #pragma unroll
-                            for (int ci = 0; ci < 16; ++ci)
-                                if (ci < cin0) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
+                                for (int ci = 0; ci < 16; ++ci)
+                                    if (ci < cin0) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
+                            }
                             v[j] = a;
                         }
                         write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);

@@ -173,6 +173,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to the shared memory of any CTA of the cluster -> visible to the async proxy (tcgen05.mma operands)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 
 }  // namespace flo
