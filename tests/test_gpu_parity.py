@@ -302,3 +302,30 @@ def test_bf16_param_dtype_follows_module(goldens):
     v = m(g["x0"].cuda().to(torch.bfloat16), g["fwd_t"].cuda())
     assert v.dtype == torch.bfloat16
     assert rel_l2(v.float(), g["fwd_v"]) <= 3e-2          # weights themselves are bf16-rounded here
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 7, 13, 100, 300, 600])
+def test_ragged_and_large_batches_fused_vs_fp32_path(B):
+    """Batch sizes that leave the last CTA / cluster group partly empty (1, 7, 13, 100) and sizes that select the other
+    N-split variants of the low-resolution stages (<= 296: clusters of 4; 300: clusters of 2; 600: no split).  The
+    fp16 fused path must stay within the per-step bar of the fp32 CUDA path (itself pinned to the reference above),
+    per sample, and a class-conditional CFG trajectory must stay within the final-latent bar."""
+    from flocoder_b200 import sampling
+    m16 = gpu_model(102, "fp16")
+    m32 = gpu_model(102, "fp32")
+    gen = torch.Generator().manual_seed(4242 + B)
+    x = torch.randn(B, 4, 16, 16, generator=gen).cuda()
+    t = (torch.rand(B, generator=gen) * 999).cuda()                      # per-sample times: per-sample FiLM rows
+    cls = torch.randint(0, 102, (B,), generator=gen).cuda()
+    for cond in (None, {"class_cond": cls}):
+        v16 = m16(x, t, cond).float()
+        v32 = m32(x, t, cond).float()
+        per_sample = (v16 - v32).flatten(1).norm(dim=1) / v32.flatten(1).norm(dim=1)
+        assert torch.isfinite(v16).all()
+        assert float(per_sample.max()) <= 3e-3, (B, float(per_sample.max()))     # worst single sample
+        assert rel_l2(v16, v32) <= 2e-3
+    if B <= 100:
+        x16, _ = sampling.generate_latents_rk4(m16, (B, 4, 16, 16), n_steps=6, cond={"class_cond": cls}, cfg_strength=3.0, source=x)
+        x32, _ = sampling.generate_latents_rk4(m32, (B, 4, 16, 16), n_steps=6, cond={"class_cond": cls}, cfg_strength=3.0, source=x)
+        assert rel_l2(x16, x32) <= BF16_FINAL_TOL
