@@ -923,6 +923,14 @@ int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const
     Builder b(*h);
     rc = b.build();
     if (rc) return rc;
+    // the layer-wise GroupNorm kernel (fp32 path, FLO_FLAG_LAYERWISE) keeps one (sample, group) unit in the registers of a CTA
+    if (!h->spec.fused)
+        for (const Op& op : h->ops)
+            if (op.kind == OP_GN && (op.C / op.groups) * op.H * op.W > 8192) {
+                set_error("GroupNorm '%s' normalises %d elements per (sample, group); the layer-wise path holds at most 8192 "
+                          "(use a 16-bit compute_dtype for this dim / latent size)", op.name.c_str(), (op.C / op.groups) * op.H * op.W);
+                return FLO_ERR_UNSUPPORTED;
+            }
     allocate_arena(*h);
     if (h->spec.fused) {
         FusedBuilder fb(*h, h->ftensors, h->fstages, 4);

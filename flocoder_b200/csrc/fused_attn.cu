@@ -632,10 +632,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
             esync();
             const int row = lane, s = row / n, px = row - s * n, b = b0 + s;
-            const int cq = C >> 2;                                           // channels per warp
             if (b < p.B) {
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
-                for (int c16 = warp * cq; c16 < (warp + 1) * cq; c16 += 16) {
+                for (int c16 = warp * 16; c16 < C; c16 += 64) {              // 16-channel chunks round-robin over the warps
                     const uint4 xa = xsrc[(size_t)((c16 >> 3) * p.B + b) * n + px];
                     const uint4 xb = xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * n + px];
                     float v[16], x2[16];

@@ -329,3 +329,29 @@ def test_ragged_and_large_batches_fused_vs_fp32_path(B):
         x16, _ = sampling.generate_latents_rk4(m16, (B, 4, 16, 16), n_steps=6, cond={"class_cond": cls}, cfg_strength=3.0, source=x)
         x32, _ = sampling.generate_latents_rk4(m32, (B, 4, 16, 16), n_steps=6, cond={"class_cond": cls}, cfg_strength=3.0, source=x)
         assert rel_l2(x16, x32) <= BF16_FINAL_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,mults,hw,ncls", [(16, [1, 2, 4], 16, 10), (32, [1, 2, 4], 16, 0), (16, [1, 2, 4], 8, 0),
+                                               (16, [1, 1, 2, 2], 16, 0)])
+def test_other_unet_shapes_fused_vs_fp32_path(dim, mults, hw, ncls):
+    """U-Nets other than the three BASELINE configurations (other widths, depths, latent sizes) go through the same
+    planner: the fp16 fused path must agree with the fp32 CUDA path within the per-step bar."""
+    from flocoder_b200.unet import Unet
+    torch.manual_seed(7)
+    m32 = Unet(dim=dim, channels=4, dim_mults=mults, n_classes=ncls, compute_dtype="fp32").cuda().eval()
+    m16 = Unet(dim=dim, channels=4, dim_mults=mults, n_classes=ncls, compute_dtype="fp16").cuda().eval()
+    m16.load_state_dict(m32.state_dict())
+    x = torch.randn(5, 4, hw, hw).cuda()
+    t = torch.rand(5).cuda() * 999
+    assert rel_l2(m16(x, t), m32(x, t).cpu()) <= 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,mults,hw,dtype", [(16, [1, 2, 4, 8], 32, "fp16"), (32, [1, 2, 4, 8], 16, "fp16"), (64, [1, 2], 16, "fp32")])
+def test_unsupported_shapes_fail_loudly(dim, mults, hw, dtype):
+    """Outside the supported envelope the library refuses at plan time; it never falls back."""
+    from flocoder_b200.unet import Unet
+    m = Unet(dim=dim, channels=4, dim_mults=mults, n_classes=0, compute_dtype=dtype).cuda().eval()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(2, 4, hw, hw).cuda(), torch.rand(2).cuda() * 999)
