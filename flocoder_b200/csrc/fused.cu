@@ -241,7 +241,9 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
             for (int q = 0; q < n_parts; ++q)
                 st_cluster_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
                               make_float2(sx, sq));
-        for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
+        epi_sync();                      // the publishing lanes' remote stores are ordered before the release-arrives below
+        if (tid == 0)
+            for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
         mbar_wait_cluster(xc->bar_x, *xc->phase & 1u);
         ++*xc->phase;
         if (active) {
@@ -306,8 +308,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
-        mbar_init(bar_epi, EPI_THREADS * Q);
-        mbar_init(bar_x, EPI_THREADS * Q);
+        // N-split: one elected thread per CTA arrives (after a CTA-local barrier) on the barriers of every CTA of the cluster
+        mbar_init(bar_epi, SPLIT ? Q : EPI_THREADS);
+        mbar_init(bar_x, SPLIT ? Q : EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -773,9 +776,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             }
             if (dbg && r == 0) dbg[i * 8 + 5] = clock64();
             tc_fence_before();
-            if (Q > 1) {
+            if (SPLIT) {
                 fence_proxy_async_all();     // local and remote shared-memory results -> visible to every CTA's next tcgen05.mma
-                for (int q = 0; q < Q; ++q) mbar_arrive_cluster(mapa_shared(bar_epi, (uint32_t)q));
+                epi_sync();                  // every thread's stores are ordered before the elected thread's release-arrives
+                if (r == 0)
+                    for (int q = 0; q < Q; ++q) mbar_arrive_cluster(mapa_shared(bar_epi, (uint32_t)q));
             } else {
                 fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
                 mbar_arrive(bar_epi);
