@@ -139,7 +139,7 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region through NVML in a background thread (spawning
     nvidia-smi every 100 ms was measured to halve the throughput of a launch-bound step by contending for the driver)."""
 
-    def __init__(self, index, period=0.25):
+    def __init__(self, index, period=0.1):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.thread, self.stop_flag = None, False
