@@ -253,10 +253,12 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
         }
     }
     if (active) {
-        const float cnt = (float)(cpg * HW * n_parts);
-        const float mean = sx / cnt;
-        const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // reciprocal and rsqrt through MUFU (2 ulp): the IEEE division / sqrt sequences are ~100 instructions on this
+        // serial stretch between the two barriers
+        const float icnt = fast_rcp((float)(cpg * HW * n_parts));
+        const float mean = sx * icnt;
+        const float var = fmaxf(sq * icnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
         for (int c = gi * cpg + li; c < (gi + 1) * cpg; c += seg) {
             const float2 gb = gpar[c];
             float a = rstd * gb.x, bb = gb.y - mean * a;

@@ -607,10 +607,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (et < p.nb) {
                 float sx = 0.f, sq = 0.f;
                 for (int k = 0; k < parts; ++k) { sx += partial[et * parts + k].x; sq += partial[et * parts + k].y; }
-                const float cnt = (float)(C * n);
-                const float mean = sx / cnt;
-                const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-                stat[et] = make_float2(mean, 1.0f / sqrtf(var + 1e-5f));
+                const float icnt = fast_rcp((float)(C * n));
+                const float mean = sx * icnt;
+                const float var = fmaxf(sq * icnt - mean * mean, 0.f);
+                stat[et] = make_float2(mean, rsqrtf(var + 1e-5f));
             }
             esync();
         }
