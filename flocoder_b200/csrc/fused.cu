@@ -210,14 +210,16 @@ struct XChg {                    // cross-CTA (cluster) reduction of per-sample 
 };
 __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int C, int HW,
                               bool has_film, int tid, const XChg* xc = nullptr) {
-    const int combos = g.nb * G, cpg = C / G;
+    // G, C, seg are powers of two: shifts instead of runtime integer divisions on this serial stretch
+    const int lgG = 31 - __clz(G), combos = g.nb * G, cpg = C >> lgG;
     const int cpw = (combos + 3) >> 2;
     int seg = 32;
     while (seg * cpw > 32) seg >>= 1;
     const int warp = tid >> 5, lane = tid & 31;
-    const int combo = warp * (32 / seg) + lane / seg, li = lane & (seg - 1);
+    const int lgS = 31 - __clz(seg);
+    const int combo = warp * (32 >> lgS) + (lane >> lgS), li = lane & (seg - 1);
     const bool active = combo < combos;
-    const int s = active ? combo / G : 0, gi = active ? combo - s * G : 0;
+    const int s = active ? (combo >> lgG) : 0, gi = active ? (combo & (G - 1)) : 0;
     epi_sync();
     float sx = 0.f, sq = 0.f;
     if (active) {
@@ -487,9 +489,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 const float* beta = fblob + p.st[i].beta_off;
                 float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
                 for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c0 + c], beta[c0 + c]);
-                const int foff = p.st[i].film_off;
+                const int foff = p.st[i].film_off, lgC = 31 - __clz(C);
                 for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
-                    const int s = idx / C, c = idx - s * C;
+                    const int s = idx >> lgC, c = idx & (C - 1);
                     float2 f = make_float2(1.0f, 0.0f);
                     if (foff >= 0 && b0 + s < geo.B) {
                         const float* fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + foff;

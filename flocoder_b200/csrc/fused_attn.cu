@@ -67,7 +67,8 @@ __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t sme
 
 __device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, int px, int c16, const float* v) {
     const int ncb = p.C >> 3;
-    const int h = px / p.W, w = px - h * p.W;
+    const int lgW = 31 - __clz(p.W);
+    const int h = px >> lgW, w = px & (p.W - 1);
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const int cb = (c16 >> 3) + hb;
@@ -142,7 +143,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     const int n = p.n, n_pad = p.n_pad, C = p.C;
     const uint32_t plane = (uint32_t)p.plane_bytes;
     const uint32_t xh_plane = (uint32_t)(p.nb * n) * 16u;
-    const int mtS = (n + 127) / 128;                    // 128-row tiles per sample in the out contraction
+    const int lgn = 31 - __clz(n);                      // n = H*W is a power of two (planner): shifts, not divisions
+    const int mtS = (n + 127) >> 7;                    // 128-row tiles per sample in the out contraction
 
     if (warp == w_prod && lane == 0) {
         for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             // two 16-channel chunks per iteration: both TMEM loads are in flight together and the two shuffle
             // reductions are independent, so their latencies overlap
             for (int t = t0; t < p.n_mtiles; t += tstep) {
-                const int rd = t * 128 + r, s = rd / n;
+                const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 for (int c32 = 0; c32 < 128; c32 += 32) {
                     uint32_t ua[16], ub[16];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && r == 0) dbg[3] = clock64();
             esync();
             if (n >= 32) {
-                const int wps = n / 32;                      // warp-rows per sample
+                const int wps = n >> 5;                      // warp-rows per sample
                 for (int idx = et; idx < p.nb * 128; idx += n_epi) {
                     const int s = idx >> 7, c = idx & 127;
                     float m = -INFINITY;
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 esync();
             }
             for (int t = t0; t < p.n_mtiles; t += tstep) {
-                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 for (int c16 = 0; c16 < 128; c16 += 16) {
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     float c0[16], c1[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { c0[j] = __uint_as_float(u0[j]); c1[j] = __uint_as_float(u1[j]); }
-                    const float inv = 0.17677669529663687f / __uint_as_float(us[0]);      // 32^-0.5 / sum_n exp(k - max)
+                    const float inv = 0.17677669529663687f * fast_rcp(__uint_as_float(us[0]));      // 32^-0.5 / sum_n exp(k - max)
                     uint8_t* base = smem + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
             for (int t = t0; t < p.n_mtiles; t += tstep) {
-                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 // two heads per iteration (four TMEM loads in flight, two independent softmax chains); max and sum as
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int j = 0; j < 32; ++j) { q[j] = fast_exp(q[j] - m); s4[j & 3] += q[j]; }
-                        const float inv = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+                        const float inv = fast_rcp((s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
                         for (int j = 0; j < 32; ++j) q[j] *= inv;
                         uint8_t* qd = smem + p.p_off + (uint32_t)(4 * (h2 + k)) * plane + row_off;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     float kv[16], vv[16], qv[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); qv[j] = __uint_as_float(qu[j]); }
-                    const uint32_t kvrow = (uint32_t)((lane % n) * p.nb + lane / n);
+                    const uint32_t kvrow = (uint32_t)((lane & (n - 1)) * p.nb + (lane >> lgn));
                     uint8_t* kd = kbuf + kvrow * KP + (uint32_t)c16 * 2u;
                     uint8_t* vd = vbuf + kvrow * KP + (uint32_t)c16 * 2u;
                     *reinterpret_cast<uint4*>(kd) = pack8(kv, p.fmt);
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             esync();
             {
                 const int row = lane, h = warp;
-                const int s = row / n;
+                const int s = row >> lgn;
                 const bool valid = b0 + s < p.B;
                 float q[32];
                 const float4* qs = reinterpret_cast<const float4*>(qbuf + row * QP + h * 32);
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 float sum = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { sim[j] = (j < n) ? fast_exp(sim[j] - m) : 0.f; sum += sim[j]; }
-                const float inv = 1.0f / sum;
+                const float inv = fast_rcp(sum);
                 float o[32];
 #pragma unroll
                 for (int e = 0; e < 32; ++e) o[e] = 0.f;
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         const float* bias = par;
         if (!p.full) {
             for (int t = t0; t < p.n_mtiles; t += tstep) {
-                const int rd = t * 128 + r, s = rd / n;
+                const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 float sx = 0.f, sq = 0.f;
                 float sx2 = 0.f, sq2 = 0.f;
@@ -596,8 +598,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             while (parts * 2 * p.nb <= 128 && parts < 16) parts *= 2;
             esync();
             if (et < p.nb * parts) {
-                const int part = et % parts, s = et / parts;
-                const int per = (n + parts - 1) / parts;
+                const int lgp = 31 - __clz(parts);
+                const int part = et & (parts - 1), s = et >> lgp;
+                const int per = (n + parts - 1) >> lgp;
                 const int a = s * n + part * per, bnd = min((s + 1) * n, a + per);
                 float sx = 0.f, sq = 0.f;
                 for (int k = a; k < bnd; ++k) { sx += rowstat[k].x; sq += rowstat[k].y; }
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
             esync();
-            const int row = lane, s = row / n, px = row - s * n, b = b0 + s;
+            const int row = lane, s = row >> lgn, px = row & (n - 1), b = b0 + s;
             if (b < p.B) {
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
                 for (int c16 = warp * 16; c16 < C; c16 += 64) {              // 16-channel chunks round-robin over the warps
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
         } else {
             for (int t = t0; t < p.n_mtiles; t += tstep) {
-                const int rd = t * 128 + r, s = rd / n, px = rd - s * n;
+                const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const int b = b0 + s;
                 const float2 ms = s < p.nb ? stat[s] : make_float2(0.f, 1.f);
