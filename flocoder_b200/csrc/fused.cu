@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     // N-split: the Q CTAs of a cluster own the same samples and 1/Q of every step's output channels
     const int Q = SPLIT ? p.nsplit : 1;
     const uint32_t qrank = SPLIT ? cluster_ctarank() : 0u;
-    const int b0 = ((int)blockIdx.x / Q) * geo.nb;
+    const int lgQ = SPLIT ? 31 - __clz(Q) : 0;          // cluster sizes are powers of two
+    const int b0 = ((int)blockIdx.x >> lgQ) * geo.nb;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
     const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
     const int ones_off = p.ones_off;
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         for (int i = 0; i < n_steps; ++i) {
             // ---- step parameters into registers
             const int epi = p.st[i].epi, Ctot = p.st[i].C, acc_col = p.st[i].acc_col, res_col = p.st[i].res_col;
-            const int C = Ctot / Q, c0 = (int)qrank * C;      // this CTA's channels [c0, c0 + C) of the step's Ctot
+            const int C = Ctot >> lgQ, c0 = (int)qrank * C;      // this CTA's channels [c0, c0 + C) of the step's Ctot
             const int res_mode = p.st[i].res_mode, res_slot_off = p.st[i].res_slot_off;
             const int is_final = p.st[i].final, pn_g = p.st[i].pn_g;
             OutDst od;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 }
             } else {
                 // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
-                const int G = p.st[i].groups / Q, cpg = C / G, silu = p.st[i].silu;       // this CTA's groups
+                const int G = p.st[i].groups >> lgQ, cpg = C >> (31 - __clz(G)), silu = p.st[i].silu;       // this CTA's groups (powers of two)
                 // pass 1: per-row (sum, sumsq) per group; the TMEM loads of all tiles are issued before one wait
                 if (cpg >= 16) {
                     for (int gi = 0; gi < G; ++gi) {

@@ -21,6 +21,7 @@
 namespace flo {
 
 struct RingA { int cc; };
+constexpr int ATTN_RING = 4;       // weight ring depth of k_attn (the planner sets n_ring to it): masks, not divisions
 
 // weight chunk g of the stage: K, V, Q projections (qkv_chunks each), then to_out (o_chunks)
 __device__ __forceinline__ void attn_issue_chunk(const AttnFusedParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
@@ -31,8 +32,8 @@ __device__ __forceinline__ void attn_issue_chunk(const AttnFusedParams& p, uint3
     else if (g < 2 * qc) { w = p.wblob + p.wv_off; ci = g - qc; bytes = qkv_bytes; }
     else if (g < 3 * qc) { w = p.wblob + p.wq_off; ci = g - 2 * qc; bytes = qkv_bytes; }
     else { w = p.wblob + p.wo_off; ci = g - 3 * qc; bytes = o_bytes; }
-    const int slot = g % p.n_ring;
-    if (g >= p.n_ring) mbar_wait(bar_empty + 8 * slot, ((g / p.n_ring) - 1) & 1);
+    const int slot = g & (ATTN_RING - 1);
+    if (g >= ATTN_RING) mbar_wait(bar_empty + 8 * slot, ((g / ATTN_RING) - 1) & 1);
     mbar_expect_tx(bar_full + 8 * slot, (uint32_t)bytes);
     bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes, reinterpret_cast<const uint8_t*>(w) + (size_t)ci * bytes,
                  (uint32_t)bytes, bar_full + 8 * slot);
@@ -42,11 +43,11 @@ __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t sme
                                           uint32_t bar_empty, RingA& rs, uint32_t a_off, uint32_t a_plane, int n, int col,
                                           int n_chunks, int S) {
     const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
-    const int n_ring = p.n_ring, n_mtiles = p.n_mtiles;
+    const int n_mtiles = p.n_mtiles;
     const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
     for (int ci = 0; ci < n_chunks; ++ci) {
-        const int slot = rs.cc % n_ring;
-        mbar_wait(bar_full + 8 * slot, (rs.cc / n_ring) & 1);
+        const int slot = rs.cc & (ATTN_RING - 1);
+        mbar_wait(bar_full + 8 * slot, (rs.cc / ATTN_RING) & 1);
         tc_fence_after();
         const uint32_t bstage = smem_base + ring_off + slot * ring_slot_bytes;
         for (int s = 0; s < S; ++s) {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
 
     if (warp == w_prod) {
         if (lane == 0) {
-            const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(p.n_ring, total);
+            const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(ATTN_RING, total);
             for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
             griddep_wait();          // weights are constants; the activations come from the previous kernel
             griddep_launch();
