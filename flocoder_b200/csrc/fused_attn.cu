@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && r == 0) dbg[18] = clock64();
             for (int s = 0; s < p.nb; ++s)
                 for (int t = (mtS > 1 ? t0 : 0); t < mtS; t += (mtS > 1 ? tstep : 1)) {
-                    if (mtS == 1 && half != (s % tstep)) continue;      // one-tile samples: round-robin over the warp groups
+                    if (mtS == 1 && half != (s & (tstep - 1))) continue;      // one-tile samples: round-robin over the warp groups
                     const int px = t * 128 + r;
                     const bool valid = px < n && b0 + s < p.B;
                     const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
