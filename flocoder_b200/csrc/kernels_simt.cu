@@ -198,7 +198,9 @@ template <typename TO>
 __global__ void __launch_bounds__(256) k_gn(GnParams p) {
     __shared__ float red[32];
     const int G = p.groups, cpg = p.C / G, HW = p.H * p.W;
-    const int b = blockIdx.x / G, g = blockIdx.x % G;
+    // H, W, groups are powers of two on every supported shape (checked at plan time): shifts, not integer divisions
+    const int lgG = 31 - __clz(G), lgW = 31 - __clz(p.W), lgPC = 31 - __clz(HW * 2);
+    const int b = blockIdx.x >> lgG, g = blockIdx.x & (G - 1);
     const int nvec = cpg * HW / 4;
     const int NT = blockDim.x, tid = threadIdx.x;
     const int ncb = p.C >> 3;
@@ -215,9 +217,8 @@ __global__ void __launch_bounds__(256) k_gn(GnParams p) {
         if (i < nvec) {
             int cb, sub, px;
             if (cpg >= 8) {                 // the group spans whole channel blocks
-                const int per_cb = HW * 2;
-                cb = g * (cpg >> 3) + i / per_cb;
-                const int r = i % per_cb;
+                cb = g * (cpg >> 3) + (i >> lgPC);
+                const int r = i & (HW * 2 - 1);
                 px = r >> 1; sub = (r & 1) * 4;
             } else {                        // cpg == 4: half a channel block
                 cb = (g * 4) >> 3; sub = (g & 1) * 4; px = i;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(256) k_gn(GnParams p) {
         if (p.out_m) store4(p.out_m + offs[k], o);
         if (out_o) store4(out_o + offs[k], o);
         if (out_un || out_up) {
-            const int h = pix[k] / p.W, w = pix[k] % p.W, cb = c0 >> 3, sub = c0 & 7;
+            const int h = pix[k] >> lgW, w = pix[k] & (p.W - 1), cb = c0 >> 3, sub = c0 & 7;
             if (out_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)
                 const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
                 const int q = (h >> 1) * (p.W >> 1) + (w >> 1);

@@ -1,4 +1,4 @@
-"""Per-op CUDA-event profile of one forward (developer tool): python tools/gpu_profile.py <dtype> <B>"""
+"""Per-op CUDA-event profile of one forward (developer tool): python tools/gpu_profile.py <dtype> <B> [layerwise]"""
 import os
 import sys
 
@@ -15,6 +15,9 @@ def main():
     cd, B = sys.argv[1], int(sys.argv[2])
     torch.manual_seed(1234)
     m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, compute_dtype=cd).cuda().eval()
+    if "layerwise" in sys.argv:
+        from flocoder_b200 import _lib
+        m.engine_flags = _lib.FLO_FLAG_LAYERWISE
     eng = m.engine(16, 16)
     info = eng.op_info()
     ms = eng.profile_ops(B, reps=10)
