@@ -380,7 +380,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             const int pre = min(n_ring, n_chunks);
             for (int cc = 0; cc < pre; ++cc) issue(cc);
             griddep_wait();
-            griddep_launch();
             if (n_loads > 0) {
                 uint32_t lbytes = 0;
                 for (int i = 0; i < n_loads; ++i) lbytes += (uint32_t)p.load_ncb[i] * plane_bytes;
@@ -440,7 +439,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         const float* fblob = p.fblob;
         const int HW = geo.H * geo.W;
         griddep_wait();              // ctrl, the FiLM table and every activation come from earlier kernels
-        griddep_launch();
         void* gt[CH_MAX_GT];
 #pragma unroll
         for (int i = 0; i < CH_MAX_GT; ++i) gt[i] = p.gt[i];
@@ -504,6 +502,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             mbar_wait(bar_mma, i & 1);
             tc_fence_after();
             if (dbg && r == 0) dbg[i * 8 + 2] = clock64();
+            // programmatic dependent launch: let the next stage kernel become resident only now, during the last epilogue
+            // (its barrier init, TMEM allocation, table copy and weight prefetch overlap this kernel's tail); triggering at
+            // kernel start was measured to slow the running kernel (profiles/r01_pdl_gaps.txt)
+            if (i == n_steps - 1) griddep_launch();
 
             if (epi == CE_INIT) {
                 // ---- init_conv 1x1 from the NCHW fp32 integrator state (unet.py:295)
@@ -811,7 +813,7 @@ cudaError_t fused_configure() {
     return attn_configure();
 }
 
-static bool g_pdl = false;
+static bool g_pdl = true;
 void fused_set_pdl(bool on) { g_pdl = on; }
 cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster) {
     cudaLaunchConfig_t cfg;

@@ -182,7 +182,6 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(ATTN_RING, total);
             for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
             griddep_wait();          // weights are constants; the activations come from the previous kernel
-            griddep_launch();
             mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * xh_plane);
             tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
             for (int g = pre; g < total; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
@@ -581,6 +580,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
         if (dbg && r == 0) dbg[26] = clock64();
+        griddep_launch();            // PDL: the next stage kernel may become resident during the last epilogue
         const float* bias = par;
         if (!p.full) {
             for (int t = t0; t < p.n_mtiles; t += tstep) {
