@@ -27,7 +27,7 @@ from . import _lib
 from .unet import Unet
 
 __all__ = ["warp_time", "rk4_step", "v_func_cfg", "generate_latents_rk4", "generate_latents",
-           "euler_sampler", "time_grid"]
+           "euler_sampler", "time_grid", "g2rgb", "decode_latents", "sampler"]
 
 
 def warp_time(t, dt=None, s=.5):
@@ -173,3 +173,86 @@ def euler_sampler(model, shape, sample_N, device=None, cond=None, source=None, e
     ts32 = torch.tensor(times, dtype=torch.float64).to(torch.float32).tolist()
     eng.integrate(state, ts32, _lib.FLO_EULER_LEGACY, dt=dt, class_ids=cls, cfg_strength=0.0)
     return state.to(out_dtype).cpu(), sample_N
+
+
+# --------------------------------------------------------------------------------------------------
+# The immediate caller of the path: sampler() = conditioning set-up +
+# generate_latents + chunked decode through a user-supplied codec.  The codec itself (SD-VAE / VQGAN) is out
+# of scope: any object with .encode(images) / .decode(latents) / .parameters() works.
+# --------------------------------------------------------------------------------------------------
+def g2rgb(gf_img, keep_gray=False):
+    """Grayscale piano-roll -> quantised RGB (``metrics.py:319-327``): value >= .75 -> red, within .25 of .5 -> green,
+    else black; ``keep_gray`` gives a black/white image thresholded at .5.  3-channel input passes through."""
+    if gf_img.shape[-3] == 3:
+        return gf_img
+    g = gf_img.squeeze(-3)
+    if keep_gray:
+        return (g > 0.5).float().unsqueeze(-3).repeat(1, 3, 1, 1)
+    red = (g >= 0.75).float()
+    green = ((g - 0.5).abs() < 0.25).float()
+    return torch.stack([red, green, torch.zeros_like(g)], dim=-3)
+
+
+def decode_latents(codec, latents, is_midi=False, keep_gray=False, device=None, chunk_size=128, debug=False):
+    """Decode in chunks of ``chunk_size`` (``sampling.py:169-183``): each chunk goes to the codec's device, is decoded,
+    optionally mapped through :func:`g2rgb`, parked on the host, and the concatenation returns to ``latents.device``."""
+    if device is None:
+        try:
+            device = next(codec.parameters()).device
+        except (StopIteration, AttributeError, TypeError):
+            device = latents.device
+    out = []
+    for i in range(0, latents.shape[0], chunk_size):
+        img = codec.decode(latents[i:i + chunk_size].to(device))
+        if is_midi:
+            img = g2rgb(img, keep_gray=keep_gray)
+        out.append(img.cpu())
+    return torch.cat(out, dim=0).to(latents.device)
+
+
+@torch.no_grad()
+def sampler(model, codec, method="rk4", batch_size=256, n_steps=100, cond=None, n_classes=0, latent_shape=(4, 16, 16),
+            cfg_strength=3.0, is_midi=False, keep_gray=False, device=None, source=None, init_image=None,
+            init_strength=0.0, debug=False):
+    """``sampling.py:187-229``: returns ``(pred_latents, decoded, nfe)``.
+
+    * ``cond`` is a dict (``None`` is treated as ``{}``; the reference would raise on ``None``).  Without a
+      ``class_cond`` and with ``n_classes > 0`` it draws 10 random classes and tiles them ``batch_size // 10`` times
+      (one class per grid column, ``sampling.py:217-218``); an existing ``class_cond`` / ``mask_cond`` / ``source`` is
+      cut to ``batch_size``.
+    * ``init_image`` (a path, a PIL image or a ``[C,H,W]`` / ``[1,C,H,W]`` float tensor in [0,1]) is encoded by the codec
+      and repeated over the batch; integration then starts at ``t = init_strength`` (``sampling.py:104-109``).
+    """
+    if device is None:
+        device = next(model.parameters()).device
+    codec_device = next(codec.parameters()).device
+    assert device == codec_device, f"sampler, device mismatch: device = {device}, but  codec_device {codec_device}"
+    cond = {} if cond is None else cond
+
+    init_latents = None
+    if init_image is not None:
+        if isinstance(init_image, str):
+            from PIL import Image
+            init_image = Image.open(init_image)
+        if not torch.is_tensor(init_image):
+            from torchvision.transforms import ToTensor       # what the reference uses (sampling.py:11,208)
+            init_image = ToTensor()(init_image)
+        img = init_image if init_image.dim() == 4 else init_image.unsqueeze(0)
+        init_latents = codec.encode(img.to(device))
+        if init_latents.shape[0] == 1 and batch_size > 1:
+            init_latents = init_latents.repeat(batch_size, 1, 1, 1)
+
+    shape = (batch_size,) + tuple(latent_shape)
+    if source is not None:
+        source = source[:batch_size]
+    if cond.get("class_cond") is None and n_classes > 0:
+        cond["class_cond"] = torch.randint(n_classes, (10,)).repeat(batch_size // 10).to(device)
+    elif cond.get("class_cond") is not None:
+        cond["class_cond"] = cond["class_cond"][:batch_size]
+    if cond.get("mask_cond") is not None:
+        cond["mask_cond"] = cond["mask_cond"][:batch_size]
+
+    pred_latents, nfe = generate_latents(model, shape, method, n_steps, cond, cfg_strength, device=device, source=source,
+                                         init_latents=init_latents, init_strength=init_strength)
+    decoded = decode_latents(codec, pred_latents, is_midi, keep_gray, device=device)
+    return pred_latents, decoded, nfe

@@ -355,3 +355,29 @@ def test_unsupported_shapes_fail_loudly(dim, mults, hw, dtype):
     m = Unet(dim=dim, channels=4, dim_mults=mults, n_classes=0, compute_dtype=dtype).cuda().eval()
     with pytest.raises(NotImplementedError):
         m(torch.randn(2, 4, hw, hw).cuda(), torch.rand(2).cuda() * 999)
+
+
+@pytest.mark.gpu
+def test_sampler_with_our_unet_and_a_codec(goldens):
+    """sampler() (sampling.py:187-229) end to end on the GPU: class-conditional CFG trajectory through flo_integrate, then
+    the chunked decode through a caller-supplied codec."""
+    from torch import nn
+    from flocoder_b200 import sampling
+
+    class Codec(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dec = nn.Conv2d(4, 3, 1)
+
+        def decode(self, z):
+            return torch.sigmoid(self.dec(z))
+
+    g = goldens["flowers_sd"]
+    m = gpu_model(102, "fp32")
+    codec = Codec().cuda().eval()
+    lat, img, nfe = sampling.sampler(m, codec, method="rk4", batch_size=8, n_steps=10, cond={"class_cond": g["cls"].cuda()},
+                                     n_classes=102, cfg_strength=3.0, source=g["x0"].cuda())
+    assert nfe == 40 and img.shape == (8, 3, 16, 16) and img.device.type == "cuda"
+    assert rel_l2(lat, g["rk4_10_cfg3"]) <= 1e-5
+    with torch.no_grad():
+        assert torch.allclose(img, codec.decode(lat), atol=1e-6)
