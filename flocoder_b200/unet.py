@@ -235,3 +235,46 @@ class Unet(nn.Module):
             raise ValueError(f"time must have {b} elements, got {time.numel()}")
         v = eng.forward(x.to(torch.float32).contiguous(), time.contiguous(), cls)
         return v.to(x.dtype)
+
+
+def infer_unet_config(state_dict) -> dict:
+    """U-Net constructor arguments recoverable from a reference ``state_dict`` (``generate_samples.py:91-101`` infers only
+    ``dim`` and ``channels`` from ``init_conv.weight`` and takes the rest from a Hydra config):
+    ``dim`` / ``channels`` from ``init_conv.weight [dim, channels, 1, 1]``; ``dim_mults`` from the output width of every
+    level's down-sampling conv (``downs.{l}.3[.1].weight``, ``unet.py:251-255``); ``n_classes`` from the class embedding
+    (``class_cond_mlp.0.weight [n_classes, time_dim]``, ``unet.py:206-212``; 0 if absent).  GroupNorm group counts are not
+    stored in a state dict (reference default 4)."""
+    w0 = state_dict["init_conv.weight"]
+    dim, channels = int(w0.shape[0]), int(w0.shape[1])
+    mults, level = [], 0
+    while True:
+        key = next((k for k in (f"downs.{level}.3.1.weight", f"downs.{level}.3.weight") if k in state_dict), None)
+        if key is None:
+            break
+        dout = int(state_dict[key].shape[0])
+        if dout % dim:
+            raise ValueError(f"{key}: width {dout} is not a multiple of dim={dim}")
+        mults.append(dout // dim)
+        level += 1
+    if not mults:
+        raise ValueError("state_dict has no 'downs.*' levels: not a flocoder U-Net checkpoint")
+    emb = state_dict.get("class_cond_mlp.0.weight")
+    return {"dim": dim, "channels": channels, "dim_mults": mults, "n_classes": int(emb.shape[0]) if emb is not None else 0}
+
+
+def unet_from_checkpoint(checkpoint, device=None, compute_dtype=None, strict=False, **overrides) -> "Unet":
+    """Build a :class:`Unet` from a flocoder flow checkpoint (a path to ``flow_*.pt`` / a dict with ``model_state_dict``,
+    as written by ``train_flow.py``, or a bare ``state_dict``) the way ``generate_samples.py:78-108`` does — minus its
+    invalid ``condition=`` keyword — and load the weights with the reference's ``strict=False``.  ``overrides`` replace
+    inferred constructor arguments (e.g. ``resnet_block_groups``)."""
+    if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__"):
+        checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=False)
+    sd = checkpoint["model_state_dict"] if "model_state_dict" in checkpoint else checkpoint
+    cfg = infer_unet_config(sd)
+    cfg.update(overrides)
+    model = Unet(compute_dtype=compute_dtype, **cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=strict)
+    model.load_report = {"missing": list(missing), "unexpected": list(unexpected), "config": cfg}
+    if device is not None:
+        model = model.to(device)
+    return model.eval()

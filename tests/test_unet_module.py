@@ -62,3 +62,23 @@ def test_load_reference_state_dict_roundtrip():
     assert not missing.missing_keys and not missing.unexpected_keys
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
+
+
+@pytest.mark.parametrize("kw", [dict(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=102), dict(dim=8, channels=4, dim_mults=[1, 2, 4], n_classes=0),
+                                dict(dim=32, channels=3, dim_mults=[1, 2], n_classes=10)])
+def test_unet_from_checkpoint_infers_the_constructor_arguments(kw, tmp_path):
+    """generate_samples.py:78-108: a flow checkpoint ({'model_state_dict': ...}) -> U-Net; here dim_mults and n_classes are
+    recovered from the tensors themselves instead of a Hydra config."""
+    from flocoder_b200.unet import Unet, infer_unet_config, unet_from_checkpoint
+    torch.manual_seed(3)
+    src = Unet(**kw)
+    assert infer_unet_config(src.state_dict()) == {"dim": kw["dim"], "channels": kw["channels"], "dim_mults": kw["dim_mults"], "n_classes": kw["n_classes"]}
+    path = tmp_path / "flow_test.pt"
+    torch.save({"model_state_dict": src.state_dict(), "epoch": 3}, path)
+    m = unet_from_checkpoint(str(path))
+    assert m.load_report["missing"] == [] and m.load_report["unexpected"] == [] and not m.training
+    for (ka, va), (kb, vb) in zip(src.state_dict().items(), m.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    # strict=False like the reference: a checkpoint with an extra buffer still loads and is reported
+    sd = dict(src.state_dict()); sd["ema.decay"] = torch.tensor(0.999)
+    assert unet_from_checkpoint(sd).load_report["unexpected"] == ["ema.decay"]
