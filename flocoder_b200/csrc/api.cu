@@ -253,7 +253,9 @@ struct Plan {
     std::vector<void*> buf_ptr;
     std::vector<ConvUmmaParams> umma;   // per op (valid for conv ops on the bf16 path)
     std::vector<CUtensorMap> tmA0, tmA1;
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr;        // one forward
+    cudaGraphExec_t graph4 = nullptr;       // four forwards back to back (one RK4 interval): the dependent-launch chain then
+                                            // also covers final stage -> first stage of the next evaluation
     size_t total_bytes = 0;
     uint8_t* base = nullptr;
     // fused path
@@ -715,6 +717,8 @@ static int launch_unit(Handle& h, Plan& pl, int i, cudaStream_t st) {
 
 static void destroy_plan(Plan& pl) {
     if (pl.graph) cudaGraphExecDestroy(pl.graph);
+    if (pl.graph4) cudaGraphExecDestroy(pl.graph4);
+    pl.graph4 = nullptr;
     if (pl.base) cudaFree(pl.base);
     pl.graph = nullptr; pl.base = nullptr;
 }
@@ -781,6 +785,16 @@ static int get_plan(Handle& h, int B, Plan** out) {
         ce = cudaGraphInstantiate(&pl->graph, g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(ce)); destroy_plan(*pl); return FLO_ERR_CUDA; }
+        if (s.fused && !getenv("FLO_NO_GRAPH4")) {     // the stage kernels find their ODE stage in the device-side control block
+            g = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(h.capture_stream, cudaStreamCaptureModeThreadLocal));
+            for (int k = 0; k < 4 && rc == FLO_OK; ++k)
+                for (int i = 0; i < n_units(h) && rc == FLO_OK; ++i) rc = launch_unit(h, *pl, i, h.capture_stream);
+            ce = cudaStreamEndCapture(h.capture_stream, &g);
+            if (rc == FLO_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&pl->graph4, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (rc || ce != cudaSuccess) { set_error("graph capture (x4) failed"); destroy_plan(*pl); return rc ? rc : FLO_ERR_CUDA; }
+        }
     }
     *out = pl.get();
     h.plans[B] = std::move(pl);
@@ -1093,6 +1107,14 @@ static int integrate_impl(Handle* h, Plan* pl, float* y, const float* ts, int n_
             cc.film = pass_per_sample[p] ? pl->film_ps : h->d_film_u;
             CUDA_TRY(launch_setup_ctrl(pl->ctrl, cc, nullptr, nullptr, st));
             h->launches += 1;
+        }
+        // four consecutive passes with nothing to launch in between go out as one graph
+        if (pl->graph4 && p + 3 < n_pass && !pass_per_sample[p] && !pass_per_sample[p + 1] && !pass_per_sample[p + 2] &&
+            !pass_per_sample[p + 3]) {
+            CUDA_TRY(cudaGraphLaunch(pl->graph4, st));
+            h->launches += 4 * (int64_t)n_units(*h);
+            p += 3;
+            continue;
         }
         rc = run_forward(*h, *pl, st);
         if (rc) return rc;
