@@ -381,3 +381,18 @@ def test_sampler_with_our_unet_and_a_codec(goldens):
     assert rel_l2(lat, g["rk4_10_cfg3"]) <= 1e-5
     with torch.no_grad():
         assert torch.allclose(img, codec.decode(lat), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_stl_sd_euler_100_steps_batch_512():
+    """BASELINE configs[4] per-GPU shape: stl_sd U-Net (n_classes=10), legacy Euler with 100 steps, 512 samples per GPU.
+    The fp16 fused trajectory (100 graph-chained evaluations) stays within the final-latent bar of the fp32 CUDA path, and
+    repeats bit-for-bit."""
+    from flocoder_b200 import sampling
+    m16, m32 = gpu_model(10, "fp16"), gpu_model(10, "fp32")
+    x0 = torch.randn(512, 4, 16, 16, generator=torch.Generator().manual_seed(99)).cuda()
+    a, nfe = sampling.euler_sampler(m16, (512, 4, 16, 16), 100, source=x0)
+    b, _ = sampling.euler_sampler(m16, (512, 4, 16, 16), 100, source=x0)
+    assert nfe == 100 and torch.equal(a, b)
+    ref, _ = sampling.euler_sampler(m32, (512, 4, 16, 16), 100, source=x0[:64])
+    assert rel_l2(a[:64], ref.cpu()) <= BF16_FINAL_TOL
