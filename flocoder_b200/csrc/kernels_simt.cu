@@ -12,6 +12,8 @@
 //                 epilogue (sampling.py:43-48,69-74)
 //
 // All tensors other than the NCHW latents use the blocked layout of flo_internal.h.
+#include <type_traits>
+
 #include "flo_internal.h"
 
 namespace flo {
@@ -291,7 +293,158 @@ __global__ void __launch_bounds__(256) k_gn(GnParams p) {
         }
     }
 }
+// Warp-team variant for units of <= 1024 float4 (every GroupNorm of the BASELINE U-Nets):
+// a team of T <= 32 lanes owns one unit, holds it in registers (V float4 per lane), reduces with xor-shuffles only
+// (no shared memory, no __syncthreads) and reads / writes whole 32-byte pixel rows.  When a group is half a channel
+// block (cpg == 4) the team takes the PAIR of groups sharing that block, so that consecutive lanes touch consecutive
+// 16 bytes (full sectors both ways); lane parity = group, and the reduction skips the xor-1 step.
+// MUFU forms for the 16-bit variant (same as the fused kernels' epilogues; the fp32 variant keeps expf / IEEE division)
+__device__ __forceinline__ float gn_fast_silu(float y) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return y * r;
+}
+constexpr int GNW_THREADS = 64;
+template <typename TO, int V>
+__global__ void __launch_bounds__(GNW_THREADS) k_gn_warp(GnParams p, int T, int pair, int n_units) {
+    constexpr bool kFast = !std::is_same<TO, float>::value;              // 16-bit outputs: folded affine + MUFU SiLU
+    const int G = p.groups, cpg = p.C / G, HW = p.H * p.W;
+    const int lgW = 31 - __clz(p.W), lgPC = 31 - __clz(HW * 2), lgT = 31 - __clz(T);
+    const int lane = threadIdx.x & 31, lt = lane & (T - 1);
+    const int unit = ((blockIdx.x * (GNW_THREADS / 32) + (threadIdx.x >> 5)) << (5 - lgT)) + (lane >> lgT);
+    const bool live = unit < n_units;
+    const int upb = pair ? (p.C >> 3) : G, lgU = 31 - __clz(upb);       // units per sample (power of two)
+    const int b = unit >> lgU, j = unit & (upb - 1);
+    const int cb0 = pair ? j : j * (cpg >> 3);
+    const int ncb = p.C >> 3;
+
+    float4 v[V];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int i = lt + k * T;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const size_t off = ((size_t)((cb0 + (i >> lgPC)) * p.B + b) * HW) * 8 + (size_t)(i & (HW * 2 - 1)) * 4;
+            v[k] = __ldcs(reinterpret_cast<const float4*>(p.in + off));
+        }
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const int o_min = pair ? 2 : 1;
+    for (int o = T >> 1; o >= o_min; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv_n = 1.f / (float)(cpg * HW);
+    const float mean = sum * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const float a = v[k].x - mean, b2 = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        sq += (a * a + b2 * b2) + (c * c + d * d);
+    }
+    for (int o = T >> 1; o >= o_min; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (!live) return;
+    const float rstd = 1.0f / sqrtf(sq * inv_n + 1e-5f);                // biased variance (nn.GroupNorm)
+
+    const float* film = nullptr;
+    if (p.film_off >= 0) {
+        const Ctrl* c = p.ctrl;
+        const int row = c->film_per_sample ? b : c->stages[c->step].film_row;
+        film = c->film + (size_t)row * p.film_dim + p.film_off;
+    }
+    TO* out_o = reinterpret_cast<TO*>(p.out_o);
+    TO* out_un = reinterpret_cast<TO*>(p.out_unshuf);
+    TO* out_up = reinterpret_cast<TO*>(p.out_up);
+    // per-channel coefficients, reloaded only when the lane moves to another channel quad (never, when the unit is one
+    // channel block): exact variant keeps (gamma, beta, scale+1, shift) and the reference's operation order
+    // (unet.py:64-70); fast variant folds them into y = x * ca + cb.
+    int c_prev = -1;
+    float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb_[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f}, ch[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int i = lt + k * T, r = i & (HW * 2 - 1);
+        const int cb = cb0 + (i >> lgPC), sub = (r & 1) * 4, c0 = cb * 8 + sub, px = r >> 1;
+        const size_t off = ((size_t)(cb * p.B + b) * HW) * 8 + (size_t)r * 4;
+        if (c0 != c_prev) {
+            c_prev = c0;
+            const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
+            const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
+            ca[0] = ga.x; ca[1] = ga.y; ca[2] = ga.z; ca[3] = ga.w;
+            cb_[0] = be.x; cb_[1] = be.y; cb_[2] = be.z; cb_[3] = be.w;
+            if (film) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { cs[q] = film[c0 + q] + 1.0f; ch[q] = film[p.C + c0 + q]; }
+            }
+            if (kFast) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float g2 = rstd * ca[q];
+                    ca[q] = g2 * cs[q];
+                    cb_[q] = fmaf(fmaf(-mean, g2, cb_[q]), cs[q], ch[q]);
+                }
+            }
+        }
+        float x[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float y;
+            if (kFast) {
+                y = fmaf(x[q], ca[q], cb_[q]);
+                if (p.silu) y = gn_fast_silu(y);
+            } else {
+                y = (x[q] - mean) * rstd * ca[q] + cb_[q];
+                if (film) y = y * cs[q] + ch[q];                              // unet.py:70
+                if (p.silu) y = y / (1.0f + expf(-y));                        // x*sigmoid(x)
+            }
+            x[q] = y;
+        }
+        if (p.res) {
+            const float4 rr = __ldcs(reinterpret_cast<const float4*>(p.res + off));
+            x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+        }
+        const float4 o = make_float4(x[0], x[1], x[2], x[3]);
+        if (p.out_m) store4(p.out_m + off, o);
+        if (out_o) store4(out_o + off, o);
+        if (out_un || out_up) {
+            const int h = px >> lgW, w = px & (p.W - 1);
+            if (out_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)
+                const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
+                const int q2 = (h >> 1) * (p.W >> 1) + (w >> 1);
+                store4(out_un + ((size_t)(plane * p.B + b) * (HW >> 2) + q2) * 8 + sub, o);
+            }
+            if (out_up) {   // nearest x2: dst(2h+dy, 2w+dx) = src(h, w)
+                const int W2 = p.W * 2;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int q2 = (2 * h + (d >> 1)) * W2 + 2 * w + (d & 1);
+                    store4(out_up + ((size_t)(cb * p.B + b) * (HW * 4) + q2) * 8 + sub, o);
+                }
+            }
+        }
+    }
+}
+template <typename TO>
+static void launch_gn_warp(const GnParams& p, int nvec, int pair, cudaStream_t s) {
+    const int T = nvec < 32 ? nvec : 32, V = nvec / T;
+    const int n_units = p.B * (pair ? p.C / 8 : p.groups);
+    const int warps = (n_units + 32 / T - 1) / (32 / T), wpb = GNW_THREADS / 32, grid = (warps + wpb - 1) / wpb;
+    switch (V) {
+        case 1:  k_gn_warp<TO, 1><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+        case 2:  k_gn_warp<TO, 2><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+        case 4:  k_gn_warp<TO, 4><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+        case 8:  k_gn_warp<TO, 8><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+        case 16: k_gn_warp<TO, 16><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+        default: k_gn_warp<TO, 32><<<grid, GNW_THREADS, 0, s>>>(p, T, pair, n_units); break;
+    }
+}
 cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
+    const int cpg = p.C / p.groups, HW = p.H * p.W;
+    const int pair = cpg == 4 ? 1 : 0;
+    const int nvec_w = pair ? HW * 2 : cpg * HW / 4;                     // float4 per warp-team unit
+    if (!getenv("FLO_GN_CTA") && nvec_w >= 2 && nvec_w <= 1024 && (nvec_w & (nvec_w - 1)) == 0 && (pair || (cpg & 7) == 0)) {
+        if (p.o_is_bf16) launch_gn_warp<__nv_bfloat16>(p, nvec_w, pair, s);
+        else launch_gn_warp<float>(p, nvec_w, pair, s);
+        return cudaGetLastError();
+    }
     const int nvec = (p.C / p.groups) * p.H * p.W / 4;
     int nt = 32;
     while (nt < 256 && nt * GN_VPT < nvec) nt <<= 1;

@@ -396,3 +396,20 @@ def test_stl_sd_euler_100_steps_batch_512():
     assert nfe == 100 and torch.equal(a, b)
     ref, _ = sampling.euler_sampler(m32, (512, 4, 16, 16), 100, source=x0[:64])
     assert rel_l2(a[:64], ref.cpu()) <= BF16_FINAL_TOL
+
+
+@pytest.mark.gpu
+def test_midi_vqgan_rk4_50_steps_batch_1024():
+    """BASELINE configs[2] at full size: midi_vqgan-shaped U-Net (n_classes=0, inpainting off), RK4 n_steps=50, 1024
+    samples on one GPU (the unsplit variant of the low-resolution stages).  Size-independent properties: the run repeats
+    bit-for-bit, every sample is finite, and the first 32 samples stay within the final-latent bar of the fp32 CUDA path
+    (itself pinned to the reference) integrating only that slice - samples never see each other."""
+    from flocoder_b200 import sampling
+    m16, m32 = gpu_model(0, "fp16"), gpu_model(0, "fp32")
+    shape = (1024, 4, 16, 16)
+    x0 = torch.randn(*shape, generator=torch.Generator().manual_seed(1024)).cuda()
+    a, nfe = sampling.generate_latents_rk4(m16, shape, n_steps=50, source=x0)
+    b, _ = sampling.generate_latents_rk4(m16, shape, n_steps=50, source=x0)
+    assert nfe == 200 and a.shape == shape and torch.isfinite(a).all() and torch.equal(a, b)
+    ref, _ = sampling.generate_latents_rk4(m32, (32, 4, 16, 16), n_steps=50, source=x0[:32])
+    assert rel_l2(a[:32], ref.cpu()) <= BF16_FINAL_TOL
