@@ -14,7 +14,9 @@
 // All tensors other than the NCHW latents use the blocked layout of flo_internal.h.
 #include <type_traits>
 
-#include "flo_internal.h"
+#include <algorithm>
+
+#include "umma_common.cuh"
 
 namespace flo {
 
@@ -422,6 +424,202 @@ __global__ void __launch_bounds__(GNW_THREADS) k_gn_warp(GnParams p, int T, int 
         }
     }
 }
+// Staged variant for units of >= 2 KB: the pass is HBM-bound, so what matters is bytes in flight.  A TEAM of TW warps
+// (1, 2 or 4) owns a two-deep ring of unit-sized shared-memory stages filled by 1-D bulk copies (cp.async.bulk + mbarrier
+// complete_tx; a unit is cpg/8 contiguous runs of HW*32 bytes in the blocked layout, plus the same runs of the residual)
+// and strides over the units persistently: while it normalises unit k out of one stage, unit k+1 is landing in the
+// other, and the refill for k+2 is issued as soon as the team has finished reading.  The three passes (sum, centred
+// squares, normalise) re-read shared memory with conflict-free 16-byte accesses, so the register footprint is small;
+// reductions are xor-shuffles inside a warp and a fixed-order sum of TW partials across the team (named barrier of
+// TW*32 threads; nothing CTA-wide after the prologue).  Teams of more than one warp keep 24 warps per SM busy on the
+// 8-32 KB stages that would otherwise leave 3-12.
+constexpr int GNT_STAGES = 2;
+constexpr int GNT_MAX_WARPS = 8;
+template <typename TO>
+__global__ void __launch_bounds__(GNT_MAX_WARPS * 32) k_gn_tma(GnParams p, int pair, int n_units, int n_chunks, int total_teams, int TW) {
+    extern __shared__ __align__(128) uint8_t gn_smem[];
+    constexpr bool kFast = !std::is_same<TO, float>::value;
+    const int G = p.groups, cpg = p.C / G, HW = p.H * p.W;
+    const int lgW = 31 - __clz(p.W), lgTW = 31 - __clz(TW);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, tpb = (blockDim.x >> 5) >> lgTW;
+    const int team = w >> lgTW, wt = w & (TW - 1);
+    const int VCw = (HW >> 4) >> lgTW;                                   // float4 per lane per chunk (HW * 2 / 32 / TW)
+    const int chunk_bytes = HW * 32, unit_bytes = n_chunks * chunk_bytes;
+    const int stage_bytes = unit_bytes * (p.res ? 2 : 1);
+    const int Vw = (unit_bytes >> 9) >> lgTW;                            // float4 per lane per unit
+    const int upb = pair ? (p.C >> 3) : G, lgU = 31 - __clz(upb);
+    const int ncb = p.C >> 3, sub = (lane & 1) * 4;
+    const int step = TW * 32;                                            // float4 between a lane's consecutive vectors
+    uint8_t* my = gn_smem + (size_t)team * GNT_STAGES * stage_bytes;
+    uint8_t* tail = gn_smem + (size_t)tpb * GNT_STAGES * stage_bytes;
+    const uint32_t bar0 = smem_u32(tail) + team * GNT_STAGES * 8;
+    float* red = reinterpret_cast<float*>(tail + GNT_MAX_WARPS * GNT_STAGES * 8) + team * 16;     // [2 (sum|sq)][TW <= 4][2 groups]
+    const int gteam = blockIdx.x * tpb + team;
+
+    auto issue = [&](int k) {          // one lane of the team
+        const int unit = gteam + k * total_teams;
+        if (unit >= n_units) return;
+        const int s = k & 1, b = unit >> lgU, j = unit & (upb - 1);
+        const int cb0 = pair ? j : j * (cpg >> 3);
+        const uint32_t bar = bar0 + s * 8, dst = smem_u32(my + (size_t)s * stage_bytes);
+        mbar_expect_tx(bar, (uint32_t)stage_bytes);
+        for (int c = 0; c < n_chunks; ++c) {
+            const size_t off = ((size_t)((cb0 + c) * p.B + b) * HW) * 8;
+            bulk_load_1d(dst + c * chunk_bytes, p.in + off, (uint32_t)chunk_bytes, bar);
+            if (p.res) bulk_load_1d(dst + unit_bytes + c * chunk_bytes, p.res + off, (uint32_t)chunk_bytes, bar);
+        }
+    };
+    auto team_sync = [&]() {
+        if (TW == 1) __syncwarp();
+        else named_bar_sync(1 + team, TW * 32);
+    };
+    // warp partial -> team total, per group (lane parity = group when two groups share the channel block)
+    auto team_sum = [&](float v, int which, int o_min) -> float {
+        for (int o = 16; o >= o_min; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (TW == 1) return v;
+        if (lane < 2) red[which * 8 + wt * 2 + lane] = v;
+        named_bar_sync(1 + team, TW * 32);
+        float t = 0.f;
+        for (int q = 0; q < TW; ++q) t += red[which * 8 + q * 2 + (lane & 1)];
+        return t;
+    };
+    if (wt == 0 && lane == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        issue(0); issue(1);
+    }
+    __syncthreads();
+
+    const float inv_n = 1.f / (float)(cpg * HW);
+    const int o_min = pair ? 2 : 1;
+    TO* out_o = reinterpret_cast<TO*>(p.out_o);
+    TO* out_un = reinterpret_cast<TO*>(p.out_unshuf);
+    TO* out_up = reinterpret_cast<TO*>(p.out_up);
+    for (int k = 0;; ++k) {
+        const int unit = gteam + k * total_teams;
+        if (unit >= n_units) break;
+        const int s = k & 1, b = unit >> lgU, j = unit & (upb - 1);
+        const int cb0 = pair ? j : j * (cpg >> 3);
+        mbar_wait(bar0 + s * 8, (uint32_t)((k >> 1) & 1));
+        const float4* xs = reinterpret_cast<const float4*>(my + (size_t)s * stage_bytes) + wt * 32 + lane;
+        const float4* rs = reinterpret_cast<const float4*>(my + (size_t)s * stage_bytes + unit_bytes) + wt * 32 + lane;
+        float sum = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < Vw; ++i) { const float4 v = xs[i * step]; sum += (v.x + v.y) + (v.z + v.w); }
+        const float mean = team_sum(sum, 0, o_min) * inv_n;
+        float sq = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < Vw; ++i) {
+            const float4 v = xs[i * step];
+            const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, d = v.w - mean;
+            sq += (a * a + b2 * b2) + (c * c + d * d);
+        }
+        const float rstd = 1.0f / sqrtf(team_sum(sq, 1, o_min) * inv_n + 1e-5f);       // biased variance (nn.GroupNorm)
+        const float* film = nullptr;
+        if (p.film_off >= 0) {
+            const Ctrl* c = p.ctrl;
+            const int row = c->film_per_sample ? b : c->stages[c->step].film_row;
+            film = c->film + (size_t)row * p.film_dim + p.film_off;
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            // per-channel coefficients of this channel block (lane parity = channel quad): the exact variant keeps
+            // (gamma, beta, scale+1, shift) and the reference's operation order (unet.py:64-70); the 16-bit variant
+            // folds them into y = x * ca + cb.
+            const int cb = cb0 + c, c0 = cb * 8 + sub;
+            float ca[4], cb_[4], cs[4] = {1.f, 1.f, 1.f, 1.f}, ch[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                const float4 ga = *reinterpret_cast<const float4*>(p.gamma + c0);
+                const float4 be = *reinterpret_cast<const float4*>(p.beta + c0);
+                ca[0] = ga.x; ca[1] = ga.y; ca[2] = ga.z; ca[3] = ga.w;
+                cb_[0] = be.x; cb_[1] = be.y; cb_[2] = be.z; cb_[3] = be.w;
+                if (film) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { cs[q] = film[c0 + q] + 1.0f; ch[q] = film[p.C + c0 + q]; }
+                }
+                if (kFast) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float g2 = rstd * ca[q];
+                        ca[q] = g2 * cs[q];
+                        cb_[q] = fmaf(fmaf(-mean, g2, cb_[q]), cs[q], ch[q]);
+                    }
+                }
+            }
+            const size_t base = ((size_t)(cb * p.B + b) * HW) * 8 + (size_t)(wt * 32 + lane) * 4;
+            float* om = p.out_m ? p.out_m + base : nullptr;
+            TO* oo = out_o ? out_o + base : nullptr;
+            const float4* xc = xs + c * (HW * 2);
+            const float4* rc = rs + c * (HW * 2);
+#pragma unroll 4
+            for (int it = 0; it < VCw; ++it) {
+                const float4 v = xc[it * step];
+                float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float y;
+                    if (kFast) {
+                        y = fmaf(x[q], ca[q], cb_[q]);
+                        if (p.silu) y = gn_fast_silu(y);
+                    } else {
+                        y = (x[q] - mean) * rstd * ca[q] + cb_[q];
+                        if (film) y = y * cs[q] + ch[q];                      // unet.py:70
+                        if (p.silu) y = y / (1.0f + expf(-y));                // x*sigmoid(x)
+                    }
+                    x[q] = y;
+                }
+                if (p.res) {
+                    const float4 rr = rc[it * step];
+                    x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+                }
+                const float4 o = make_float4(x[0], x[1], x[2], x[3]);
+                if (om) store4(om + it * step * 4, o);
+                if (oo) store4(oo + it * step * 4, o);
+                if (out_un || out_up) {
+                    const int px = (it * step + wt * 32 + lane) >> 1;
+                    const int h = px >> lgW, ww = px & (p.W - 1);
+                    if (out_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)
+                        const int plane = ((h & 1) * 2 + (ww & 1)) * ncb + cb;
+                        const int q2 = (h >> 1) * (p.W >> 1) + (ww >> 1);
+                        store4(out_un + ((size_t)(plane * p.B + b) * (HW >> 2) + q2) * 8 + sub, o);
+                    }
+                    if (out_up) {   // nearest x2: dst(2h+dy, 2w+dx) = src(h, w)
+                        const int W2 = p.W * 2;
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            const int q2 = (2 * h + (d >> 1)) * W2 + 2 * ww + (d & 1);
+                            store4(out_up + ((size_t)(cb * p.B + b) * (HW * 4) + q2) * 8 + sub, o);
+                        }
+                    }
+                }
+            }
+        }
+        team_sync();                       // every lane of the team has finished reading this stage
+        if (wt == 0 && lane == 0) issue(k + 2);
+    }
+}
+static int gn_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+constexpr int GNT_MAX_SMEM = 72 * 1024;
+template <typename TO>
+static void launch_gn_tma(const GnParams& p, int pair, int n_chunks, cudaStream_t s) {
+    const int HW = p.H * p.W, unit_bytes = n_chunks * HW * 32, stage_bytes = unit_bytes * (p.res ? 2 : 1);
+    const int n_units = p.B * (pair ? p.C / 8 : p.groups);
+    int TW = 1;                                                          // warps per unit: ~4 KB of stage per warp
+    while (TW < 4 && TW * 2 <= HW / 16 && stage_bytes / (TW * 2) >= 4096) TW *= 2;
+    int tpb = GNT_MAX_SMEM / (GNT_STAGES * stage_bytes);
+    tpb = std::max(1, std::min(tpb, GNT_MAX_WARPS / TW));
+    const int smem = tpb * GNT_STAGES * stage_bytes + GNT_MAX_WARPS * GNT_STAGES * 8 + GNT_MAX_WARPS * 16 * 4;
+    const int per_sm = std::max(1, std::min(16, (220 * 1024) / (smem + 1024)));
+    const int grid = std::min((n_units + tpb - 1) / tpb, gn_num_sms() * per_sm);
+    k_gn_tma<TO><<<grid, tpb * TW * 32, smem, s>>>(p, pair, n_units, n_chunks, grid * tpb, TW);
+}
 template <typename TO>
 static void launch_gn_warp(const GnParams& p, int nvec, int pair, cudaStream_t s) {
     const int T = nvec < 32 ? nvec : 32, V = nvec / T;
@@ -440,6 +638,13 @@ cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
     const int cpg = p.C / p.groups, HW = p.H * p.W;
     const int pair = cpg == 4 ? 1 : 0;
     const int nvec_w = pair ? HW * 2 : cpg * HW / 4;                     // float4 per warp-team unit
+    const int n_chunks = pair ? 1 : cpg / 8, unit_bytes = n_chunks * HW * 32;
+    if (!getenv("FLO_GN_CTA") && !getenv("FLO_GN_NO_TMA") && (pair || (cpg & 7) == 0) && unit_bytes >= 2048 &&
+        unit_bytes <= 16384 && HW >= 16 && (HW & (HW - 1)) == 0 && (unit_bytes & (unit_bytes - 1)) == 0) {
+        if (p.o_is_bf16) launch_gn_tma<__nv_bfloat16>(p, pair, n_chunks, s);
+        else launch_gn_tma<float>(p, pair, n_chunks, s);
+        return cudaGetLastError();
+    }
     if (!getenv("FLO_GN_CTA") && nvec_w >= 2 && nvec_w <= 1024 && (nvec_w & (nvec_w - 1)) == 0 && (pair || (cpg & 7) == 0)) {
         if (p.o_is_bf16) launch_gn_warp<__nv_bfloat16>(p, nvec_w, pair, s);
         else launch_gn_warp<float>(p, nvec_w, pair, s);
@@ -550,7 +755,10 @@ __global__ void __launch_bounds__(LA_THREADS) k_linattn(AttnParams p) {
 }
 static size_t linattn_smem(int n) { return (size_t)(3 * 32 * (n + 1) + 32 * 33) * sizeof(float); }
 cudaError_t simt_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_gn_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM + 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gn_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM + 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)linattn_smem(256));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_linattn<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
