@@ -4,7 +4,8 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
 for src, dst in [("bench.json", "r01_bench_fused_bf16_B256.json"), ("bench_ref.json", "r01_bench_reference_arm.json"),
                  ("bench_b1024.json", "r01_bench_fused_bf16_B1024.json"), ("bench_fp16.json", "r01_bench_fused_fp16_B256.json"),
-                 ("timeline.txt", "r01_stage_timeline_fused_bf16_B256.txt"), ("launches.csv", "r01_launches_fused_bf16_B256.csv")]:
+                 ("timeline.txt", "r01_stage_timeline_fused_bf16_B256.txt"), ("launches.csv", "r01_launches_fused_bf16_B256.csv"),
+                 ("layerwise_b4096.txt", "r01_event_profile_layerwise_bf16_B4096.txt")]:
     if os.path.isfile(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "r01_full_forward.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -50,3 +51,23 @@ for k in tt:
 for f in ("r01_bench_fused_bf16_B256.json", "r01_bench_fused_bf16_B1024.json", "r01_bench_fused_fp16_B256.json", "r01_bench_reference_arm.json"):
     d = json.loads(open(os.path.join(P, f)).read().strip().splitlines()[-1])
     print(f, round(d["value"], 1), round(d["e2e"]["value"], 1), (round(d["roofline"]["achieved"], 2), round(d["roofline"]["frac"], 4)) if "roofline" in d else "", d.get("cpu_baseline", {}).get("value"))
+
+# the standalone GroupNorm+FiLM+SiLU pass: ncu --set full of the first six GN launches of a layer-wise forward at B=4096
+gn_rep = os.path.join(G, "r01_gn_tma_b4096.ncu-rep")
+if os.path.isfile(gn_rep):
+    raw = subprocess.run(["ncu", "-i", gn_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_active",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+    cols = [c for c in want if c in h]
+    with open(os.path.join(P, "r01_ncu_gn_pass_B4096.csv"), "w") as f:
+        w = csv.writer(f); w.writerow(cols); w.writerow([units[h.index(c)] for c in cols])
+        for r in rows[2:]:
+            w.writerow([r[h.index(c)] for c in cols])
+    print("gn pass:", [(r[h.index("gpu__time_duration.sum")], r[h.index("dram__bytes_read.sum")], r[h.index("dram__bytes_write.sum")]) for r in rows[2:]])
