@@ -300,12 +300,19 @@ __global__ void __launch_bounds__(256) k_gn(GnParams p) {
 // (no shared memory, no __syncthreads) and reads / writes whole 32-byte pixel rows.  When a group is half a channel
 // block (cpg == 4) the team takes the PAIR of groups sharing that block, so that consecutive lanes touch consecutive
 // 16 bytes (full sectors both ways); lane parity = group, and the reduction skips the xor-1 step.
-// MUFU forms for the 16-bit variant (same as the fused kernels' epilogues; the fp32 variant keeps expf / IEEE division)
+// MUFU forms for the 16-bit variant (the fp32 variant keeps expf / IEEE division).  With h = y/2,
+// SiLU(y) = y * sigmoid(y) = h + h * tanh(h): one MUFU and one FMA per element once the affine is folded to produce h
+// directly.  tanh.approx.f32 is accurate to ~2^-11, a quarter of the bf16 output rounding that follows.
 __device__ __forceinline__ float gn_fast_silu(float y) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * y));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return y * r;
+}
+__device__ __forceinline__ float gn_silu_from_half(float h) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
 }
 constexpr int GNW_THREADS = 64;
 template <typename TO, int V>
@@ -504,18 +511,32 @@ __global__ void __launch_bounds__(GNT_MAX_WARPS * 32) k_gn_tma(GnParams p, int p
         mbar_wait(bar0 + s * 8, (uint32_t)((k >> 1) & 1));
         const float4* xs = reinterpret_cast<const float4*>(my + (size_t)s * stage_bytes) + wt * 32 + lane;
         const float4* rs = reinterpret_cast<const float4*>(my + (size_t)s * stage_bytes + unit_bytes) + wt * 32 + lane;
-        float sum = 0.f;
+        float mean, rstd;
+        if (kFast) {                       // one pass: sum and sum of squares (fp32, <= 4096 values of O(1) magnitude)
+            float sum = 0.f, sq = 0.f;
 #pragma unroll 4
-        for (int i = 0; i < Vw; ++i) { const float4 v = xs[i * step]; sum += (v.x + v.y) + (v.z + v.w); }
-        const float mean = team_sum(sum, 0, o_min) * inv_n;
-        float sq = 0.f;
+            for (int i = 0; i < Vw; ++i) {
+                const float4 v = xs[i * step];
+                sum += (v.x + v.y) + (v.z + v.w);
+                sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq))));
+            }
+            mean = team_sum(sum, 0, o_min) * inv_n;
+            const float var = fmaxf(team_sum(sq, 1, o_min) * inv_n - mean * mean, 0.f);
+            rstd = rsqrtf(var + 1e-5f);
+        } else {                           // two passes, the reference's formula (biased variance of nn.GroupNorm)
+            float sum = 0.f;
 #pragma unroll 4
-        for (int i = 0; i < Vw; ++i) {
-            const float4 v = xs[i * step];
-            const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, d = v.w - mean;
-            sq += (a * a + b2 * b2) + (c * c + d * d);
+            for (int i = 0; i < Vw; ++i) { const float4 v = xs[i * step]; sum += (v.x + v.y) + (v.z + v.w); }
+            mean = team_sum(sum, 0, o_min) * inv_n;
+            float sq = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < Vw; ++i) {
+                const float4 v = xs[i * step];
+                const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, d = v.w - mean;
+                sq += (a * a + b2 * b2) + (c * c + d * d);
+            }
+            rstd = 1.0f / sqrtf(team_sum(sq, 1, o_min) * inv_n + 1e-5f);
         }
-        const float rstd = 1.0f / sqrtf(team_sum(sq, 1, o_min) * inv_n + 1e-5f);       // biased variance (nn.GroupNorm)
         const float* film = nullptr;
         if (p.film_off >= 0) {
             const Ctrl* c = p.ctrl;
@@ -543,6 +564,7 @@ __global__ void __launch_bounds__(GNT_MAX_WARPS * 32) k_gn_tma(GnParams p, int p
                         const float g2 = rstd * ca[q];
                         ca[q] = g2 * cs[q];
                         cb_[q] = fmaf(fmaf(-mean, g2, cb_[q]), cs[q], ch[q]);
+                        if (p.silu) { ca[q] *= 0.5f; cb_[q] *= 0.5f; }       // the loop below then yields h = y / 2
                     }
                 }
             }
@@ -560,7 +582,7 @@ __global__ void __launch_bounds__(GNT_MAX_WARPS * 32) k_gn_tma(GnParams p, int p
                     float y;
                     if (kFast) {
                         y = fmaf(x[q], ca[q], cb_[q]);
-                        if (p.silu) y = gn_fast_silu(y);
+                        if (p.silu) y = gn_silu_from_half(y);
                     } else {
                         y = (x[q] - mean) * rstd * ca[q] + cb_[q];
                         if (film) y = y * cs[q] + ch[q];                      // unet.py:70
