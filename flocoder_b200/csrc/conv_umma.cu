@@ -432,7 +432,9 @@ cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, f
 
 // Back-to-back tcgen05.mma throughput probe: one elected thread issues `n_mma` M=128 x N x K=16 MMAs on zeroed no-swizzle
 // operands (A start address cycling through 4 tiles), one commit, then waits.  cycles[0] = issue loop, cycles[1] = until done.
-__global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int n_mma, int n_acc) {
+// a_mode: 0 = A from shared memory; 1 = A from tensor memory (the .ts form: 8 TMEM columns per K16 slice);
+// a_shift: byte offset added to the shared-memory A start (16 = one pixel of a 3x3 tap, i.e. off the 128-byte line).
+__global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int n_mma, int n_acc, int a_mode, int a_shift) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tslot;
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int cols = 32;
-    while (cols < N * (n_acc < 0 ? 2 : n_acc)) cols <<= 1;
+    while (cols < N * (n_acc < 0 ? 2 : n_acc) + (a_mode ? 32 : 0)) cols <<= 1;
     if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
     tc_fence_before();
     __syncthreads();
@@ -457,15 +459,27 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
     if (warp == 1 || (dual && warp == 2)) {
         const uint32_t idesc = make_idesc_bf16(128, N);
         const uint32_t base = smem_u32(smem);
-        const uint64_t ad0 = make_smem_desc(base, 2048u, 128u);                  // A: LBO = 2 KB plane, SBO = 128 B
+        const uint64_t ad0 = make_smem_desc(base + (uint32_t)a_shift, 2048u, 128u);   // A: LBO = 2 KB plane, SBO = 128 B
+        const uint32_t a_t0 = tbase + (uint32_t)(N * nacc);                     // A tiles in TMEM (contents irrelevant for timing)
         const uint64_t bd0 = make_smem_desc(base + 64 * 1024, (uint32_t)N * 16u, 128u);
         const uint32_t tcol = tbase + (uint32_t)((warp - 1) * N);
         t0 = clock64();
         if (elect_one()) {
             const uint32_t acc_mask = (uint32_t)(nacc - 1);
 #pragma unroll 4
-            for (int i = 0; i < n_mma; ++i)
-                umma_bf16(tcol + ((uint32_t)i & acc_mask) * (uint32_t)N, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
+            for (int i = 0; i < n_mma; ++i) {
+                const uint32_t dcol = tcol + ((uint32_t)i & acc_mask) * (uint32_t)N;
+                if (a_mode) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                        ::"r"(dcol), "r"(a_t0 + (uint32_t)((i & 3) * 8)), "l"(bd0), "r"(idesc), "r"(1u)
+                        : "memory");
+                } else {
+                    umma_bf16(dcol, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
+                }
+            }
             umma_commit(smem_u32(&bar));
         }
         __syncwarp();
@@ -478,13 +492,13 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, cols);
 }
-cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cudaStream_t s) {
+cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cudaStream_t s, int a_mode, int a_shift) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(k_umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         configured = true;
     }
-    k_umma_rate<<<1, 128, 200 * 1024, s>>>(cycles, N, n_mma, n_acc);
+    k_umma_rate<<<1, 128, 200 * 1024, s>>>(cycles, N, n_mma, n_acc, a_mode, a_shift);
     return cudaGetLastError();
 }
 

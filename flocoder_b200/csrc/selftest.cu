@@ -237,11 +237,15 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
         long long* dc; long long hc[2];
         ST_CUDA(cudaMalloc(&dc, 16));
         const int Ns[4] = {16, 32, 64, 128}, counts[4] = {1, 8, 32, 128};
-        for (int acc = -1; acc <= 1; acc += 2)       // -1: two issuing warps, one accumulator each; 1: one issuer
+        // acc -1: two issuing warps, one accumulator each; 1: one issuer.  Then, one issuer: A start one pixel (16 bytes)
+        // and one padded row + pixel (16*19 bytes) off the line, as the 3x3 tap descriptors are; and A read from TMEM.
+        const int modes[5][3] = {{-1, 0, 0}, {1, 0, 0}, {1, 0, 16}, {1, 0, 16 * 19}, {1, 1, 0}};
+        for (int m = 0; m < 5; ++m)
             for (int ni = 0; ni < 4; ++ni) {
-                char buf[256]; int o = snprintf(buf, sizeof(buf), "INFO umma_rate N=%-3d acc=%d :", Ns[ni], acc);
+                char buf[320]; int o = snprintf(buf, sizeof(buf), "INFO umma_rate N=%-3d acc=%d a=%s shift=%d :", Ns[ni], modes[m][0],
+                                                modes[m][1] ? "tmem" : "smem", modes[m][2]);
                 for (int ci = 0; ci < 4; ++ci) {
-                    ST_CUDA(launch_umma_rate(dc, Ns[ni], counts[ci], acc, st));
+                    ST_CUDA(launch_umma_rate(dc, Ns[ni], counts[ci], modes[m][0], st, modes[m][1], modes[m][2]));
                     ST_CUDA(cudaStreamSynchronize(st));
                     ST_CUDA(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost));
                     o += snprintf(buf + o, sizeof(buf) - o, "  n=%d issue %lld done %lld", counts[ci], hc[0], hc[1]);
