@@ -2,8 +2,10 @@
 //
 //   k_init_conv   init_conv 1x1 (unet.py:295) reading the NCHW fp32 integrator state
 //   k_conv_simt   fp32 direct convolution on blocked tensors (the FLO_F32 path, <=1e-5 parity)
-//   k_gn          GroupNorm + timestep-FiLM + SiLU + residual in ONE pass (unet.py:64-73,96,133,157):
-//                 each value is read once into registers, reduced with warp shuffles, written once
+//   k_gn_tma /    GroupNorm + timestep-FiLM + SiLU + residual in ONE pass (unet.py:64-73,96,133,157), HBM-bound:
+//   k_gn_warp /   each value is read once and written once; k_gn_tma stages (sample, group) units through shared memory
+//   k_gn          with 1-D bulk copies and warp teams, k_gn_warp holds small units in registers (shuffle-only
+//                 reductions), k_gn is the one-CTA-per-unit fallback
 //   k_linattn     LinearAttention core (unet.py:142-149), one CTA per (sample, head)
 //   k_midattn     mid-block Attention core (unet.py:114-121), one CTA per (sample, head)
 //   k_temb        sinusoidal embedding + time/class MLPs + all ResnetBlock FiLM projections
