@@ -413,3 +413,33 @@ def test_midi_vqgan_rk4_50_steps_batch_1024():
     assert nfe == 200 and a.shape == shape and torch.isfinite(a).all() and torch.equal(a, b)
     ref, _ = sampling.generate_latents_rk4(m32, (32, 4, 16, 16), n_steps=50, source=x0[:32])
     assert rel_l2(a[:32], ref.cpu()) <= BF16_FINAL_TOL
+
+
+@pytest.mark.gpu
+def test_groupnorm_pass_kernel_variants_agree(monkeypatch):
+    """The standalone GroupNorm+FiLM+SiLU pass of the layer-wise path has three kernels chosen by unit size (k_gn_tma: bulk-copy
+    staged warp teams; k_gn_warp: register-resident warp teams; k_gn: one CTA per unit).  Forced through each of them (the
+    developer switches of DESIGN.md 5.2, read when a plan is captured), one forward of a ragged batch must agree: to fp32
+    rounding in the fp32 mode (same formula, different summation order), and to the bf16 format floor in the bf16 mode
+    (whose 16-bit variant also uses a one-pass variance and a MUFU SiLU in the staged / warp kernels)."""
+    from flocoder_b200 import _lib
+    from flocoder_b200.unet import Unet
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(37, 4, 16, 16, generator=gen).cuda()
+    t = (torch.rand(37, generator=gen) * 999).cuda()
+    outs = {}
+    for tag, env in (("tma", {}), ("warp", {"FLO_GN_NO_TMA": "1"}), ("cta", {"FLO_GN_CTA": "1"})):
+        for k in ("FLO_GN_NO_TMA", "FLO_GN_CTA"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for cd in ("fp32", "bf16"):
+            torch.manual_seed(1234)
+            m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, compute_dtype=cd)
+            m.engine_flags = _lib.FLO_FLAG_LAYERWISE
+            outs[tag, cd] = m.cuda().eval()(x, t).float().cpu()
+            assert torch.isfinite(outs[tag, cd]).all()
+    for tag in ("warp", "cta"):
+        assert rel_l2(outs[tag, "fp32"], outs["tma", "fp32"]) <= 1e-5, tag
+        assert rel_l2(outs[tag, "bf16"], outs["tma", "bf16"]) <= 1.5e-2, tag
+    assert rel_l2(outs["tma", "bf16"], outs["tma", "fp32"]) <= 1.5e-2
