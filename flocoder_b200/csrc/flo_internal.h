@@ -281,6 +281,7 @@ struct AttnFusedParams {
 };
 
 cudaError_t fused_configure();
+int fused_max_active_clusters(int nsplit, int smem_bytes);
 void fused_set_pdl(bool on);     // programmatic dependent launch between the fused stage kernels (default on; FLO_NO_PDL=1 disables)
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s);

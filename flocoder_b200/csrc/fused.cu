@@ -835,6 +835,23 @@ cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStr
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
+// How many clusters of `nsplit` k_chain<1, true> CTAs with `smem_bytes` of dynamic shared memory the device keeps resident
+// at once (clusters must sit inside one GPC, so this is less than SMs / nsplit: 148 SMs hold 32-36 clusters of four, not 37).
+// Returns -1 when the query is not available; the caller then falls back to the SM-count estimate.
+int fused_max_active_clusters(int nsplit, int smem_bytes) {
+    if (nsplit <= 1) return -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(nsplit * 64)); cfg.blockDim = dim3((unsigned)FUSED_THREADS); cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)nsplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k_chain<1, true>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
     const void* fn;
     switch (p.n_mtiles) {

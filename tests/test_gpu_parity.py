@@ -308,7 +308,7 @@ def test_bf16_param_dtype_follows_module(goldens):
 @pytest.mark.parametrize("B", [1, 7, 13, 100, 300, 600])
 def test_ragged_and_large_batches_fused_vs_fp32_path(B):
     """Batch sizes that leave the last CTA / cluster group partly empty (1, 7, 13, 100) and sizes that select the other
-    N-split variants of the low-resolution stages (<= 296: clusters of 4; 300: clusters of 2; 600: no split).  The
+    N-split variants of the low-resolution stages (up to the 32-36 clusters of 4 the GPCs hold, i.e. B <= 256..288: clusters of 4; 300: clusters of 2; 600: no split).  The
     fp16 fused path must stay within the per-step bar of the fp32 CUDA path (itself pinned to the reference above),
     per sample, and a class-conditional CFG trajectory must stay within the final-latent bar."""
     from flocoder_b200 import sampling
