@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     int cols = 32;
-    while (cols < N * (n_acc < 0 ? 2 : n_acc) + (a_mode ? 32 : 0)) cols <<= 1;
+    while (cols < N * (n_acc < 0 ? 2 : n_acc) + (a_mode == 1 ? 32 : 0)) cols <<= 1;
     if (warp == 0) tmem_alloc(smem_u32(&tslot), cols);
     tc_fence_before();
     __syncthreads();
@@ -459,7 +459,10 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
     if (warp == 1 || (dual && warp == 2)) {
         const uint32_t idesc = make_idesc_bf16(128, N);
         const uint32_t base = smem_u32(smem);
-        const uint64_t ad0 = make_smem_desc(base + (uint32_t)a_shift, 2048u, 128u);   // A: LBO = 2 KB plane, SBO = 128 B
+        // A: LBO = 2 KB plane, SBO = 128 B; a_mode >= 2: the strided row groups of the zero-copy im2col (SBO = a_mode * 16 bytes,
+        // e.g. 18 = the padded row of a 16-pixel-wide image), LBO = 8 KB planes
+        const uint64_t ad0 = a_mode >= 2 ? make_smem_desc(base + (uint32_t)a_shift, 8192u, (uint32_t)a_mode * 16u)
+                                         : make_smem_desc(base + (uint32_t)a_shift, 2048u, 128u);
         const uint32_t a_t0 = tbase + (uint32_t)(N * nacc);                     // A tiles in TMEM (contents irrelevant for timing)
         const uint64_t bd0 = make_smem_desc(base + 64 * 1024, (uint32_t)N * 16u, 128u);
         const uint32_t tcol = tbase + (uint32_t)((warp - 1) * N);
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
 #pragma unroll 4
             for (int i = 0; i < n_mma; ++i) {
                 const uint32_t dcol = tcol + ((uint32_t)i & acc_mask) * (uint32_t)N;
-                if (a_mode) {
+                if (a_mode == 1) {
                     asm volatile(
                         "{\n\t.reg .pred p;\n\t"
                         "setp.ne.b32 p, %4, 0;\n\t"
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(128) k_umma_rate(long long* cycles, int N, int
                         ::"r"(dcol), "r"(a_t0 + (uint32_t)((i & 3) * 8)), "l"(bd0), "r"(idesc), "r"(1u)
                         : "memory");
                 } else {
-                    umma_bf16(dcol, ad0 + (uint64_t)((i & 3) * (4096 >> 4)), bd0, idesc, 1u);
+                    umma_bf16(dcol, ad0 + (uint64_t)((i & 3) * ((a_mode >= 2 ? 16384 : 4096) >> 4)), bd0, idesc, 1u);
                 }
             }
             umma_commit(smem_u32(&bar));

@@ -237,6 +237,9 @@ struct ChainParams {
     int n_loads, load_off[CH_MAX_LOADS], load_ncb[CH_MAX_LOADS];
     int zero_off, zero_bytes;               // shared-memory range to clear at start (epilogue-written slots)
     int ones_off;                           // 4 KB constant A tile [1,0,...] that multiplies the bias slice
+    int fast;                               // 1: the stage runs the warp-shuffle GroupNorm variant of k_chain (one sample per CTA, one
+                                            // accumulator chunk per thread in every step); FLO_NO_FAST_GN=1 forces the generic variant
+    int max_c;                              // largest per-step channel count (sizes gpar and the tables of the warp-shuffle GroupNorm path)
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
     int ring_off, ring_slot_bytes, n_ring;

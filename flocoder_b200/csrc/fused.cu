@@ -15,16 +15,20 @@
 //           * init_conv (unet.py:295) as the first epilogue of the first stage and final_conv + the RK4 / Euler
 //             / CFG stage update (unet.py:372, sampling.py:43-48,69-74) as the last epilogue of the last stage.
 //
-// Three decoupled loops per CTA (192 threads): warp 4 lane 0 = TMA producer (input tiles, weight ring),
-// warp 5 = tcgen05.mma issuer (warp-uniform code, one elected lane issues a whole weight chunk of MMAs with
-// incrementally updated descriptors), warps 0-3 = epilogue (TMEM lane quadrants).  Steps alternate
-// MMA(i) -> EPI(i) -> MMA(i+1) ... through two mbarriers (bar_mma: tcgen05.commit, bar_epi: 128 arrivals).
-// Every role copies what it needs of the (constant-bank) parameter block into registers first: the
-// asm-volatile "memory" clobbers of the PTX wrappers would otherwise force re-loads inside the hot loops.
-// The kernel is templated on the number of 128-row M tiles per CTA so tile loops and row bookkeeping are static.
+// Warp roles (320 threads): warps 0-7 = epilogue, warp 8 lane 0 = TMA producer (input tiles, weight ring), warp 9 =
+// tcgen05.mma issuer (warp-uniform code, one elected lane issues a whole weight chunk of MMAs).
+// The EIGHT epilogue warps are two warp groups that share the four TMEM lane quadrants: with several M tiles per
+// CTA a warp group owns whole tiles (tile t -> group t & 1), with one M tile the groups split the output channels
+// (group g -> channels [g C/2, (g+1) C/2)), so a thread normalises 8..16 accumulator values per step instead of 32:
+// the epilogue is a latency chain (TMEM load -> FMA -> MUFU -> pack -> store), and its length, not the instruction
+// count, is what a step costs.  The kernel is templated on the M tiles per CTA, the N-split and the 16-bit operand
+// format, so tile loops, row bookkeeping and pack/unpack code are static.
+// Steps alternate MMA(i) -> EPI(i) -> MMA(i+1) ... through two mbarriers (bar_mma: tcgen05.commit, bar_epi: 256
+// arrivals); overlap of one sample group's epilogue with another's MMAs comes from the co-resident CTA.
 #include <cuda_fp16.h>
 
 #include <cstring>
+#include <type_traits>
 #include "flo_internal.h"
 #include "umma_common.cuh"
 #include "fused_common.cuh"
@@ -48,7 +52,6 @@ __device__ __forceinline__ int tile_row0(const Geo& g, int t) {
 struct RowInfo {
     int pp;        // flattened padded pixel index inside the CTA's planes
     int s, px;     // sample within the CTA, unpadded pixel index h*W+w
-    int h, w;
     bool valid;
 };
 __device__ __forceinline__ RowInfo make_row(const Geo& g, int t, int r, int b0) {
@@ -57,8 +60,7 @@ __device__ __forceinline__ RowInfo make_row(const Geo& g, int t, int r, int b0) 
     ri.s = ri.pp / g.PP;
     const int rem = ri.pp - ri.s * g.PP;
     const int hh = rem / g.Wp, ww = rem - hh * g.Wp;
-    ri.h = hh - 1; ri.w = ww - 1;
-    ri.px = ri.h * g.W + ri.w;
+    ri.px = (hh - 1) * g.W + (ww - 1);
     ri.valid = (ri.s < g.nb) && (b0 + ri.s < g.B) && hh >= 1 && hh <= g.H && ww >= 1 && ww <= g.W;
     return ri;
 }
@@ -79,7 +81,7 @@ struct IssueCtx {
     uint32_t tmem_base, bar_full, bar_empty, ring_lo, ring_slot16, ones_lo;
     uint32_t plane16;          // plane stride >> 4
     uint32_t desc_hi_a, desc_hi_ones;
-    int n_ring, fmt;
+    int n_ring;
     uint32_t row0[MT];
     int cc;                    // global ring chunk counter
     RingPos rp;
@@ -92,9 +94,9 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
 }
 // The A operand of K16 slice ks = two channel-block planes of one input slot, shifted by the 3x3 tap: its start
 // address comes from the table built at kernel start, so the issuing thread runs load / add / tcgen05.mma only.
-template <int MT>
+template <int MT, int FMT>
 __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) {
-    const uint32_t idesc = make_idesc16(128, c.n, x.fmt, 0, 0);
+    const uint32_t idesc = make_idesc16(128, c.n, FMT, 0, 0);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);
     const uint32_t b_lbo = ((uint32_t)c.n & 0x3FFFu) << 16;      // n*16 bytes >> 4 in the LBO field
     const uint32_t a_lbo = (x.plane16 & 0x3FFFu) << 16;
@@ -158,64 +160,30 @@ __device__ __forceinline__ void issue_conv(IssueCtx<MT>& x, const ConvIssue& c) 
         x.rp.next(x.n_ring);
     }
 }
+
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
-struct OutDst {                 // destinations of one step's result, in registers
-    int slot_off;               // shared-memory slot or -1
-    uint4* g; uint4* g_un; uint4* g_up;
-    int ncb;
-    uint32_t smem_base; int nsplit;      // nsplit > 1: the slot is replicated in every CTA of the cluster (DSMEM stores)
-};
-__device__ __forceinline__ void write_outputs(const OutDst& o, const Geo& g, uint8_t* smem, uint32_t plane_bytes, const RowInfo& ri,
-                                              int b, int c16, const float* v, int fmt) {
-    const int HW = g.H * g.W;
-#pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
-        const int cb = (c16 >> 3) + hb;
-        const uint4 u = pack8(v + hb * 8, fmt);
-        if (o.slot_off >= 0) {
-            const uint32_t soff = (uint32_t)o.slot_off + (uint32_t)cb * plane_bytes + (uint32_t)ri.pp * 16u;
-            if (o.nsplit == 1) *reinterpret_cast<uint4*>(smem + soff) = u;
-            else
-                for (int q = 0; q < o.nsplit; ++q) st_cluster_v4(mapa_shared(o.smem_base + soff, (uint32_t)q), u);
-        }
-        if (o.g) o.g[(size_t)(cb * g.B + b) * HW + ri.px] = u;
-        if (o.g_un) {   // 'b c (h p1) (w p2) -> b (c p1 p2) h w' with our channel order (p1 p2 c)  (unet.py:52)
-            const int plane = ((ri.h & 1) * 2 + (ri.w & 1)) * o.ncb + cb;
-            const int q = (ri.h >> 1) * (g.W >> 1) + (ri.w >> 1);
-            o.g_un[(size_t)(plane * g.B + b) * (HW >> 2) + q] = u;
-        }
-        if (o.g_up) {   // nearest x2 (unet.py:44)
-            const int W2 = g.W * 2;
-            uint4* dst = o.g_up + (size_t)(cb * g.B + b) * (HW * 4);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) dst[(2 * ri.h + (d >> 1)) * W2 + 2 * ri.w + (d & 1)] = u;
-        }
-    }
-}
+template <int N> struct IntTag { static constexpr int value = N; };
 
-// Per-(sample, group) statistics from the per-row (sum, sumsq) pairs in shared memory, then the collapsed
+// Per-(sample, group) statistics from the per-row (sum, sumsq) partials in shared memory, then the collapsed
 // (scale, offset) table:  y = x*scale + offset  ==  FiLM(GroupNorm(x)).
-//   rowstat[row * G + g], rows = MT*128.  A segment of `seg` lanes owns one (sample, group): every lane sums a
-//   strided share of the rows in a fixed order, a shuffle tree combines them (deterministic), and the same lanes
-//   then write the group's channels of coef[s*C + c].  Two named barriers per call.
-struct FilmSrc {
-    const float* tab;       // FiLM table
-    int per_sample, row, dim;
-};
+//   rowstat[row * GS + gs], rows = MT*128, GS = G * pm: `pm` partial columns per group (2 when the two warp groups of
+//   a one-tile CTA each hold half of a group's channels).  A segment of `seg` lanes owns one (sample, group): every
+//   lane sums a strided share of the rows in a fixed order, a shuffle tree combines them (deterministic), and the same
+//   lanes then write the group's channels of coef[s*C + c].  Two named barriers per call.
 // `gpar[c]` = (gamma, beta); with `has_film`, coef[s*C+c] holds (1+scale, shift) on entry.
 struct XChg {                    // cross-CTA (cluster) reduction of per-sample statistics; nsplit == 1: unused
     int nsplit; uint32_t rank, smem_base, bar_x; int xpart_off; uint32_t* phase; uint8_t* smem;
 };
-__device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int C, int HW,
-                              bool has_film, int tid, const XChg* xc = nullptr) {
+__device__ __forceinline__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int pm,
+                                              int C, int HW, bool has_film, int et, const XChg* xc = nullptr) {
     // G, C, seg are powers of two: shifts instead of runtime integer divisions on this serial stretch
-    const int lgG = 31 - __clz(G), combos = g.nb * G, cpg = C >> lgG;
-    const int cpw = (combos + 3) >> 2;
+    const int lgG = 31 - __clz(G), combos = g.nb * G, cpg = C >> lgG, GS = G * pm;
+    const int cpw = (combos + EPI_WARPS - 1) / EPI_WARPS;
     int seg = 32;
     while (seg * cpw > 32) seg >>= 1;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = et >> 5, lane = et & 31;
     const int lgS = 31 - __clz(seg);
     const int combo = warp * (32 >> lgS) + (lane >> lgS), li = lane & (seg - 1);
     const bool active = combo < combos;
@@ -228,7 +196,15 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
             lo = min(max(s * g.PP - (g.Wp + 1), 0), R);
             hi = min(max((s + 1) * g.PP - (g.Wp + 1), 0), R);
         }
-        for (int r = lo + li; r < hi; r += seg) { const float2 v = rowstat[r * G + gi]; sx += v.x; sq += v.y; }
+        const float2* rs = rowstat + gi * pm;
+        if (pm == 1) {
+            for (int r = lo + li; r < hi; r += seg) { const float2 v = rs[r * GS]; sx += v.x; sq += v.y; }
+        } else {
+            for (int r = lo + li; r < hi; r += seg) {
+                const float4 v = *reinterpret_cast<const float4*>(rs + r * GS);
+                sx += v.x + v.z; sq += v.y + v.w;
+            }
+        }
     }
     for (int o = seg >> 1; o > 0; o >>= 1) {
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
@@ -244,7 +220,7 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
                 st_cluster_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
                               make_float2(sx, sq));
         epi_sync();                      // the publishing lanes' remote stores are ordered before the release-arrives below
-        if (tid == 0)
+        if (et == 0)
             for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
         mbar_wait_cluster(xc->bar_x, *xc->phase & 1u);
         ++*xc->phase;
@@ -274,19 +250,48 @@ __device__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2
     epi_sync();
 }
 
+// Sum of NV values per lane over the 32 lanes of a warp.  A butterfly would move all NV values at every level (NV x 5
+// shuffles); here every level also halves the values a lane is responsible for, so the exchange costs NV/2 + NV/4 + ...
+// + 1 shuffles for the splitting levels and one per remaining level.  On return p[0] holds the warp total of value
+// `idx` (the return value: bit k of idx = lane bit 4-k); the 32/NV lanes with the same upper lane bits hold the same
+// total.  Fixed exchange pattern: deterministic.
+template <int NV>
+__device__ __forceinline__ int warp_sum_scatter(float (&p)[NV], int lane) {
+    int idx = 0, o = 16;
+#pragma unroll
+    for (int h = NV / 2; h >= 1; h >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < h; ++j) {
+            const float send = upper ? p[j] : p[j + h];
+            const float keep = upper ? p[j + h] : p[j];
+            p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        idx += upper ? h : 0;
+    }
+    for (; o >= 1; o >>= 1) p[0] += __shfl_xor_sync(0xffffffffu, p[0], o);
+    return idx;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_chain
 // ------------------------------------------------------------------------------------------------
 // SPLIT: the N-split (cluster) variant; false compiles every cluster / DSMEM path out (Q == 1, c0 == 0 fold away)
+#ifndef FLO_CHAIN_MINB
+#define FLO_CHAIN_MINB 2
+#endif
 constexpr int FINAL_MAX_CH = 4;     // latent channels the fused final epilogue handles (api.cu routes more to the layer-wise path)
-template <int MT, bool SPLIT>
-__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
+// FAST: every GroupNorm step of the stage takes the warp-shuffle path (one sample per CTA, one accumulator chunk per
+// thread: chosen by the planner); the generic row-statistics path is compiled out, and vice versa.
+template <int MT, bool SPLIT, int FMT, bool FAST>
+__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
                                                          const __grid_constant__ CUtensorMap tm3,
                                                          const __grid_constant__ ChainParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1;
     const uint32_t smem_base = smem_u32(smem);
     const int bar_off = p.bar_off;
     const uint32_t bar_full = smem_base + bar_off;
@@ -304,12 +309,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     const int lgQ = SPLIT ? 31 - __clz(Q) : 0;          // cluster sizes are powers of two
     const int b0 = ((int)blockIdx.x >> lgQ) * geo.nb;
     const uint32_t plane_bytes = (uint32_t)p.plane_px * 16u;
-    const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, fmt = p.fmt, tmem_cols = p.tmem_cols;
+    const int n_steps = p.n_steps, n_ring = p.n_ring, n_loads = p.n_loads, tmem_cols = p.tmem_cols;
     const int ones_off = p.ones_off;
     long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
 
-    if (warp == 4 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
@@ -318,11 +323,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         mbar_init(bar_x, SPLIT ? Q : EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     {   // clear the slots the epilogues write (their halo must read as zero) and build the "ones" A tile
         const int zoff = p.zero_off, zbytes = p.zero_bytes;
         for (int i = tid * 16; i < zbytes; i += FUSED_THREADS * 16) *reinterpret_cast<uint4*>(smem + zoff + i) = make_uint4(0, 0, 0, 0);
-        const uint32_t ones2 = pack2(1.0f, 1.0f, fmt);
+        const uint32_t ones2 = pack2t<FMT>(1.0f, 1.0f);
         for (int i = tid; i < 256; i += FUSED_THREADS)      // plane 0: [1,1,0,0,0,0,0,0] per row (bias hi + lo); plane 1: zeros
             *reinterpret_cast<uint4*>(smem + ones_off + i * 16) = make_uint4(i < 128 ? ones2 : 0u, 0, 0, 0);
     }
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8] = clock64();
     if (dbg && tid == 0) dbg[101] = global_ns();
 
-    if (warp == 4) {
+    if (warp == W_PROD) {
         // ============================ producer ============================
         if (lane == 0) {
             const uint32_t ring_base = smem_base + p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             }
             for (int cc = pre; cc < n_chunks; ++cc) issue(cc);
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
         IssueCtx<MT> x;
         x.tmem_base = tmem_base; x.bar_full = bar_full; x.bar_empty = bar_empty;
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         x.plane16 = plane_bytes >> 4;
         x.desc_hi_a = (((uint32_t)geo.sbo_px * 16u) >> 4) | (1u << 14);
         x.desc_hi_ones = (128u >> 4) | (1u << 14);
-        x.n_ring = n_ring; x.fmt = fmt; x.cc = 0; x.rp.slot = 0; x.rp.phase = 0; x.dbg = dbg;
+        x.n_ring = n_ring; x.cc = 0; x.rp.slot = 0; x.rp.phase = 0; x.dbg = dbg;
 #pragma unroll
         for (int t = 0; t < MT; ++t) x.row0[t] = (uint32_t)tile_row0(geo, t);
         if (n_loads > 0) mbar_wait(bar_load, 0);
@@ -414,11 +419,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 c.tab = atab + p.st[i].tab_idx;
                 c.n = p.st[i].n; c.col = p.st[i].acc_col; c.slices = p.st[i].slices;
                 c.S = p.st[i].slices_per_chunk;
-                issue_conv<MT>(x, c);
+                issue_conv<MT, FMT>(x, c);
                 if (p.st[i].has_res) {
                     c.tab = atab + p.st[i].res_tab_idx;
                     c.col = p.st[i].res_col; c.slices = p.st[i].res_slices; c.S = p.st[i].res_slices_per_chunk;
-                    issue_conv<MT>(x, c);
+                    issue_conv<MT, FMT>(x, c);
                 }
                 if (dbg && lane == 0) dbg[i * 8 + 1] = clock64();
                 if (elect_one()) umma_commit(bar_mma);
@@ -429,26 +434,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
         }
     } else {
         // ============================ epilogue warps ============================
-        const int r = warp * 32 + lane;                       // row inside every M tile == TMEM lane
-        const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int wg = warp >> 2, quad = warp & 3;            // warp group; TMEM lane quadrant
+        const int r = quad * 32 + lane;                       // row inside every M tile == TMEM lane
+        const int et = tid;                                   // epilogue thread index (warps 0..7)
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);
         float2* coef = rowstat + MT * 128 * p.g_max;          // [nb][C] (scale, offset)
         float* cpar = reinterpret_cast<float*>(coef + p.coef_n);   // small per-step constants (init / final conv weights)
         const int cpar_n = p.cpar_n;
+        float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
+        float* const fastbuf = reinterpret_cast<float*>(gpar + p.max_c);
         Ctrl* ctrl = p.ctrl;
         const float* fblob = p.fblob;
         const int HW = geo.H * geo.W;
         griddep_wait();              // ctrl, the FiLM table and every activation come from earlier kernels
-        void* gt[CH_MAX_GT];
-#pragma unroll
-        for (int i = 0; i < CH_MAX_GT; ++i) gt[i] = p.gt[i];
         const int step_idx = ctrl->step;
         const Stage sg = ctrl->stages[step_idx];
-        FilmSrc film;
-        film.tab = ctrl->film; film.per_sample = ctrl->film_per_sample; film.row = sg.film_row; film.dim = p.film_dim;
-        RowInfo ri[MT];
+        const float* film_tab = ctrl->film;
+        const int film_per_sample = ctrl->film_per_sample, film_row = sg.film_row, film_dim = p.film_dim;
+        // the M tiles of this thread's warp group: tile wg, wg + 2, ... (one tile: both groups work on tile 0)
+        constexpr int TW = (MT + 1) / 2;
+        RowInfo ri[TW];
 #pragma unroll
-        for (int t = 0; t < MT; ++t) ri[t] = make_row(geo, t, r, b0);
+        for (int k = 0; k < TW; ++k) {
+            const int t = (MT == 1) ? 0 : wg + 2 * k;
+            if (t < MT) ri[k] = make_row(geo, t, r, b0);
+            else { ri[k].pp = 0; ri[k].s = 0; ri[k].px = 0; ri[k].valid = false; }
+        }
         if (n_loads > 0) mbar_wait(bar_load, 0);
         uint32_t xphase = 0;
         XChg xc;
@@ -461,39 +473,149 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             const int C = Ctot >> lgQ, c0 = (int)qrank * C;      // this CTA's channels [c0, c0 + C) of the step's Ctot
             const int res_mode = p.st[i].res_mode, res_slot_off = p.st[i].res_slot_off;
             const int is_final = p.st[i].final, pn_g = p.st[i].pn_g;
-            OutDst od;
-            od.slot_off = p.st[i].out_slot_off; od.ncb = Ctot >> 3; od.smem_base = smem_base; od.nsplit = Q;
-            od.g = p.st[i].out_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_g]) : nullptr;
-            od.g_un = p.st[i].out_un_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_un_g]) : nullptr;
-            od.g_up = p.st[i].out_up_g >= 0 ? reinterpret_cast<uint4*>(gt[p.st[i].out_up_g]) : nullptr;
+            const int out_slot_off = p.st[i].out_slot_off;
+            uint4* const og = p.st[i].out_g >= 0 ? reinterpret_cast<uint4*>(p.gt[p.st[i].out_g]) : nullptr;
+            // this thread's channels of the step: one tile -> the warp groups split the channels (the final epilogue needs all
+            // channels of a row in one thread: warp group 0 alone); several tiles -> all channels of the group's tiles
+            int cbeg = 0, cend = C;
+            if (MT == 1) {
+                if (is_final) { cend = wg == 0 ? C : 0; }
+                else { cbeg = wg * (C >> 1); cend = cbeg + (C >> 1); }
+            }
+            const bool cw8 = (cend - cbeg) == 8;
+            // one 8-channel block of one row -> shared-memory slot(s) and/or the global tensor
+            auto write8 = [&](const RowInfo& R, int cb, const float* v8) -> uint4 {
+                const uint4 u = pack8t<FMT>(v8);
+                if (out_slot_off >= 0) {
+                    const uint32_t soff = (uint32_t)out_slot_off + (uint32_t)cb * plane_bytes + (uint32_t)R.pp * 16u;
+                    if (!SPLIT) *reinterpret_cast<uint4*>(smem + soff) = u;
+                    else
+                        for (int q = 0; q < Q; ++q) st_cluster_v4(mapa_shared(smem_base + soff, (uint32_t)q), u);
+                }
+                if (og) og[(size_t)(cb * geo.B + b0 + R.s) * HW + R.px] = u;
+                return u;
+            };
+            // calls fn(k, c, IntTag<CW>) for every (tile, channel chunk) of this thread
+            auto for_chunks = [&](auto&& fn) {
+                if (cw8) {
+                    fn(0, cbeg, IntTag<8>());
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TW; ++k) {
+                        if (MT > 1 && wg + 2 * k >= MT) continue;
+                        for (int c = cbeg; c < cend; c += 16) fn(k, c, IntTag<16>());
+                    }
+                }
+            };
+            auto tile_of = [&](int k) { return (MT == 1) ? 0 : wg + 2 * k; };
+            // ---- final_conv bias + RK4 / Euler / CFG stage update (sampling.py:43-48,69-74)
+            // the integrator state this thread updates is requested in one batch (independent loads in flight instead of
+            // a dependent chain per element); the control block's pointers are read once
+            auto final_update = [&](const float (&kacc)[(MT + 1) / 2][FINAL_MAX_CH]) {
+                float* const Y = ctrl->y; float* const ACC = ctrl->acc; float* const XS = ctrl->xs; float* const VOUT = ctrl->vout;
+                float* const VC = ctrl->vcond; float* const VT = ctrl->vtrace;
+                const float cfg_s = ctrl->cfg;
+                const int nch = p.channels, dim = p.dim;
+                const size_t plane = (size_t)geo.B * nch * HW;
+#pragma unroll
+                for (int k = 0; k < (MT + 1) / 2; ++k) {
+                    if (MT > 1 && wg + 2 * k >= MT) continue;
+                    if (!ri[k].valid) continue;
+                    const int b = b0 + ri[k].s;
+                    float fy[4], fa[4], fc[4];
+#pragma unroll
+                    for (int co = 0; co < 4; ++co) {
+                        fy[co] = 0.f; fa[co] = 0.f; fc[co] = 0.f;
+                        if (co < nch) {
+                            const size_t o = ((size_t)b * nch + co) * HW + ri[k].px;
+                            if (sg.kind != ST_PLAIN && sg.kind != ST_CFG_COND) fy[co] = Y[o];
+                            if (sg.kind == ST_RK2 || sg.kind == ST_RK3 || sg.kind == ST_RK4) fa[co] = ACC[o];
+                            if (sg.flags & SF_CFG_COMBINE) fc[co] = VC[o];
+                        }
+                    }
+#pragma unroll
+                    for (int co = 0; co < FINAL_MAX_CH; ++co) {
+                        if (co >= nch) continue;
+                        float kv = kacc[k][co] + cpar[nch * dim + co];
+                        const size_t o = ((size_t)b * nch + co) * HW + ri[k].px;
+                        if (sg.flags & SF_CFG_COMBINE) kv = __fadd_rn(kv, __fmul_rn(cfg_s, __fsub_rn(fc[co], kv)));
+                        if (VT && sg.eval_idx >= 0) VT[(size_t)sg.eval_idx * plane + o] = kv;
+                        switch (sg.kind) {
+                            case ST_PLAIN: VOUT[o] = kv; break;
+                            case ST_CFG_COND: VC[o] = kv; break;
+                            case ST_RK1:
+                                ACC[o] = kv;
+                                XS[o] = __fadd_rn(fy[co], __fmul_rn(__fmul_rn(sg.dt, kv), 0.5f));
+                                break;
+                            case ST_RK2:
+                                ACC[o] = __fadd_rn(fa[co], __fmul_rn(2.0f, kv));
+                                XS[o] = __fadd_rn(fy[co], __fmul_rn(__fmul_rn(sg.dt, kv), 0.5f));
+                                break;
+                            case ST_RK3:
+                                ACC[o] = __fadd_rn(fa[co], __fmul_rn(2.0f, kv));
+                                XS[o] = __fadd_rn(fy[co], __fmul_rn(sg.dt, kv));
+                                break;
+                            case ST_RK4: {
+                                const float yn = __fadd_rn(fy[co], __fmul_rn(sg.dt6, __fadd_rn(fa[co], kv)));
+                                Y[o] = yn; XS[o] = yn;
+                            } break;
+                            case ST_EULER: {
+                                const float yn = __fadd_rn(fy[co], __fmul_rn(kv, sg.dt));
+                                Y[o] = yn; XS[o] = yn;
+                            } break;
+                            default: break;
+                        }
+                    }
+                }
+            };
+            // warp-shuffle GroupNorm path: one sample per CTA and one accumulator chunk per thread
+            constexpr bool fast_gn_k = FAST;
+            const bool fast_gn = FAST && epi == CE_GN;
+            float* const wpart = fastbuf;                                           // [8 warps][8] block norm | [8][2] PreNorm at +64
+            float2* const gcoef = reinterpret_cast<float2*>(fastbuf + 128) + (i & 1) * p.max_c;          // (gamma', beta') with FiLM folded
+            float2* const pnpar = reinterpret_cast<float2*>(fastbuf + 128) + (2 + (i & 1)) * p.max_c;    // PreNorm (gamma, beta)
+
             // small constants staged while the MMAs of this step run
             if (epi == CE_INIT) {
                 const float* w = fblob + p.init_w_off;
                 const float* bias = fblob + p.init_b_off;
                 const int cin0 = p.cin0;
-                for (int k = r; k < C * cin0; k += EPI_THREADS) cpar[k] = w[k];
-                for (int k = r; k < C; k += EPI_THREADS) cpar[C * cin0 + k] = bias[k];
+                for (int k = et; k < C * cin0; k += EPI_THREADS) cpar[k] = w[k];
+                for (int k = et; k < C; k += EPI_THREADS) cpar[C * cin0 + k] = bias[k];
                 epi_sync();
             } else if (is_final) {
                 const float* w = fblob + p.final_w_off;
                 const float* bias = fblob + p.final_b_off;
                 const int nch = p.channels, dim = p.dim;
-                for (int k = r; k < nch * dim; k += EPI_THREADS) cpar[k] = w[k];
-                for (int k = r; k < nch; k += EPI_THREADS) cpar[nch * dim + k] = bias[k];
+                for (int k = et; k < nch * dim; k += EPI_THREADS) cpar[k] = w[k];
+                for (int k = et; k < nch; k += EPI_THREADS) cpar[nch * dim + k] = bias[k];
             }
-            if (epi == CE_GN) {
+            if (fast_gn) {
+                // per-channel GroupNorm affine with the sample's FiLM factors folded in, fetched while the MMAs run:
+                //   FiLM(GN(x)) = xhat*gamma' + beta',  gamma' = gamma (1+scale), beta' = beta (1+scale) + shift   (unet.py:70)
+                // The tables alternate between two buffers by step parity: a thread cannot be two steps ahead of another one.
+                const float* gamma = fblob + p.st[i].gamma_off;
+                const float* beta = fblob + p.st[i].beta_off;
+                const int foff = p.st[i].film_off;
+                const float* fl = film_tab + (size_t)(film_per_sample ? b0 : film_row) * film_dim + foff;
+                for (int c = et; c < C; c += EPI_THREADS) {
+                    float f1 = 1.0f, f2 = 0.0f;
+                    if (foff >= 0) { f1 = fl[c] + 1.0f; f2 = fl[C + c]; }
+                    gcoef[c] = make_float2(gamma[c] * f1, fmaf(beta[c], f1, f2));
+                    if (pn_g >= 0) pnpar[c] = make_float2(fblob[p.st[i].pn_gamma_off + c], fblob[p.st[i].pn_beta_off + c]);
+                }
+            } else if (epi == CE_GN) {
                 // per-channel GroupNorm affine and per-(sample, channel) FiLM factors, fetched while the MMAs run
                 epi_sync();           // every thread is done reading the previous step's coef / gpar
                 const float* gamma = fblob + p.st[i].gamma_off;
                 const float* beta = fblob + p.st[i].beta_off;
-                float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
-                for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c0 + c], beta[c0 + c]);
+                for (int c = et; c < C; c += EPI_THREADS) gpar[c] = make_float2(gamma[c0 + c], beta[c0 + c]);
                 const int foff = p.st[i].film_off, lgC = 31 - __clz(C);
-                for (int idx = r; idx < geo.nb * C; idx += EPI_THREADS) {
+                for (int idx = et; idx < geo.nb * C; idx += EPI_THREADS) {
                     const int s = idx >> lgC, c = idx & (C - 1);
                     float2 f = make_float2(1.0f, 0.0f);
                     if (foff >= 0 && b0 + s < geo.B) {
-                        const float* fl = film.tab + (size_t)(film.per_sample ? (b0 + s) : film.row) * film.dim + foff;
+                        const float* fl = film_tab + (size_t)(film_per_sample ? (b0 + s) : film_row) * film_dim + foff;
                         f = make_float2(fl[c0 + c] + 1.0f, fl[Ctot + c0 + c]);          // x*(scale+1)+shift, unet.py:70
                     }
                     coef[idx] = f;
@@ -501,7 +623,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
             }
             mbar_wait(bar_mma, i & 1);
             tc_fence_after();
-            if (dbg && r == 0) dbg[i * 8 + 2] = clock64();
+            if (dbg && et == 0) dbg[i * 8 + 2] = clock64();
             // programmatic dependent launch: let the next stage kernel become resident only now, during the last epilogue
             // (its barrier init, TMEM allocation, table copy and weight prefetch overlap this kernel's tail); triggering at
             // kernel start was measured to slow the running kernel (profiles/r01_pdl_gaps.txt)
@@ -512,265 +634,362 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                 const float* xs = ctrl->xs;
                 const int cin0 = p.cin0;
 #pragma unroll
-                for (int t = 0; t < MT; ++t) {
-                    if (!ri[t].valid) continue;
-                    const int b = b0 + ri[t].s;
+                for (int k = 0; k < TW; ++k) {
+                    if (MT > 1 && wg + 2 * k >= MT) continue;
+                    if (!ri[k].valid) continue;
+                    const int b = b0 + ri[k].s;
                     float xin[16];
 #pragma unroll
-                    for (int ci = 0; ci < 16; ++ci) xin[ci] = ci < cin0 ? xs[((size_t)b * cin0 + ci) * HW + ri[t].px] : 0.f;
-                    for (int c16 = 0; c16 < C; c16 += 16) {
-                        float v[16];
+                    for (int ci = 0; ci < 16; ++ci) xin[ci] = ci < cin0 ? xs[((size_t)b * cin0 + ci) * HW + ri[k].px] : 0.f;
+                    for (int c8 = cbeg; c8 < cend; c8 += 8) {
+                        float v[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = cpar[C * cin0 + c16 + j];
+                        for (int j = 0; j < 8; ++j) {
+                            float a = cpar[C * cin0 + c8 + j];
                             if (cin0 == 4) {          // the usual latent: one 16-byte weight row per output channel
-                                const float4 w4 = *reinterpret_cast<const float4*>(cpar + (c16 + j) * 4);
+                                const float4 w4 = *reinterpret_cast<const float4*>(cpar + (c8 + j) * 4);
                                 a = fmaf(xin[0], w4.x, a); a = fmaf(xin[1], w4.y, a); a = fmaf(xin[2], w4.z, a); a = fmaf(xin[3], w4.w, a);
                             } else {
 #pragma unroll
                                 for (int ci = 0; ci < 16; ++ci)
-                                    if (ci < cin0) a = fmaf(xin[ci], cpar[(c16 + j) * cin0 + ci], a);
+                                    if (ci < cin0) a = fmaf(xin[ci], cpar[(c8 + j) * cin0 + ci], a);
                             }
                             v[j] = a;
                         }
-                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c16, v, fmt);
+                        write8(ri[k], (c0 + c8) >> 3, v);
                     }
                 }
             } else if (epi == CE_BIAS) {
-                // ---- conv (+bias via the GEMM) (+ residual from a shared-memory slot)
+                // ---- conv (+bias via the GEMM)
+                for_chunks([&](int k, int c, auto tag) {
+                    constexpr int CW = decltype(tag)::value;
+                    uint32_t u[CW];
+                    const uint32_t ta = tlane + (uint32_t)(acc_col + tile_of(k) * C + c);
+                    if constexpr (CW == 16) tmem_ld16_issue(ta, u); else tmem_ld8_issue(ta, u);
+                    tmem_ld_wait();
+                    if (!ri[k].valid) return;
+                    float v[CW];
 #pragma unroll
-                for (int t = 0; t < MT; ++t) {
-                    const int b = b0 + ri[t].s;
-                    for (int c16 = 0; c16 < C; c16 += 16) {
-                        float v[16];
-                        tmem_ld16(tlane + (uint32_t)(acc_col + t * C + c16), v);
-                        if (!ri[t].valid) continue;
-                        if (res_mode == 2) {
-                            float rr[16];
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + c16) >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
-                            unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
-                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
+                    for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(u[j]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += rr[j];
-                        }
-                        write_outputs(od, geo, smem, plane_bytes, ri[t], b, c0 + c16, v, fmt);
-                    }
-                }
+                    for (int hb = 0; hb < CW / 8; ++hb) write8(ri[k], ((c0 + c) >> 3) + hb, v + hb * 8);
+                });
             } else {
                 // ---- conv (+bias) -> GroupNorm -> FiLM -> SiLU -> + residual     (unet.py:64-73,96)
-                const int G = p.st[i].groups >> lgQ, cpg = C >> (31 - __clz(G)), silu = p.st[i].silu;       // this CTA's groups (powers of two)
-                // pass 1: per-row (sum, sumsq) per group; the TMEM loads of all tiles are issued before one wait
-                if (cpg >= 16) {
-                    for (int gi = 0; gi < G; ++gi) {
-                        float sx[MT], sq[MT];
+                const int G = p.st[i].groups >> lgQ, lg_cpg = 31 - __clz(C) - (31 - __clz(G)), cpg = 1 << lg_cpg;
+                float kacc[TW][FINAL_MAX_CH];       // final 1x1 conv accumulators (latent channels; fused path: <= 4)
+                float psx[TW], psq[TW];
 #pragma unroll
-                        for (int t = 0; t < MT; ++t) { sx[t] = 0.f; sq[t] = 0.f; }
-                        for (int c16 = gi * cpg; c16 < (gi + 1) * cpg; c16 += 16) {
-                            uint32_t v[MT][16];
+                for (int k = 0; k < TW; ++k) {
+                    psx[k] = 0.f; psq[k] = 0.f;
 #pragma unroll
-                            for (int t = 0; t < MT; ++t) tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), v[t]);
+                    for (int j = 0; j < FINAL_MAX_CH; ++j) kacc[k][j] = 0.f;
+                }
+                if constexpr (fast_gn_k) {
+                    if (dbg && et == 0) dbg[i * 8 + 3] = clock64();
+                    // ======== one sample per CTA, one accumulator chunk per thread: the values stay in registers between the
+                    // statistics and the normalisation, the statistics are reduced with warp shuffles and ONE named barrier,
+                    // and every thread derives mean / rstd of its own groups from the eight per-warp partial sums.
+                    float y[16];
+                    uint4 pk[2];
+                    const bool has_work = cend > cbeg;             // warp-uniform (the idle warp group of a one-tile final step)
+                    const int t = tile_of(0);
+                    // warps whose partial sums make up this thread's groups
+                    const int wlo = (MT == 1 && (G > 1 || is_final)) ? wg * 4 : 0;
+                    const int whi = (MT == 1 && (G > 1 || is_final)) ? wg * 4 + 4 : EPI_WARPS;
+                    const float icnt = fast_rcp((float)(cpg * HW));
+                    auto head = [&](auto cw_tag, auto ng_tag) {
+                        constexpr int CW = decltype(cw_tag)::value, NG = decltype(ng_tag)::value, NV = 2 * NG, CG = CW / NG;
+                        if (has_work) {
+                            uint32_t av[CW];
+                            const uint32_t ta = tlane + (uint32_t)(acc_col + t * C + cbeg);
+                            if constexpr (CW == 16) tmem_ld16_issue(ta, av); else tmem_ld8_issue(ta, av);
                             tmem_ld_wait();
+                            float ps[NV];
 #pragma unroll
-                            for (int t = 0; t < MT; ++t)
+                            for (int g = 0; g < NG; ++g) {
+                                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) { const float xv = __uint_as_float(v[t][j]); sx[t] += xv; sq[t] = fmaf(xv, xv, sq[t]); }
-                        }
-#pragma unroll
-                        for (int t = 0; t < MT; ++t)
-                            rowstat[(size_t)(t * 128 + r) * G + gi] = ri[t].valid ? make_float2(sx[t], sq[t]) : make_float2(0.f, 0.f);
-                    }
-                } else {
-                    for (int c16 = 0; c16 < C; c16 += 16) {
-                        uint32_t v[MT][16];
-#pragma unroll
-                        for (int t = 0; t < MT; ++t) tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), v[t]);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int t = 0; t < MT; ++t) {
-                            float2* rs_row = rowstat + (size_t)(t * 128 + r) * G;
-                            const bool valid = ri[t].valid;
-                            if (cpg == 4) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    float sx = 0.f, sq = 0.f;
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) { const float xv = __uint_as_float(v[t][q * 4 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
-                                    rs_row[(c16 >> 2) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                                for (int j = 0; j < CG; j += 2) {
+                                    const float xa = __uint_as_float(av[g * CG + j]), xb = __uint_as_float(av[g * CG + j + 1]);
+                                    s0 += xa; q0 = fmaf(xa, xa, q0); s1 += xb; q1 = fmaf(xb, xb, q1);
                                 }
-                            } else {   // cpg == 8
+                                const bool valid = ri[0].valid;
+                                ps[2 * g] = valid ? s0 + s1 : 0.f; ps[2 * g + 1] = valid ? q0 + q1 : 0.f;
+                            }
+                            const int idx = warp_sum_scatter<NV>(ps, lane);
+                            if ((lane & (32 / NV - 1)) == 0) wpart[warp * 8 + idx] = ps[0];
 #pragma unroll
-                                for (int q = 0; q < 2; ++q) {
-                                    float sx = 0.f, sq = 0.f;
+                            for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(av[j]);
+                        }
+                        epi_sync();
+                        if (!has_work) return;
+                        float sum[NV];
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) { const float xv = __uint_as_float(v[t][q * 8 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
-                                    rs_row[(c16 >> 3) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                        for (int v = 0; v < NV; ++v) sum[v] = 0.f;
+                        for (int w = wlo; w < whi; ++w) {           // fixed order: identical in every thread, deterministic
+                            if constexpr (NV == 2) {
+                                const float2 a = *reinterpret_cast<const float2*>(wpart + w * 8);
+                                sum[0] += a.x; sum[1] += a.y;
+                            } else {
+#pragma unroll
+                                for (int v4 = 0; v4 < NV / 4; ++v4) {
+                                    const float4 a = *reinterpret_cast<const float4*>(wpart + w * 8 + v4 * 4);
+                                    sum[v4 * 4] += a.x; sum[v4 * 4 + 1] += a.y; sum[v4 * 4 + 2] += a.z; sum[v4 * 4 + 3] += a.w;
                                 }
                             }
                         }
-                    }
-                }
-                if (dbg && r == 0) dbg[i * 8 + 3] = clock64();
-                stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), G, C, HW, true, r);
-                if (dbg && r == 0) dbg[i * 8 + 4] = clock64();
-                // pass 2: y = x*scale + offset, SiLU, + residual, write.  Chunk-major so that the TMEM loads of all
-                // tiles are in flight together and the per-element chains of MT*16 values interleave.
-                float kacc[MT][FINAL_MAX_CH];       // final 1x1 conv accumulators (latent channels; fused path: <= 4)
-                float psx[MT], psq[MT];
 #pragma unroll
-                for (int t = 0; t < MT; ++t) {
-                    psx[t] = 0.f; psq[t] = 0.f;
+                        for (int g = 0; g < NG; ++g) {
+                            const float mean = sum[2 * g] * icnt;
+                            const float var = fmaxf(sum[2 * g + 1] * icnt - mean * mean, 0.f);
+                            const float rstd = rsqrtf(var + 1e-5f);
+                            const float nmr = -mean * rstd;
 #pragma unroll
-                    for (int j = 0; j < FINAL_MAX_CH; ++j) kacc[t][j] = 0.f;
-                }
-                for (int c16 = 0; c16 < C; c16 += 16) {
-                    uint32_t av[MT][16], rv[MT][16];
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c16), av[t]);
-                        if (res_mode == 1) tmem_ld16_issue(tlane + (uint32_t)(res_col + t * C + c16), rv[t]);
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        if (!ri[t].valid) continue;
-                        const int b = b0 + ri[t].s;
-                        const float2* cf = coef + ri[t].s * C + c16;
-                        float v[16], rr[16];
+                            for (int j = 0; j < CG; ++j) y[g * CG + j] = fmaf(y[g * CG + j], rstd, nmr);
+                        }
+                    };
+                    auto tail = [&](auto cw_tag) {
+                        constexpr int CW = decltype(cw_tag)::value;
+                        if (!has_work) return;
+                        uint32_t rv[CW];
+                        if (res_mode == 1) {
+                            const uint32_t ta = tlane + (uint32_t)(res_col + t * C + cbeg);
+                            if constexpr (CW == 16) tmem_ld16_issue(ta, rv); else tmem_ld8_issue(ta, rv);
+                            tmem_ld_wait();
+                        }
+                        if (!ri[0].valid) return;
+                        float rr[CW];
                         if (res_mode == 2) {
-                            const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + c16) >> 3) * plane_bytes + (uint32_t)ri[t].pp * 16u;
-                            unpack8(*reinterpret_cast<const uint4*>(src), rr, fmt);
-                            unpack8(*reinterpret_cast<const uint4*>(src + plane_bytes), rr + 8, fmt);
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(cbeg >> 3) * plane_bytes + (uint32_t)ri[0].pp * 16u;
+#pragma unroll
+                            for (int hb = 0; hb < CW / 8; ++hb) unpack8t<FMT>(*reinterpret_cast<const uint4*>(src + hb * plane_bytes), rr + hb * 8);
                         } else if (res_mode == 1) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) rr[j] = __uint_as_float(rv[t][j]);
-                        }
+                            for (int j = 0; j < CW; ++j) rr[j] = __uint_as_float(rv[j]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 ab = cf[j];
-                            float y = fmaf(__uint_as_float(av[t][j]), ab.x, ab.y);
-                            if (silu) y = fast_silu(y);
-                            if (res_mode) y += rr[j];
-                            v[j] = y;
-                            psx[t] += y; psq[t] = fmaf(y, y, psq[t]);
+                            for (int j = 0; j < CW; ++j) rr[j] = 0.f;
                         }
+                        const float4* gc = reinterpret_cast<const float4*>(gcoef + cbeg);
+                        float sxa = 0.f, sqa = 0.f, sxb = 0.f, sqb = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CW; j += 2) {
+                            const float4 ab = gc[j >> 1];
+                            float ya = fmaf(y[j], ab.x, ab.y);
+                            float yb = fmaf(y[j + 1], ab.z, ab.w);
+                            ya = fast_silu(ya); yb = fast_silu(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
+                            ya += rr[j]; yb += rr[j + 1];
+                            y[j] = ya; y[j + 1] = yb;
+                            sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);
+                        }
+                        psx[0] = sxa + sxb; psq[0] = sqa + sqb;
                         if (is_final) {
                             const int nch = p.channels, dim = p.dim;
 #pragma unroll
                             for (int co = 0; co < FINAL_MAX_CH; ++co) {
                                 if (co < nch) {
-                                    float a = kacc[t][co];
+                                    float a = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) a = fmaf(v[j], cpar[co * dim + c16 + j], a);
-                                    kacc[t][co] = a;
+                                    for (int j = 0; j < CW; ++j) a = fmaf(y[j], cpar[co * dim + cbeg + j], a);
+                                    kacc[0][co] = a;
                                 }
                             }
                         } else {
-                            write_outputs(od, geo, smem, plane_bytes, ri[t], b, c0 + c16, v, fmt);
+#pragma unroll
+                            for (int hb = 0; hb < CW / 8; ++hb) pk[hb] = write8(ri[0], (cbeg >> 3) + hb, y + hb * 8);
                         }
+                    };
+                    const int ng = cpg >= 16 ? 1 : (cw8 ? 8 : 16) >> lg_cpg;          // groups inside this thread's chunk
+                    if (cw8) {
+                        if (ng == 2) head(IntTag<8>(), IntTag<2>()); else head(IntTag<8>(), IntTag<1>());
+                        if (dbg && et == 0) dbg[i * 8 + 4] = clock64();
+                        tail(IntTag<8>());
+                    } else {
+                        if (ng == 4) head(IntTag<16>(), IntTag<4>());
+                        else if (ng == 2) head(IntTag<16>(), IntTag<2>());
+                        else head(IntTag<16>(), IntTag<1>());
+                        if (dbg && et == 0) dbg[i * 8 + 4] = clock64();
+                        tail(IntTag<16>());
                     }
-                }
-                // the integrator state this thread will update in the last epilogue is requested in one batch (8 independent
-                // loads in flight instead of a dependent chain per element); the control block's pointers are read once
-                float fy[MT][4], fa[MT][4], fc[MT][4];
-                float *Y = nullptr, *ACC = nullptr, *XS = nullptr, *VOUT = nullptr, *VC = nullptr, *VT = nullptr;
-                float cfg_s = 0.f;
-                const bool fast_final = is_final && p.channels <= 4;
-                if (is_final) {
-                    Y = ctrl->y; ACC = ctrl->acc; XS = ctrl->xs; VOUT = ctrl->vout; VC = ctrl->vcond; VT = ctrl->vtrace; cfg_s = ctrl->cfg;
-                }
-                if (fast_final) {
-                    const int nch = p.channels;
+                    if (pn_g >= 0) {
+                        // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result; every warp
+                        // holds C/2 (one tile) or C (two tiles) channels of its rows
+                        float ps[2];
+                        ps[0] = ri[0].valid ? psx[0] : 0.f; ps[1] = ri[0].valid ? psq[0] : 0.f;
+                        warp_sum_scatter<2>(ps, lane);
+                        if ((lane & 15) == 0) wpart[64 + warp * 2 + (lane >> 4)] = ps[0];
+                        epi_sync();
+                        float sx = 0.f, sq = 0.f;
+                        for (int w = 0; w < EPI_WARPS; ++w) { const float2 a = *reinterpret_cast<const float2*>(wpart + 64 + w * 2); sx += a.x; sq += a.y; }
+                        const float icn = fast_rcp((float)(C * HW));
+                        const float mean = sx * icn;
+                        const float rstd = rsqrtf(fmaxf(sq * icn - mean * mean, 0.f) + 1e-5f);
+                        if (ri[0].valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.gt[pn_g]);
+                            const int nhb = cw8 ? 1 : 2;
 #pragma unroll
-                    for (int t = 0; t < MT; ++t)
+                            for (int hb = 0; hb < 2; ++hb) {
+                                if (hb >= nhb) break;
+                                const int gcb = (cbeg >> 3) + hb;
+                                float xv[8];
+                                unpack8t<FMT>(pk[hb], xv);
+                                const float4* pp4 = reinterpret_cast<const float4*>(pnpar + cbeg + hb * 8);
 #pragma unroll
-                        for (int co = 0; co < 4; ++co) {
-                            fy[t][co] = 0.f; fa[t][co] = 0.f; fc[t][co] = 0.f;
-                            if (ri[t].valid && co < nch) {
-                                const size_t o = ((size_t)(b0 + ri[t].s) * nch + co) * HW + ri[t].px;
-                                if (sg.kind != ST_PLAIN && sg.kind != ST_CFG_COND) fy[t][co] = Y[o];
-                                if (sg.kind == ST_RK2 || sg.kind == ST_RK3 || sg.kind == ST_RK4) fa[t][co] = ACC[o];
-                                if (sg.flags & SF_CFG_COMBINE) fc[t][co] = VC[o];
+                                for (int j = 0; j < 8; j += 2) {
+                                    const float4 gb = pp4[j >> 1];                       // (gamma, beta) x 2 channels
+                                    const float a0 = rstd * gb.x, a1 = rstd * gb.z;
+                                    xv[j] = fmaf(xv[j], a0, gb.y - mean * a0); xv[j + 1] = fmaf(xv[j + 1], a1, gb.w - mean * a1);
+                                }
+                                dst[(size_t)(gcb * geo.B + b0) * HW + ri[0].px] = pack8t<FMT>(xv);
                             }
                         }
-                }
+                    }
+                } else {
+                const int pm = (MT == 1 && G == 1 && !is_final) ? 2 : 1;   // partial columns per group in rowstat
+                const int GS = G * pm;
+                // pass 1: per-row (sum, sumsq) per group
+                {
+                    float run_sx = 0.f, run_sq = 0.f;
+                    for_chunks([&](int k, int c, auto tag) {
+                        constexpr int CW = decltype(tag)::value;
+                        uint32_t u[CW];
+                        const uint32_t ta = tlane + (uint32_t)(acc_col + tile_of(k) * C + c);
+                        if constexpr (CW == 16) tmem_ld16_issue(ta, u); else tmem_ld8_issue(ta, u);
+                        tmem_ld_wait();
+                        float2* rs = rowstat + (size_t)(tile_of(k) * 128 + r) * GS;
+                        const bool valid = ri[k].valid;
+                        if (cpg == 4) {
 #pragma unroll
-                for (int t = 0; t < MT; ++t) {
-                    const bool valid = ri[t].valid;
-                    const int b = b0 + ri[t].s;
-                    if (pn_g >= 0) rowstat[(size_t)(t * 128 + r)] = valid ? make_float2(psx[t], psq[t]) : make_float2(0.f, 0.f);
-                    if (is_final && valid) {
-                        // ---- final_conv bias + RK4 / Euler / CFG stage update (sampling.py:43-48,69-74)
+                            for (int q = 0; q < CW / 4; ++q) {
+                                float sx = 0.f, sq = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { const float xv = __uint_as_float(u[q * 4 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
+                                rs[(c >> 2) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                            }
+                        } else if (cpg == 8) {
+#pragma unroll
+                            for (int q = 0; q < CW / 8; ++q) {
+                                float sx = 0.f, sq = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { const float xv = __uint_as_float(u[q * 8 + j]); sx += xv; sq = fmaf(xv, xv, sq); }
+                                rs[(c >> 3) + q] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                            }
+                        } else {
+                            float sx0 = 0.f, sq0 = 0.f, sx1 = 0.f, sq1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < CW; j += 2) {
+                                const float xa = __uint_as_float(u[j]), xb = __uint_as_float(u[j + 1]);
+                                sx0 += xa; sq0 = fmaf(xa, xa, sq0); sx1 += xb; sq1 = fmaf(xb, xb, sq1);
+                            }
+                            run_sx += sx0 + sx1; run_sq += sq0 + sq1;
+                            if (((c + CW) & (cpg - 1)) == 0 || c + CW == cend) {
+                                rs[pm == 2 ? wg : (c >> lg_cpg)] = valid ? make_float2(run_sx, run_sq) : make_float2(0.f, 0.f);
+                                run_sx = 0.f; run_sq = 0.f;
+                            }
+                        }
+                    });
+                }
+                if (dbg && et == 0) dbg[i * 8 + 3] = clock64();
+                stats_to_coef(geo, MT * 128, rowstat, coef, gpar, G, pm, C, HW, true, et);
+                if (dbg && et == 0) dbg[i * 8 + 4] = clock64();
+                // pass 2: y = x*scale + offset, SiLU, + residual, write
+                for_chunks([&](int k, int c, auto tag) {
+                    constexpr int CW = decltype(tag)::value;
+                    uint32_t av[CW], rv[CW];
+                    const int t = tile_of(k);
+                    if constexpr (CW == 16) {
+                        tmem_ld16_issue(tlane + (uint32_t)(acc_col + t * C + c), av);
+                        if (res_mode == 1) tmem_ld16_issue(tlane + (uint32_t)(res_col + t * C + c), rv);
+                    } else {
+                        tmem_ld8_issue(tlane + (uint32_t)(acc_col + t * C + c), av);
+                        if (res_mode == 1) tmem_ld8_issue(tlane + (uint32_t)(res_col + t * C + c), rv);
+                    }
+                    tmem_ld_wait();
+                    if (!ri[k].valid) return;
+                    float rr[CW];
+                    if (res_mode == 2) {
+                        const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + c) >> 3) * plane_bytes + (uint32_t)ri[k].pp * 16u;
+#pragma unroll
+                        for (int hb = 0; hb < CW / 8; ++hb) unpack8t<FMT>(*reinterpret_cast<const uint4*>(src + hb * plane_bytes), rr + hb * 8);
+                    } else if (res_mode == 1) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) rr[j] = __uint_as_float(rv[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) rr[j] = 0.f;
+                    }
+                    const float4* cf = reinterpret_cast<const float4*>(coef + ri[k].s * C + c);
+                    float v[CW];
+                    float sxa = 0.f, sqa = 0.f, sxb = 0.f, sqb = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CW; j += 2) {
+                        const float4 ab = cf[j >> 1];
+                        float ya = fmaf(__uint_as_float(av[j]), ab.x, ab.y);
+                        float yb = fmaf(__uint_as_float(av[j + 1]), ab.z, ab.w);
+                        ya = fast_silu(ya); yb = fast_silu(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
+                        ya += rr[j]; yb += rr[j + 1];
+                        v[j] = ya; v[j + 1] = yb;
+                        sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);
+                    }
+                    psx[k] += sxa + sxb; psq[k] += sqa + sqb;
+                    if (is_final) {
                         const int nch = p.channels, dim = p.dim;
-                        const size_t plane = (size_t)geo.B * nch * HW;
 #pragma unroll
                         for (int co = 0; co < FINAL_MAX_CH; ++co) {
-                            if (co >= nch) continue;
-                            float k = kacc[t][co] + cpar[nch * dim + co];
-                            const size_t o = ((size_t)b * nch + co) * HW + ri[t].px;
-                            // prefetched operands on the common (channels <= 4) path, direct loads otherwise
-                            const bool pre = fast_final;
-                            if (sg.flags & SF_CFG_COMBINE) k = __fadd_rn(k, __fmul_rn(cfg_s, __fsub_rn(pre ? fc[t][co & 3] : VC[o], k)));
-                            if (VT && sg.eval_idx >= 0) VT[(size_t)sg.eval_idx * plane + o] = k;
-                            switch (sg.kind) {
-                                case ST_PLAIN: VOUT[o] = k; break;
-                                case ST_CFG_COND: VC[o] = k; break;
-                                case ST_RK1:
-                                    ACC[o] = k;
-                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
-                                    break;
-                                case ST_RK2:
-                                    ACC[o] = __fadd_rn(pre ? fa[t][co & 3] : ACC[o], __fmul_rn(2.0f, k));
-                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(__fmul_rn(sg.dt, k), 0.5f));
-                                    break;
-                                case ST_RK3:
-                                    ACC[o] = __fadd_rn(pre ? fa[t][co & 3] : ACC[o], __fmul_rn(2.0f, k));
-                                    XS[o] = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(sg.dt, k));
-                                    break;
-                                case ST_RK4: {
-                                    const float yn = __fadd_rn(pre ? fy[t][co & 3] : Y[o],
-                                                               __fmul_rn(sg.dt6, __fadd_rn(pre ? fa[t][co & 3] : ACC[o], k)));
-                                    Y[o] = yn; XS[o] = yn;
-                                } break;
-                                case ST_EULER: {
-                                    const float yn = __fadd_rn(pre ? fy[t][co & 3] : Y[o], __fmul_rn(k, sg.dt));
-                                    Y[o] = yn; XS[o] = yn;
-                                } break;
-                                default: break;
+                            if (co < nch) {
+                                float a = kacc[k][co];
+#pragma unroll
+                                for (int j = 0; j < CW; ++j) a = fmaf(v[j], cpar[co * dim + c + j], a);
+                                kacc[k][co] = a;
                             }
                         }
+                    } else {
+#pragma unroll
+                        for (int hb = 0; hb < CW / 8; ++hb) write8(ri[k], ((c0 + c) >> 3) + hb, v + hb * 8);
                     }
-                }
+                });
                 if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
-                    {
-                        const float* g2 = fblob + p.st[i].pn_gamma_off;
-                        const float* b2 = fblob + p.st[i].pn_beta_off;
-                        float2* gpar = reinterpret_cast<float2*>(cpar + cpar_n);
-                        epi_sync();                                   // everyone is done with the block-norm gpar/coef
-                        for (int c = r; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c0 + c], b2[c0 + c]);
-                    }
-                    stats_to_coef(geo, MT * 128, rowstat, coef, reinterpret_cast<const float2*>(cpar + cpar_n), 1, C, HW, false, r, &xc);
-                    uint4* dst = reinterpret_cast<uint4*>(gt[pn_g]);
-                    const int out_slot = od.slot_off;
+                    const int pm2 = (MT == 1) ? 2 : 1;
+                    const float* g2 = fblob + p.st[i].pn_gamma_off;
+                    const float* b2 = fblob + p.st[i].pn_beta_off;
+                    // (rowstat and gpar were last read before the final barrier of the block-norm stats_to_coef; coef is
+                    // rewritten only behind the first barrier of the next one, which every thread reaches after its pass 2)
 #pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        if (!ri[t].valid) continue;
-                        const int b = b0 + ri[t].s;
-                        const float2* cf = coef + ri[t].s * C;
-                        for (int cb = 0; cb < (C >> 3); ++cb) {
-                            const int gcb = (c0 >> 3) + cb;
+                    for (int k = 0; k < TW; ++k) {
+                        if (MT > 1 && wg + 2 * k >= MT) continue;
+                        const int t = tile_of(k);
+                        rowstat[(size_t)(t * 128 + r) * pm2 + (pm2 == 2 ? wg : 0)] = ri[k].valid ? make_float2(psx[k], psq[k]) : make_float2(0.f, 0.f);
+                    }
+                    for (int c = et; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c0 + c], b2[c0 + c]);
+                    stats_to_coef(geo, MT * 128, rowstat, coef, gpar, 1, pm2, C, HW, false, et, &xc);
+                    uint4* dst = reinterpret_cast<uint4*>(p.gt[pn_g]);
+                    for_chunks([&](int k, int c, auto tag) {
+                        constexpr int CW = decltype(tag)::value;
+                        if (!ri[k].valid) return;
+                        const int b = b0 + ri[k].s;
+                        const float4* cf = reinterpret_cast<const float4*>(coef + ri[k].s * C + c);
+#pragma unroll
+                        for (int hb = 0; hb < CW / 8; ++hb) {
+                            const int gcb = ((c0 + c) >> 3) + hb;
                             float xv[8];
-                            unpack8(*reinterpret_cast<const uint4*>(smem + out_slot + (uint32_t)gcb * plane_bytes + (uint32_t)ri[t].pp * 16u), xv, fmt);
+                            unpack8t<FMT>(*reinterpret_cast<const uint4*>(smem + out_slot_off + (uint32_t)gcb * plane_bytes + (uint32_t)ri[k].pp * 16u), xv);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) { const float2 ab = cf[cb * 8 + j]; xv[j] = fmaf(xv[j], ab.x, ab.y); }
-                            dst[(size_t)(gcb * geo.B + b) * HW + ri[t].px] = pack8(xv, fmt);
+                            for (int j = 0; j < 8; j += 2) {
+                                const float4 ab = cf[hb * 4 + (j >> 1)];
+                                xv[j] = fmaf(xv[j], ab.x, ab.y); xv[j + 1] = fmaf(xv[j + 1], ab.z, ab.w);
+                            }
+                            dst[(size_t)(gcb * geo.B + b) * HW + ri[k].px] = pack8t<FMT>(xv);
                         }
-                    }
+                    });
                 }
+                }
+                if (is_final && cend > cbeg) final_update(kacc);
                 if (is_final) {
                     // the last CTA to finish advances the stage counter (every CTA has read ctrl->step by now)
                     epi_sync();
-                    if (r == 0) {
+                    if (et == 0) {
                         __threadfence();
                         const int done = atomicAdd(&ctrl->done_ctr, 1);
                         if (done == (int)gridDim.x - 1) {
@@ -781,12 +1000,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
                     }
                 }
             }
-            if (dbg && r == 0) dbg[i * 8 + 5] = clock64();
+            if (dbg && et == 0) dbg[i * 8 + 5] = clock64();
             tc_fence_before();
             if (SPLIT) {
                 fence_proxy_async_all();     // local and remote shared-memory results -> visible to every CTA's next tcgen05.mma
                 epi_sync();                  // every thread's stores are ordered before the elected thread's release-arrives
-                if (r == 0)
+                if (et == 0)
                     for (int q = 0; q < Q; ++q) mbar_arrive_cluster(mapa_shared(bar_epi, (uint32_t)q));
             } else {
                 fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
@@ -799,16 +1018,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? 2 : 1) k_chain(cons
     if (Q > 1) cluster_sync_all();       // no CTA may exit while a peer can still store into its shared memory
     if (dbg && tid == 0) dbg[CH_MAX_STEPS * 8 + 1] = clock64();
     if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
-    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 cudaError_t attn_configure();
+template <int MT, bool SPLIT, bool FAST>
+static cudaError_t chain_attr() {
+    cudaError_t e = cudaFuncSetAttribute(k_chain<MT, SPLIT, 0, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<MT, SPLIT, 1, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
+}
 cudaError_t fused_configure() {
-    cudaError_t e = cudaFuncSetAttribute(k_chain<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = chain_attr<1, false, false>();
+    if (e == cudaSuccess) e = chain_attr<1, true, false>();
+    if (e == cudaSuccess) e = chain_attr<2, false, false>();
+    if (e == cudaSuccess) e = chain_attr<3, false, false>();
+    if (e == cudaSuccess) e = chain_attr<4, false, false>();
+    if (e == cudaSuccess) e = chain_attr<1, false, true>();
+    if (e == cudaSuccess) e = chain_attr<2, false, true>();
     if (e != cudaSuccess) return e;
     return attn_configure();
 }
@@ -848,20 +1075,28 @@ int fused_max_active_clusters(int nsplit, int smem_bytes) {
     at[0].val.clusterDim.x = (unsigned)nsplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k_chain<1, true>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k_chain<1, true, 1, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
     return n;
 }
 
-cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
-    const void* fn;
-    switch (p.n_mtiles) {
-        case 1: fn = p.nsplit > 1 ? (const void*)k_chain<1, true> : (const void*)k_chain<1, false>; break;
-        case 2: fn = (const void*)k_chain<2, false>; break;
-        case 3: fn = (const void*)k_chain<3, false>; break;
-        case 4: fn = (const void*)k_chain<4, false>; break;
-        default: return cudaErrorInvalidValue;
+template <int FMT>
+static const void* chain_fn(int mt, bool split, bool fast) {
+    if (fast) {
+        if (split || mt > 2) return nullptr;
+        return mt == 1 ? (const void*)k_chain<1, false, FMT, true> : (const void*)k_chain<2, false, FMT, true>;
     }
+    switch (mt) {
+        case 1: return split ? (const void*)k_chain<1, true, FMT, false> : (const void*)k_chain<1, false, FMT, false>;
+        case 2: return (const void*)k_chain<2, false, FMT, false>;
+        case 3: return (const void*)k_chain<3, false, FMT, false>;
+        case 4: return (const void*)k_chain<4, false, FMT, false>;
+        default: return nullptr;
+    }
+}
+cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
     if (p.nsplit > 1 && p.n_mtiles != 1) return cudaErrorInvalidValue;
+    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0) : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0);
+    if (!fn) return cudaErrorInvalidValue;
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
     return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);
 }

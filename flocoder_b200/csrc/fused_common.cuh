@@ -6,8 +6,10 @@
 
 namespace flo {
 
-constexpr int FUSED_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+// k_chain: 8 epilogue warps (two per TMEM lane quadrant) + TMA producer + MMA issuer
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int FUSED_THREADS = EPI_THREADS + 64;
 
 // ------------------------------------------------------------------------------------------------
 // 16-bit helpers (fmt: 1 = bf16, 0 = fp16)
@@ -30,6 +32,35 @@ __device__ __forceinline__ uint4 pack8(const float* v, int fmt) {
 __device__ __forceinline__ void unpack8(uint4 u, float* v, int fmt) {
     float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt), c = unpack2(u.z, fmt), d = unpack2(u.w, fmt);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+// compile-time format variants (k_chain is templated on the operand format: no per-element format branches)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2t(float a, float b) {
+    if constexpr (FMT != 0) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+template <int FMT>
+__device__ __forceinline__ uint4 pack8t(const float* v) {
+    return make_uint4(pack2t<FMT>(v[0], v[1]), pack2t<FMT>(v[2], v[3]), pack2t<FMT>(v[4], v[5]), pack2t<FMT>(v[6], v[7]));
+}
+template <int FMT>
+__device__ __forceinline__ void unpack8t(uint4 u, float* v) {
+    if constexpr (FMT != 0) {
+        // bf16 -> fp32 is a 16-bit shift: two integer ops per pair
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+        v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+        v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x)), b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+        const float2 c = __half22float2(*reinterpret_cast<__half2*>(&u.z)), d = __half22float2(*reinterpret_cast<__half2*>(&u.w));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
 }
 constexpr int ATTN_MAX_THREADS = 320;   // k_attn with 8 epilogue warps
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, EPI_THREADS); }

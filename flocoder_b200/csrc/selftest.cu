@@ -239,11 +239,14 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
         const int Ns[4] = {16, 32, 64, 128}, counts[4] = {1, 8, 32, 128};
         // acc -1: two issuing warps, one accumulator each; 1: one issuer.  Then, one issuer: A start one pixel (16 bytes)
         // and one padded row + pixel (16*19 bytes) off the line, as the 3x3 tap descriptors are; and A read from TMEM.
-        const int modes[5][3] = {{-1, 0, 0}, {1, 0, 0}, {1, 0, 16}, {1, 0, 16 * 19}, {1, 1, 0}};
-        for (int m = 0; m < 5; ++m)
+        // {accumulators, a_mode, a_shift}: a_mode 0 = A in shared memory (contiguous row groups), 1 = A in tensor memory,
+        // >= 2 = A in shared memory with row groups a_mode*16 bytes apart (18: padded 16-pixel rows; 24: rows padded to 384 B; 10: 8-pixel rows)
+        const int modes[12][3] = {{-1, 0, 0}, {1, 0, 0}, {1, 0, 16}, {1, 0, 16 * 19}, {1, 1, 0}, {1, 18, 0}, {1, 18, 16}, {1, 18, 32},
+                                  {1, 24, 0}, {1, 24, 16}, {1, 10, 0}, {1, 10, 16}};
+        for (int m = 0; m < 12; ++m)
             for (int ni = 0; ni < 4; ++ni) {
                 char buf[320]; int o = snprintf(buf, sizeof(buf), "INFO umma_rate N=%-3d acc=%d a=%s shift=%d :", Ns[ni], modes[m][0],
-                                                modes[m][1] ? "tmem" : "smem", modes[m][2]);
+                                                modes[m][1] == 1 ? "tmem" : (modes[m][1] == 0 ? "smem" : (modes[m][1] == 18 ? "smem/sbo288" : (modes[m][1] == 24 ? "smem/sbo384" : "smem/sbo160"))), modes[m][2]);
                 for (int ci = 0; ci < 4; ++ci) {
                     ST_CUDA(launch_umma_rate(dc, Ns[ni], counts[ci], modes[m][0], st, modes[m][1], modes[m][2]));
                     ST_CUDA(cudaStreamSynchronize(st));
