@@ -7,6 +7,7 @@ path never falls back to PyTorch or to the CPU oracle.
 from __future__ import annotations
 
 import ctypes
+import weakref
 import math
 import os
 from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
@@ -22,7 +23,7 @@ FLO_F32, FLO_BF16, FLO_F16 = 0, 1, 2
 FLO_RK4, FLO_EULER_LEGACY, FLO_EULER_GRID = 0, 1, 2
 FLO_FLAG_NO_BUFFER_REUSE, FLO_FLAG_NO_GRAPH, FLO_FLAG_LAYERWISE = 1, 2, 4
 
-# every symbol include/flocoder_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them)
+# every symbol include/flocoder_b200.h declares (tests/test_cabi.py checks the .so exports them)
 EXPORTS = (
     "flo_version", "flo_last_error", "flo_param_count", "flo_param_info", "flo_unet_create",
     "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
@@ -183,9 +184,26 @@ class Engine:
             pass
 
     # -- calls ---------------------------------------------------------------------------
+    def _check_class_range(self, c: torch.Tensor):
+        """nn.Embedding (class_cond_mlp.0, unet.py:207) raises IndexError for ids outside [0, n_classes); the kernel
+        would clamp them silently.  One min/max per distinct tensor: a trajectory validates its ids once, and the
+        per-evaluation calls of the generic rk4_step path see the cached verdict."""
+        n = int(self.cfg.n_classes)
+        if n <= 0 or c.numel() == 0:
+            return
+        ok = getattr(self, "_cls_ok", None)          # (weak reference to the validated tensor object, its version counter)
+        if ok is not None and ok[0]() is c and ok[1] == c._version:
+            return
+        lo, hi = int(c.min()), int(c.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"class_cond holds ids in [{lo}, {hi}] but the model has n_classes={n} "
+                             "(index out of range in self, as nn.Embedding reports it)")
+        self._cls_ok = (weakref.ref(c), c._version)
+
     def _cls_ptr(self, class_ids, b):
         if class_ids is None:
             return None, None
+        self._check_class_range(class_ids)
         c = class_ids.to(device=self.device, dtype=torch.int64).contiguous().reshape(-1)
         if c.numel() != b:
             raise ValueError(f"class_cond must have {b} elements, got {c.numel()}")
@@ -225,6 +243,7 @@ class Engine:
         ts_arr = (c_float * len(ts))(*[float(t) for t in ts])
         cptr = None
         if class_ids is not None:
+            self._check_class_range(class_ids)
             keep = class_ids.to(device="cpu", dtype=torch.int64).contiguous()
             cptr = keep.data_ptr()
         with torch.cuda.device(self.device):

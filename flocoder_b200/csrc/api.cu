@@ -265,7 +265,18 @@ struct Plan {
     std::vector<ChainParams> fchain;
     std::vector<AttnFusedParams> fattn;
     long long* dbg = nullptr;
+    uint64_t last_use = 0;                  // LRU stamp (Handle::use_ctr)
+    Plan() = default;
+    Plan(const Plan&) = delete;
+    Plan& operator=(const Plan&) = delete;
+    ~Plan() {                               // every exit path of get_plan releases what it has allocated so far
+        if (graph) cudaGraphExecDestroy(graph);
+        if (graph4) cudaGraphExecDestroy(graph4);
+        if (base) cudaFree(base);
+        if (dbg) cudaFree(dbg);
+    }
 };
+constexpr size_t MAX_PLANS = 8;             // per-batch-size plans kept per handle (least recently used one is evicted)
 
 struct Handle {
     Spec spec;
@@ -283,6 +294,9 @@ struct Handle {
     size_t o_freqs, o_w1t, o_b1, o_w2t, o_b2, o_emb = NONE, o_wc1t = NONE, o_bc1 = NONE, o_wc3t = NONE, o_bc3 = NONE,
            o_wft, o_bf, o_init_w, o_init_b, o_final_w, o_final_b;
     std::map<int, std::unique_ptr<Plan>> plans;
+    uint64_t use_ctr = 0;
+    cudaStream_t last_stream = nullptr;     // a handle serves one stream at a time: calls on another stream first wait for this one
+    bool has_last_stream = false;
     // stage tables
     Stage* d_stages = nullptr; float* d_stage_t = nullptr; float* d_film_u = nullptr;
     int stage_cap = 0;
@@ -298,6 +312,20 @@ struct Handle {
                                             // split stages still fit the GPU in one wave)
     const std::vector<FStage>& stages(int variant) const { return variant == 0 ? fstages : fstages_alt[variant - 1]; }
     size_t farena_ps = 0;
+    Handle() = default;
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+    ~Handle() {                   // also runs on every early return of flo_unet_create (the handle lives in a unique_ptr there)
+        plans.clear();
+        if (d_f32) cudaFree(d_f32);
+        if (d_bf16) cudaFree(d_bf16);
+        if (d_stages) { cudaFree(d_stages); cudaFree(d_stage_t); cudaFree(d_film_u); }
+        for (int i = 0; i < 4; ++i) {
+            if (h_stages[i]) { cudaFreeHost(h_stages[i]); cudaFreeHost(h_stage_t[i]); }
+            if (h_ev[i]) cudaEventDestroy(h_ev[i]);
+        }
+        if (capture_stream) cudaStreamDestroy(capture_stream);
+    }
 };
 
 // ---- program builder ---------------------------------------------------------------------------
@@ -715,18 +743,29 @@ static int launch_unit(Handle& h, Plan& pl, int i, cudaStream_t st) {
     return h.spec.fused ? launch_fused_stage(h, pl, i, st) : launch_op(h, pl, i, st);
 }
 
-static void destroy_plan(Plan& pl) {
-    if (pl.graph) cudaGraphExecDestroy(pl.graph);
-    if (pl.graph4) cudaGraphExecDestroy(pl.graph4);
-    pl.graph4 = nullptr;
-    if (pl.base) cudaFree(pl.base);
-    pl.graph = nullptr; pl.base = nullptr;
+static void destroy_plan(Plan&) {}          // resources are released by ~Plan when the owning unique_ptr goes away
+
+// One stream at a time per handle (the stage table, the control block and the workspaces are per handle / per plan):
+// a call on a different stream than the previous one first waits for that stream's work.
+static int enter_stream(Handle& h, cudaStream_t st) {
+    if (h.has_last_stream && h.last_stream != st) CUDA_TRY(cudaStreamSynchronize(h.last_stream));
+    h.last_stream = st; h.has_last_stream = true;
+    return FLO_OK;
 }
 
-static int get_plan(Handle& h, int B, Plan** out) {
+static int get_plan(Handle& h, int B, Plan** out, cudaStream_t st) {
     auto it = h.plans.find(B);
-    if (it != h.plans.end()) { *out = it->second.get(); return FLO_OK; }
+    if (it != h.plans.end()) { it->second->last_use = ++h.use_ctr; *out = it->second.get(); return FLO_OK; }
     if (B <= 0) { set_error("batch size must be positive, got %d", B); return FLO_ERR_INVALID; }
+    if (h.plans.size() >= MAX_PLANS) {
+        // ragged last batches / uneven shards would otherwise grow the cache without bound: drop the least recently used plan
+        // (its workspace may still be in use by enqueued work: wait for the device first; plan creation is a slow path anyway)
+        auto lru = h.plans.begin();
+        for (auto jt = h.plans.begin(); jt != h.plans.end(); ++jt)
+            if (jt->second->last_use < lru->second->last_use) lru = jt;
+        CUDA_TRY(cudaDeviceSynchronize());
+        h.plans.erase(lru);
+    }
     const Spec& s = h.spec;
     std::unique_ptr<Plan> pl(new Plan());
     pl->B = B;
@@ -751,8 +790,10 @@ static int get_plan(Handle& h, int B, Plan** out) {
     pl->ctrl = (Ctrl*)q;
     pl->buf_ptr.resize(h.bufs.size());
     for (size_t i = 0; i < h.bufs.size(); ++i) pl->buf_ptr[i] = s.fused ? nullptr : pl->arena + h.bufs[i].off_ps * (size_t)B;
-    // halo / padding rows of the arena are never read as data, but keep everything finite
-    CUDA_TRY(cudaMemset(pl->base, 0, pl->total_bytes));
+    // halo / padding rows of the arena are never read as data, but keep everything finite.  On the CALLER's stream: the
+    // first kernels of this plan are enqueued there right after this call, and a non-blocking stream is not ordered after
+    // the legacy default stream.
+    CUDA_TRY(cudaMemsetAsync(pl->base, 0, pl->total_bytes, st));
 
     const int n_ops = (int)h.ops.size();
     pl->umma.resize(n_ops); pl->tmA0.resize(n_ops); pl->tmA1.resize(n_ops);
@@ -796,6 +837,7 @@ static int get_plan(Handle& h, int B, Plan** out) {
             if (rc || ce != cudaSuccess) { set_error("graph capture (x4) failed"); destroy_plan(*pl); return rc ? rc : FLO_ERR_CUDA; }
         }
     }
+    pl->last_use = ++h.use_ctr;
     *out = pl.get();
     h.plans[B] = std::move(pl);
     return FLO_OK;
@@ -889,16 +931,7 @@ int flo_unet_destroy(flo_unet_t* hh) {
     if (!h) return FLO_OK;
     cudaSetDevice(h->spec.device);
     cudaDeviceSynchronize();
-    for (auto& kv : h->plans) destroy_plan(*kv.second);
-    if (h->d_f32) cudaFree(h->d_f32);
-    if (h->d_bf16) cudaFree(h->d_bf16);
-    if (h->d_stages) { cudaFree(h->d_stages); cudaFree(h->d_stage_t); cudaFree(h->d_film_u); }
-    for (int i = 0; i < 4; ++i) {
-        if (h->h_stages[i]) { cudaFreeHost(h->h_stages[i]); cudaFreeHost(h->h_stage_t[i]); }
-        if (h->h_ev[i]) cudaEventDestroy(h->h_ev[i]);
-    }
-    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
-    delete h;
+    delete h;                     // ~Handle releases the plans, the packed weights, the stage tables and the capture stream
     return FLO_OK;
 }
 
@@ -977,7 +1010,8 @@ size_t flo_workspace_bytes(flo_unet_t* hh, int B) {
     if (!h) return 0;
     cudaSetDevice(h->spec.device);
     Plan* pl = nullptr;
-    if (get_plan(*h, B, &pl)) return 0;
+    if (get_plan(*h, B, &pl, nullptr)) return 0;
+    cudaStreamSynchronize(nullptr);
     return pl->total_bytes;
 }
 
@@ -987,8 +1021,10 @@ int flo_unet_forward(flo_unet_t* hh, const float* x, const float* time, const in
     if (!h || !x || !time || !v) { set_error("NULL argument"); return FLO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(h->spec.device));
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = enter_stream(*h, st);
+    if (rc) return rc;
     Plan* pl = nullptr;
-    int rc = get_plan(*h, B, &pl);
+    rc = get_plan(*h, B, &pl, st);
     if (rc) return rc;
     const Spec& s = h->spec;
     const size_t n = (size_t)B * s.channels * s.H * s.W;
@@ -1127,8 +1163,10 @@ int flo_integrate(flo_unet_t* hh, float* y, const float* ts, int n_ts, int metho
     Handle* h = reinterpret_cast<Handle*>(hh);
     if (!h || !y) { set_error("NULL argument"); return FLO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(h->spec.device));
+    int rc = enter_stream(*h, (cudaStream_t)stream);
+    if (rc) return rc;
     Plan* pl = nullptr;
-    int rc = get_plan(*h, B, &pl);
+    rc = get_plan(*h, B, &pl, (cudaStream_t)stream);
     if (rc) return rc;
     return integrate_impl(h, pl, y, ts, n_ts, method, dt, t_scale, class_ids, cfg_strength, v_trace, (cudaStream_t)stream);
 }
@@ -1139,8 +1177,10 @@ int flo_integrate_host(flo_unet_t* hh, const float* x0, float* x1, const float* 
     if (!h || !x0 || !x1) { set_error("NULL argument"); return FLO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(h->spec.device));
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = enter_stream(*h, st);
+    if (rc) return rc;
     Plan* pl = nullptr;
-    int rc = get_plan(*h, B, &pl);
+    rc = get_plan(*h, B, &pl, st);
     if (rc) return rc;
     const Spec& s = h->spec;
     const size_t bytes = (size_t)B * s.channels * s.H * s.W * sizeof(float);
@@ -1328,8 +1368,9 @@ int flo_unet_op_info(flo_unet_t* hh, int index, int* kind, double* flops_per_sam
                 if (cs.epi == CE_INIT) fl += 2.0 * hw * h->spec.dim * h->spec.channels;
                 if (!cs.has_conv) continue;
                 const double cin = (cs.a0_ncb + cs.a1_ncb) * 8.0;
-                fl += 2.0 * hw * cs.n * cin * cs.ksize * cs.ksize;
-                if (cs.has_res) fl += 2.0 * hw * cs.n * cin;
+                // cs.C = all output channels of the step (cs.n is the per-CTA slice of an N-split stage)
+                fl += 2.0 * hw * cs.C * cin * cs.ksize * cs.ksize;
+                if (cs.has_res) fl += 2.0 * hw * cs.C * cin;
                 if (cs.final) fl += 2.0 * hw * h->spec.dim * h->spec.channels;
             }
             for (int m = 0; m < st.n_maps; ++m) by += tbytes(st.map_tensor[m]);
@@ -1352,8 +1393,10 @@ int flo_unet_profile_ops(flo_unet_t* hh, int B, int reps, float* ms_per_op, void
     if (!h || !ms_per_op || reps < 1) { set_error("bad argument"); return FLO_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(h->spec.device));
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = enter_stream(*h, st);
+    if (rc) return rc;
     Plan* pl = nullptr;
-    int rc = get_plan(*h, B, &pl);
+    rc = get_plan(*h, B, &pl, st);
     if (rc) return rc;
     const int n_ops = n_units(*h);
     rc = ensure_stage_capacity(*h, 1);

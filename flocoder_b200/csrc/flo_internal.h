@@ -201,7 +201,7 @@ void set_error(const char* fmt, ...);
 // GroupNorm/FiLM/SiLU/residual epilogues entirely on-chip (activations in shared memory, accumulators
 // in TMEM, weights streamed by bulk TMA); see DESIGN.md "Fused stage kernels".
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_WSTAGES = 4;          // depth of the shared-memory weight ring
+constexpr int MAX_WSTAGES = 8;          // largest depth of the shared-memory weight ring
 constexpr int CH_MAX_STEPS = 8;
 constexpr int CH_MAX_LOADS = 4;
 constexpr int CH_MAX_GT = 10;
@@ -242,7 +242,7 @@ struct ChainParams {
     int max_c;                              // largest per-step channel count (sizes gpar and the tables of the warp-shuffle GroupNorm path)
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
-    int ring_off, ring_slot_bytes, n_ring;
+    int ring_off, ring_slot_bytes, n_ring, n_ring_deep;   // n_ring_deep: depth when one CTA owns the SM (chosen per plan)
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start
     int wtab_off, n_chunks;                 // weight chunk list (byte offset into wblob, bytes)

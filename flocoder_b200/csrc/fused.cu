@@ -409,8 +409,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
         if (n_loads > 0) mbar_wait(bar_load, 0);
         for (int i = 0; i < n_steps; ++i) {
             if (i > 0) {
+                // epilogue -> MMA hand-off: inside one CTA a named barrier the 256 epilogue threads arrive on (no 256
+                // serialised mbarrier arrivals); across a cluster the mbarrier with cluster-scope release / acquire
                 if (Q > 1) { mbar_wait_cluster(bar_epi, (i - 1) & 1); fence_proxy_async_all(); }
-                else mbar_wait(bar_epi, (i - 1) & 1);
+                else named_bar_sync(2, EPI_THREADS + 32);
             }
             tc_fence_after();
             if (dbg && lane == 0) dbg[i * 8 + 0] = clock64();
@@ -1009,7 +1011,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                     for (int q = 0; q < Q; ++q) mbar_arrive_cluster(mapa_shared(bar_epi, (uint32_t)q));
             } else {
                 fence_proxy_async();      // shared-memory results -> visible to the next step's tcgen05.mma
-                mbar_arrive(bar_epi);
+                if (i + 1 < n_steps) named_bar_arrive(2, EPI_THREADS + 32);
             }
         }
     }

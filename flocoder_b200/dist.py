@@ -55,9 +55,17 @@ def generate_latents_sharded(model, shape, n_steps=50, cond=None, cfg_strength=3
         raise ValueError("sharded sampling needs an explicit `source` so every rank slices the same noise")
     local_src = source[lo:hi].to(p.device)
     local_shape = (hi - lo,) + tuple(shape[1:])
+    # per-sample tensors handed through to the sampler (e.g. init_latents of the img2img branch, sampling.py:104-109)
+    # are sliced like the noise; anything else with a leading batch dimension would be silently mis-shaped
+    local_kwargs = dict(sampler_kwargs)
+    for k, v in sampler_kwargs.items():
+        if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == b:
+            local_kwargs[k] = v[lo:hi]
+        elif torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] != 1:
+            raise ValueError(f"sharded sampling: tensor argument '{k}' has leading dimension {v.shape[0]}, expected the global batch {b}")
     if hi > lo:
         local, nfe = sampler(model, local_shape, n_steps, shard_cond(cond, lo, hi), cfg_strength,
-                             source=local_src, **sampler_kwargs)
+                             source=local_src, **local_kwargs)
     else:
         local, nfe = local_src.clone(), n_steps * 4
     if not gather:

@@ -148,12 +148,9 @@ def generate_latents(model, shape, method="rk4", n_steps=50, cond=None, cfg_stre
 
 
 @torch.no_grad()
-def euler_sampler(model, shape, sample_N, device=None, cond=None, source=None, eps=1e-3):
-    """Legacy fixed-step Euler (``legacy/train_sd_flowers.py:43,50-67``): ``dt = 1/N``,
-    ``t_i = i/N*(1-eps)+eps``, ``x <- x + model(x, t_i*999, cond)*dt``.  Returns ``(x, nfe=N)``.
-
-    ``cond`` and ``source`` are explicit here (the legacy script drew both from globals); like
-    the legacy function the result is returned on the CPU."""
+def euler_latents(model, shape, sample_N, cond=None, source=None, eps=1e-3):
+    """The legacy Euler recurrence with the result left on the model's device (what :func:`euler_sampler` and the
+    sharded / benchmark callers share).  Returns ``(x, nfe=N)``."""
     dev, dtype = _device_dtype(model)
     x = source if source is not None else torch.randn(shape, device=dev, dtype=dtype)
     dt = 1.0 / sample_N
@@ -163,7 +160,7 @@ def euler_sampler(model, shape, sample_N, device=None, cond=None, source=None, e
         for num_t in times:
             t = torch.ones(shape[0], device=x.device, dtype=x.dtype) * num_t
             x = x.detach().clone() + model(x, t * 999, cond) * dt
-        return x.cpu(), sample_N
+        return x, sample_N
     b, c, h, w = x.shape
     eng = model.engine(h, w)
     out_dtype = x.dtype
@@ -172,7 +169,18 @@ def euler_sampler(model, shape, sample_N, device=None, cond=None, source=None, e
     # the legacy loop feeds fl32(num_t) (ones*num_t in fp32) and multiplies the velocity by fl32(dt)
     ts32 = torch.tensor(times, dtype=torch.float64).to(torch.float32).tolist()
     eng.integrate(state, ts32, _lib.FLO_EULER_LEGACY, dt=dt, class_ids=cls, cfg_strength=0.0)
-    return state.to(out_dtype).cpu(), sample_N
+    return state.to(out_dtype), sample_N
+
+
+@torch.no_grad()
+def euler_sampler(model, shape, sample_N, device=None, cond=None, source=None, eps=1e-3):
+    """Legacy fixed-step Euler (``legacy/train_sd_flowers.py:43,50-67``): ``dt = 1/N``,
+    ``t_i = i/N*(1-eps)+eps``, ``x <- x + model(x, t_i*999, cond)*dt``.  Returns ``(x, nfe=N)``.
+
+    ``cond`` and ``source`` are explicit here (the legacy script drew both from globals); like
+    the legacy function the result is returned on the CPU."""
+    x, nfe = euler_latents(model, shape, sample_N, cond=cond, source=source, eps=eps)
+    return x.cpu(), nfe
 
 
 # --------------------------------------------------------------------------------------------------

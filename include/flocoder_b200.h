@@ -14,7 +14,14 @@
  * host synchronisation, and return FLO_OK (0) or a negative flo_status; the message for the
  * last failure on the calling thread is flo_last_error().  There is no CPU fallback.
  *
- * A handle is bound to one device and is not re-entrant (one in-flight call per handle).
+ * A handle is bound to one device and is not re-entrant: its stage table, control block and per-batch
+ * workspaces are shared by all calls, so it serves ONE stream and ONE host thread at a time.  A call on a
+ * different stream than the previous call first waits (cudaStreamSynchronize) for the previous stream, so
+ * switching streams is safe but serialises; concurrent calls from two host threads are not supported --
+ * create one handle per stream / thread (weights are ~5 MB).  At most 8 per-batch-size plans (workspace +
+ * CUDA graphs) are cached per handle; the least recently used one is released when a ninth size arrives.
+ * class_ids must lie in [0, n_classes): the kernels clamp out-of-range ids instead of faulting, and the
+ * Python boundary raises IndexError for them as nn.Embedding does (unet.py:207).
  */
 #ifndef FLOCODER_B200_H
 #define FLOCODER_B200_H
@@ -136,7 +143,9 @@ FLO_API int flo_describe_plan(const flo_unet_cfg* cfg, int B, char* out, int cap
 FLO_API int flo_unet_num_ops(flo_unet_t* h);
 FLO_API int flo_unet_op_name(flo_unet_t* h, int index, char* name, int name_cap);
 /* Per-op metadata: kind (0 init conv, 1 conv, 2 GroupNorm pass, 3 linear attention, 4 mid attention,
- * 5 final conv + integrator epilogue), ALGORITHMIC flops and bytes per sample. */
+ * 5 final conv + integrator epilogue, 6 fused conv-chain stage, 7 fused attention stage), ALGORITHMIC conv
+ * flops (2*M*N*K over real pixels / channels, all output channels of an N-split stage; the sum over the
+ * ops of one forward is SURVEY.md 8d's 66,846,720 for the BASELINE U-Net) and bytes per sample. */
 FLO_API int flo_unet_op_info(flo_unet_t* h, int index, int* kind, double* flops_per_sample, double* bytes_per_sample);
 /* Runs one forward at batch B op by op (no graph) `reps` times with a CUDA event around every kernel on
  * `stream` and returns the best duration of each op in milliseconds (ms_per_op: HOST array, one per op). */

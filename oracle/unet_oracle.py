@@ -11,7 +11,7 @@ the CUDA path stores bf16.  Each helper cites the reference lines it follows
 Precision policies
 ------------------
 ``FP32``          plain fp32/fp64 arithmetic: must equal the imported reference
-                  to rounding noise (tests/test_oracle_vs_reference.py).
+                  to rounding noise (tests/test_oracle.py).
 ``BF16_MATCHED``  the same arithmetic with the operands of every tensor-core
                   convolution (all 3x3/1x1 convs except ``init_conv`` and
                   ``final_conv``) rounded to bf16, fp32 accumulation, and q/k/v
