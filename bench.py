@@ -248,7 +248,16 @@ class Runner:
             self.model.engine_flags = _lib.FLO_FLAG_LAYERWISE
         self.eng = self.model.engine(LATENT[1], LATENT[2])
         n = cfg["n_steps"]
-        if cfg["method"] == "rk4":
+        self.cfg_strength = float(getattr(args, "cfg", 0.0) or 0.0)
+        if self.cfg_strength and cfg["method"] == "rk4" and cfg["n_classes"] > 0 and cfg["scaling"] == "weak":
+            # class-conditional sampling with classifier-free guidance (sampling.py:69-74): class_cond = arange(B) % n_classes,
+            # two U-Net evaluations per stage (SURVEY 8d's optional variant)
+            cg = self.cfg_strength
+            ncls = cfg["n_classes"]
+            one = lambda shape, src: sampling.generate_latents_rk4(                                                    # noqa: E731
+                self.model, shape, n_steps=n, cond={"class_cond": (torch.arange(shape[0], device=dev) % ncls)}, cfg_strength=cg, source=src)
+            shard_fn = sampling.generate_latents_rk4
+        elif cfg["method"] == "rk4":
             one = lambda shape, src: sampling.generate_latents_rk4(self.model, shape, n_steps=n, source=src)          # noqa: E731
             shard_fn = sampling.generate_latents_rk4
         else:
@@ -312,7 +321,7 @@ def run_gpu_arm(args):
     cfg = CONFIGS[args.config]
     main = Runner(cfg, args, world, rank, dev, batch_override=args.batch)
     eng, B = main.eng, main.local_batch
-    NFE = nfe_of(cfg)
+    NFE = nfe_of(cfg) * (2 if main.cfg_strength else 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -364,7 +373,7 @@ def run_gpu_arm(args):
 
     # ---- the other BASELINE configurations this run can afford (every rank takes part: they are collective)
     others = {}
-    if args.config == "c2" and not args.no_other:
+    if args.config == "c2" and not args.no_other and not args.cfg:
         extra = []
         if world == 1:
             extra.append(("c3", "c3"))
@@ -484,7 +493,8 @@ def run_gpu_arm(args):
         "metric": metric_of(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.dtype], "data": "synthetic",
-        "config": dict(workload_config(cfg, world, main.global_batch, args.dtype), name=args.config,
+        "config": dict(workload_config(cfg, world, main.global_batch, args.dtype), name=args.config, cfg_strength=main.cfg_strength,
+                       evaluations_per_stage=2 if main.cfg_strength else 1,
                        kernels="layerwise" if args.layerwise else "fused-stage", step_ms=step_ms),
         "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
                    "samples": clk.get("samples", 0)},
@@ -590,6 +600,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override: per-GPU batch (weak configs) / global batch (strong configs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity / torch_eager_cuda legs")
     ap.add_argument("--no-other", action="store_true", help="skip the other_configs sub-records")
+    ap.add_argument("--cfg", type=float, default=0.0,
+                    help="class-conditional sampling with this classifier-free-guidance strength (weak RK4 configs: 2 evaluations per stage)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -267,6 +267,7 @@ struct AttnFusedParams {
     int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
                                             // n_mtiles = 128-row tiles of the dense rows (s*n + p)
     int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)
+    int hc, hsplit;                         // heads per CTA (4, or 2 with the head split) and CTAs per sample (cluster size 1 / 2)
     int fmt;
     unsigned wq_off, wk_off, wv_off, wo_off; // 16-bit weight streams in wblob (N = 128,128,128,C)
     int qkv_chunks, qkv_S, o_chunks, o_S;   // ring chunking of those streams

@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                             const float4 ab = gc[j >> 1];
                             float ya = fmaf(y[j], ab.x, ab.y);
                             float yb = fmaf(y[j + 1], ab.z, ab.w);
-                            ya = fast_silu(ya); yb = fast_silu(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
+                            ya = fast_silu_t<FMT>(ya); yb = fast_silu_t<FMT>(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
                             ya += rr[j]; yb += rr[j + 1];
                             y[j] = ya; y[j + 1] = yb;
                             sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);
@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                         const float4 ab = cf[j >> 1];
                         float ya = fmaf(__uint_as_float(av[j]), ab.x, ab.y);
                         float yb = fmaf(__uint_as_float(av[j + 1]), ab.z, ab.w);
-                        ya = fast_silu(ya); yb = fast_silu(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
+                        ya = fast_silu_t<FMT>(ya); yb = fast_silu_t<FMT>(yb);          // every GroupNorm step of the U-Net is followed by SiLU (unet.py:67)
                         ya += rr[j]; yb += rr[j + 1];
                         v[j] = ya; v[j + 1] = yb;
                         sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);

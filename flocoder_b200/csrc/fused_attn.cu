@@ -30,23 +30,25 @@ constexpr int ATTN_RING = 4;       // weight ring depth of k_attn (the planner s
 
 // weight chunk g of the stage: K, V, Q projections (qkv_chunks each), then to_out (o_chunks)
 __device__ __forceinline__ void attn_issue_chunk(const AttnFusedParams& p, uint32_t smem_base, uint32_t bar_full, uint32_t bar_empty,
-                                                 int g, int qkv_bytes, int o_bytes) {
+                                                 int g, int qkv_bytes, int o_bytes, int wo_rank_elems) {
     const int qc = p.qkv_chunks;
     const uint16_t* w; int ci, bytes;
     if (g < qc) { w = p.wblob + p.wk_off; ci = g; bytes = qkv_bytes; }
     else if (g < 2 * qc) { w = p.wblob + p.wv_off; ci = g - qc; bytes = qkv_bytes; }
     else if (g < 3 * qc) { w = p.wblob + p.wq_off; ci = g - 2 * qc; bytes = qkv_bytes; }
-    else { w = p.wblob + p.wo_off; ci = g - 3 * qc; bytes = o_bytes; }
+    else { w = p.wblob + p.wo_off + wo_rank_elems; ci = g - 3 * qc; bytes = o_bytes; }   // head split: this CTA's K slices of to_out
     const int slot = g & (ATTN_RING - 1);
     if (g >= ATTN_RING) mbar_wait(bar_empty + 8 * slot, ((g / ATTN_RING) - 1) & 1);
     mbar_expect_tx(bar_full + 8 * slot, (uint32_t)bytes);
     bulk_load_1d(smem_base + p.ring_off + slot * p.ring_slot_bytes, reinterpret_cast<const uint8_t*>(w) + (size_t)ci * bytes,
                  (uint32_t)bytes, bar_full + 8 * slot);
 }
-// 1x1 conv over a K-major operand slot: A rows = tile t rows [128t, 128t+128), planes at `a_plane` stride
+// 1x1 conv over a K-major operand slot: A rows = tile t rows [128t, 128t+128), planes at `a_plane` stride.
+// The weight stream holds tiles of `n_tile` output channels per K16 slice; the MMA uses `n` of them starting at byte
+// offset `b_off` inside the tile (head split: a CTA's 64 of the 128 q/k/v channels), so only descriptors change.
 __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t smem_base, uint32_t tmem_base, uint32_t bar_full,
-                                          uint32_t bar_empty, RingA& rs, uint32_t a_off, uint32_t a_plane, int n, int col,
-                                          int n_chunks, int S) {
+                                          uint32_t bar_empty, RingA& rs, uint32_t a_off, uint32_t a_plane, int n, int n_tile,
+                                          uint32_t b_off, int col, int n_chunks, int S) {
     const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
     const int n_mtiles = p.n_mtiles;
     const uint32_t ring_off = p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
@@ -54,13 +56,13 @@ __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t sme
     const uint32_t hi = (128u >> 4) | (1u << 14);                                       // SBO = 128 B, descriptor version 1
     const uint32_t a_lo0 = (((smem_base + a_off) >> 4) & 0x3FFFu) | (((a_plane >> 4) & 0x3FFFu) << 16);
     const uint32_t a_step = (2u * a_plane) >> 4;                                         // two channel-block planes per K16 slice
-    const uint32_t b_lbo = (((uint32_t)n * 16u >> 4) & 0x3FFFu) << 16, b_step = (uint32_t)n * 32u >> 4;
+    const uint32_t b_lbo = (((uint32_t)n_tile * 16u >> 4) & 0x3FFFu) << 16, b_step = (uint32_t)n_tile * 32u >> 4;
     for (int ci = 0; ci < n_chunks; ++ci) {
         const int slot = rs.cc & (ATTN_RING - 1);
         mbar_wait(bar_full + 8 * slot, (rs.cc / ATTN_RING) & 1);
         tc_fence_after();
         if (elect_one()) {
-            uint32_t b_lo = (((smem_base + ring_off + slot * ring_slot_bytes) >> 4) & 0x3FFFu) | b_lbo;
+            uint32_t b_lo = (((smem_base + ring_off + slot * ring_slot_bytes + b_off) >> 4) & 0x3FFFu) | b_lbo;
             uint32_t a_lo = a_lo0 + (uint32_t)(ci * S) * a_step;
             for (int s = 0; s < S; ++s) {
                 const uint64_t bdesc = desc64(b_lo, hi);
@@ -133,6 +135,8 @@ __device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
     return chan;
 }
 
+// HC: heads per CTA (4; 2 = the head split), a template parameter so that the channel loops keep compile-time bounds
+template <int HC>
 __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -149,7 +153,15 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     const uint32_t bar_epi = bar_mma + 8;
     const uint32_t tmem_slot = bar_epi + 8;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
-    const int b0 = blockIdx.x * p.nb;
+    // Head split (p.hsplit == 2, 16x16 level): the two CTAs of a cluster own the same sample and two of the four heads each
+    // (64 of the 128 q/k/v channels): half the shared memory and tensor memory per CTA, so two CTAs share an SM, and every
+    // phase is half as long.  Nothing crosses the CTAs until the to_out projection, whose two K halves are added through
+    // distributed shared memory in the last epilogue (CTA r finalises pixel tile r).
+    constexpr int NCH = HC * 32;
+    const int HS = HC == 4 ? 1 : 2;
+    const uint32_t hrank = HS > 1 ? cluster_ctarank() : 0u;
+    const int b0 = (HS > 1 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * p.nb;
+    const uint32_t bar_r = tmem_slot + 8, bar_d = bar_r + 8, bar_s = bar_d + 8;      // head split: one-shot cluster hand-offs
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
     const int n = p.n, n_pad = p.n_pad, C = p.C;
     const uint32_t plane = (uint32_t)p.plane_bytes;
@@ -162,6 +174,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         mbar_init(bar_epi, n_epi);
+        mbar_init(bar_r, 1); mbar_init(bar_d, 4); mbar_init(bar_s, 8);     // head split (see the last epilogue)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == w_mma) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -169,7 +182,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    if (HS > 1) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
@@ -180,11 +194,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     if (warp == w_prod) {
         if (lane == 0) {
             const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(ATTN_RING, total);
-            for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
+            const int wo_rank = (int)hrank * (NCH / 16) * C * 16;          // elements: this CTA's K16 slices of the to_out stream
+            for (int g = 0; g < pre; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, wo_rank);
             griddep_wait();          // weights are constants; the activations come from the previous kernel
             mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * xh_plane);
             tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
-            for (int g = pre; g < total; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes);
+            for (int g = pre; g < total; ++g) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, wo_rank);
         }
     } else if (warp == w_mma) {
         {   // whole warp, warp-uniform; one elected lane issues the tcgen05 instructions
@@ -193,9 +208,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             tc_fence_after();
             if (dbg && lane == 0) dbg[0] = clock64();
             // ---- phase 0: K and V convolutions (and Q for the mid attention)
-            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_k, p.qkv_chunks, p.qkv_S);
-            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_v, p.qkv_chunks, p.qkv_S);
-            if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+            const uint32_t wb_off = hrank * (uint32_t)NCH * 16u;      // this CTA's channels inside every 128-channel weight tile
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_k, p.qkv_chunks, p.qkv_S);
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_v, p.qkv_chunks, p.qkv_S);
+            if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_q, p.qkv_chunks, p.qkv_S);
             if (dbg && lane == 0) dbg[1] = clock64();
             if (elect_one()) umma_commit(bar_mma);
             __syncwarp();
@@ -205,7 +221,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 mbar_wait(bar_epi, ph & 1); ++ph;
                 tc_fence_after();
                 if (dbg && lane == 0) dbg[8] = clock64();
-                const uint32_t idesc_ctx = make_idesc16(128, 144, p.fmt, 1, 1);
+                // M = 128 channel rows are always read (with two heads per CTA rows 64..127 are whatever follows the P slot:
+                // their accumulator lanes are never loaded), N = this CTA's (h, e) channels + the ones block
+                const uint32_t idesc_ctx = make_idesc16(128, NCH + 16, p.fmt, 1, 1);
                 {
                     const int nb = p.nb, col_ctx = p.col_ctx;
                     const uint32_t p_off = p.p_off, v_off = p.v_off;
@@ -213,12 +231,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                         for (int s = 0; s < nb; ++s)
                             for (int ks = 0; ks < n_pad / 16; ++ks) {
                                 const uint32_t roff = (uint32_t)(s * n_pad + ks * 16) * 16u;
-                                umma_bf16(tmem_base + (uint32_t)(col_ctx + s * 144), make_smem_desc(smem_base + p_off + roff, 128u, plane),
+                                umma_bf16(tmem_base + (uint32_t)(col_ctx + s * (NCH + 16)), make_smem_desc(smem_base + p_off + roff, 128u, plane),
                                           make_smem_desc(smem_base + v_off + roff, 128u, plane), idesc_ctx, ks > 0 ? 1u : 0u);
                             }
                     __syncwarp();
                 }
-                attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, 128, p.col_q, p.qkv_chunks, p.qkv_S);
+                attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_q, p.qkv_chunks, p.qkv_S);
                 if (dbg && lane == 0) dbg[9] = clock64();
                 if (elect_one()) umma_commit(bar_mma);
                 __syncwarp();
@@ -233,12 +251,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     if (elect_one()) {
                         for (int s = 0; s < nb; ++s)
                             for (int t = 0; t < mtS; ++t)
-                                for (int h = 0; h < 4; ++h)
+                                for (int h = 0; h < HC; ++h)
                                     for (int k = 0; k < 2; ++k) {
                                         const uint32_t a_addr = smem_base + p_off + (uint32_t)(4 * h + 2 * k) * plane +
                                                                 (uint32_t)(s * n_pad + t * 128) * 16u;
-                                        const uint32_t b_addr = smem_base + ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)k * 1024u;
-                                        umma_bf16(tmem_base + (uint32_t)(col_out + (s * mtS + t) * 128 + h * 32),
+                                        const uint32_t b_addr = smem_base + ct_off + (uint32_t)(s * HC + h) * 2048u + (uint32_t)k * 1024u;
+                                        umma_bf16(tmem_base + (uint32_t)(col_out + (s * mtS + t) * NCH + h * 32),
                                                   make_smem_desc(a_addr, plane, 128u), make_smem_desc(b_addr, 512u, 128u), idesc_out,
                                                   k > 0 ? 1u : 0u);
                                     }
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             mbar_wait(bar_epi, ph & 1); ++ph;
             tc_fence_after();
             if (dbg && lane == 0) dbg[24] = clock64();
-            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, p.col_proj,
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, C, 0u, p.col_proj,
                       p.o_chunks, p.o_S);
             if (elect_one()) umma_commit(bar_mma);
             __syncwarp();
@@ -291,10 +309,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
-                for (int c32 = 0; c32 < 128; c32 += 32) {
+                for (int c32 = 0; c32 < NCH; c32 += 32) {
                     uint32_t ua[16], ub[16];
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c32), ua);
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c32 + 16), ub);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c32), ua);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c32 + 16), ub);
                     tmem_ld_wait();
                     float va[16], vb[16];
 #pragma unroll
@@ -342,6 +360,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int wps = n >> 5;                      // warp-rows per sample
                 for (int idx = et; idx < p.nb * 128; idx += n_epi) {
                     const int s = idx >> 7, c = idx & 127;
+                    if (c >= NCH) continue;
                     float m = -INFINITY;
                     for (int w = 0; w < wps; ++w) m = fmaxf(m, kpart[(s * wps + w) * 128 + c]);
                     kmax[idx] = m;
@@ -352,10 +371,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
-                for (int c16 = 0; c16 < 128; c16 += 16) {
+                for (int c16 = 0; c16 < NCH; c16 += 16) {
                     uint32_t ku[16], vu[16];
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * 128 + c16), ku);
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_v + t * 128 + c16), vu);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c16), ku);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_v + t * NCH + c16), vu);
                     tmem_ld_wait();
                     if (!valid) continue;
                     float kv[16], vv[16];
@@ -377,7 +396,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
                 if (valid) {
                     const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-                    *reinterpret_cast<uint4*>(smem + p.v_off + 16u * plane + row_off) = pack8(ones, p.fmt);
+                    *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)(NCH >> 3) * plane + row_off) = pack8(ones, p.fmt);
                 }
             }
             if (dbg && r == 0) dbg[4] = clock64();
@@ -391,16 +410,17 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             {
                 const int h = quad, d = lane;                // TMEM row r = (h, d)
                 for (int s = t0; s < p.nb; s += tstep) {
+                    if (h >= HC) break;                      // head split: rows 64..127 of the context accumulator are not ours (warp-uniform)
                     uint32_t u0[16], u1[16], us[16];
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32), u0);
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + h * 32 + 16), u1);
-                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * 144 + 128), us);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + h * 32), u0);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + h * 32 + 16), u1);
+                    tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + NCH), us);
                     tmem_ld_wait();
                     float c0[16], c1[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { c0[j] = __uint_as_float(u0[j]); c1[j] = __uint_as_float(u1[j]); }
                     const float inv = 0.17677669529663687f * fast_rcp(__uint_as_float(us[0]));      // 32^-0.5 / sum_n exp(k - max)
-                    uint8_t* base = smem + p.ct_off + (uint32_t)(s * 4 + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
+                    uint8_t* base = smem + p.ct_off + (uint32_t)(s * HC + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const float val = (e < 16 ? c0[e] : c1[e - 16]) * inv;
@@ -415,12 +435,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 // two heads per iteration (four TMEM loads in flight, two independent softmax chains); max and sum as
                 // 4-way trees instead of 32-long dependent chains
-                for (int h2 = 0; h2 < 4; h2 += 2) {
+                for (int h2 = 0; h2 < HC; h2 += 2) {
                     uint32_t qu[2][32];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + (h2 + k) * 32), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][0]));
-                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * 128 + (h2 + k) * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][16]));
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * NCH + (h2 + k) * 32), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][0]));
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_q + t * NCH + (h2 + k) * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(&qu[k][16]));
                     }
                     tmem_ld_wait();
                     if (!valid) continue;
@@ -459,10 +479,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const int px = t * 128 + r;
                     const bool valid = px < n && b0 + s < p.B;
                     const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
-                    for (int c32 = 0; c32 < 128; c32 += 32) {
+                    for (int c32 = 0; c32 < NCH; c32 += 32) {
                         uint32_t ua[16], ub[16];
-                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c32), ua);
-                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * 128 + c32 + 16), ub);
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * NCH + c32), ua);
+                        tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * NCH + c32 + 16), ub);
                         tmem_ld_wait();
                         if (!valid) continue;
                         float v[32];
@@ -476,6 +496,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar_epi);
+            // head split: the out MMAs (the last readers of this CTA's P slot) completed before this epilogue began, so the peer
+            // may use it as its exchange buffer from here on: tell it now, long before it asks
+            if (HS > 1 && et == 0) mbar_arrive_cluster(mapa_shared(bar_r, hrank ^ 1u));
         } else {
             // ================= mid attention: softmax(q k^T) v on CUDA cores (unet.py:99-122) =================
             // A CTA owns nb = 32/n samples = 32 rows (TMEM lane quadrant 0).  Warp 0 moves K, V (16-bit) and Q (fp32)
@@ -582,6 +605,100 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         if (dbg && r == 0) dbg[26] = clock64();
         griddep_launch();            // PDL: the next stage kernel may become resident during the last epilogue
         const float* bias = par;
+        if (HS > 1) {
+            // ================= head split: add the two K halves of the to_out projection across the CTA pair =================
+            // Warp group g holds pixel tile g of this CTA's partial projection; CTA r finalises tile r.  Three one-shot
+            // cluster-scope mbarriers, all arrived on per WARP (lane 0 after __syncwarp; no CTA-wide barrier on this path):
+            //   bar_r (1 arrival, sent by the peer at the end of ITS epilogue 2): the peer's P slot is dead, so the exchange
+            //          buffer that aliases it may be written;
+            //   bar_d (4 arrivals: the peer's four sending warps): the partial rows have been delivered;
+            //   bar_s (8 arrivals: four finalising warps of each CTA): the GroupNorm partial sums have been delivered.
+            const int t = half;                           // this warp group's pixel tile (EW == 8, two M tiles)
+            const bool mine = (uint32_t)t == hrank;
+            const uint32_t peer = hrank ^ 1u;
+            float* xbuf = reinterpret_cast<float*>(smem + p.p_off);           // [128 rows][C] fp32, written by the peer
+            float2* xstat = stat + 64;                                        // [2 CTAs][4 warps] (sum, sumsq) of the finalised tiles
+            const int rd = t * 128 + r, px = rd & (n - 1);
+            if (!mine) {
+                mbar_wait_cluster(bar_r, 0);
+                const uint32_t dst0 = mapa_shared(smem_base + p.p_off + (uint32_t)r * (uint32_t)C * 4u, peer);
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        st_cluster_v4(dst0 + (uint32_t)(c16 + 4 * k4) * 4u,
+                                      make_uint4(__float_as_uint(v[4 * k4]), __float_as_uint(v[4 * k4 + 1]), __float_as_uint(v[4 * k4 + 2]),
+                                                 __float_as_uint(v[4 * k4 + 3])));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(bar_d, peer));
+            } else {
+                // the residual rows of this tile are requested before the wait (an exposed L2 round trip otherwise)
+                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+                uint4 xres[8];
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb)
+                    xres[cb] = cb < (C >> 3) ? xsrc[(size_t)(cb * p.B + b0) * n + px] : make_uint4(0, 0, 0, 0);
+                mbar_wait_cluster(bar_d, 0);
+                float sx = 0.f, sq = 0.f;
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    float v[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+                    const float4* xb = reinterpret_cast<const float4*>(xbuf + r * C + c16);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 o = xb[k4];
+                        const float oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * k4 + e;
+                            // fixed order: (heads 0,1) + (heads 2,3)
+                            const float x = (hrank == 0 ? v[j] + oo[e] : oo[e] + v[j]) + bias[c16 + j];
+                            sx += x; sq = fmaf(x, x, sq);
+                        }
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+                if (lane == 0) {
+                    const uint32_t off = (uint32_t)((uint8_t*)(xstat + hrank * 4 + quad) - smem);
+                    st_cluster_f2(mapa_shared(smem_base + off, 0u), make_float2(sx, sq));
+                    st_cluster_f2(mapa_shared(smem_base + off, 1u), make_float2(sx, sq));
+                    mbar_arrive_cluster(mapa_shared(bar_s, 0u));
+                    mbar_arrive_cluster(mapa_shared(bar_s, 1u));
+                }
+                mbar_wait_cluster(bar_s, 0);
+                float tx = 0.f, tq = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { tx += xstat[k].x; tq += xstat[k].y; }          // fixed order, identical in both CTAs
+                const float icnt = fast_rcp((float)(C * n));
+                const float mean = tx * icnt;
+                const float rstd = rsqrtf(fmaxf(tq * icnt - mean * mean, 0.f) + 1e-5f);
+                const float* gamma = par + 128;
+                const float* beta = par + 256;
+                for (int c16 = 0; c16 < C; c16 += 16) {
+                    float v[16], x2[16];
+                    tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
+                    const float4* xb = reinterpret_cast<const float4*>(xbuf + r * C + c16);
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb)
+                        if (cb == (c16 >> 3)) { unpack8(xres[cb], x2, p.fmt); unpack8(xres[cb + (cb < 7 ? 1 : 0)], x2 + 8, p.fmt); }
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 o = xb[k4];
+                        const float oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * k4 + e;
+                            const float a = hrank == 0 ? v[j] + oo[e] : oo[e] + v[j];
+                            const float y = (a + bias[c16 + j] - mean) * rstd * gamma[c16 + j] + beta[c16 + j];
+                            v[j] = y + x2[j];
+                        }
+                    }
+                    attn_write_out(p, b0, px, c16, v);
+                }
+            }
+        } else {
         if (!p.full) {
             for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
@@ -695,21 +812,25 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
         }
     }
+    }
     tc_fence_before();
     __syncthreads();
+    if (HS > 1) cluster_sync_all();          // no CTA of the pair may exit while the other can still store into its shared memory
     if (dbg && tid == 0) dbg[65] = clock64();
     if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
     if (warp == w_mma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 cudaError_t attn_configure() {
-    return cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_attn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
 }
 
 cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
     void* args[2] = {(void*)&xh_map, (void*)&p};
-    return launch_pdl((const void*)k_attn, grid, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, 1);
+    return launch_pdl(p.hc == 2 ? (const void*)k_attn<2> : (const void*)k_attn<4>, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
 }
 
 }  // namespace flo
