@@ -505,4 +505,63 @@ cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cud
     return cudaGetLastError();
 }
 
+// Micro-benchmark: how fast ONE CTA pulls a weight stream from L2 through a ring of bulk copies (what the chain stages do at the
+// low resolutions): thread 0 issues cp.async.bulk copies (`pieces` per chunk) into an n_ring-deep ring, thread 32 consumes a chunk
+// as soon as it is full.  Every CTA of the grid streams the same bytes (same_src) or its own region.
+__global__ void __launch_bounds__(64) k_stream_rate(const uint8_t* src, long long* cycles, int total_bytes, int chunk_bytes, int n_ring,
+                                                    int pieces, int same_src) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 32];
+    const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[32]);
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < n_ring; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* my = src + (same_src ? 0 : (size_t)blockIdx.x * (size_t)total_bytes);
+    const int n_chunks = total_bytes / chunk_bytes;
+    const long long t0 = clock64();
+    // pieces > 0: thread 0 issues `pieces` copies per chunk; pieces < 0: lanes 0..-pieces-1 of warp 0 issue the chunks round-robin
+    // (one whole-chunk copy each, all lanes in the same instruction)
+    if (pieces < 0 && tid < -pieces) {
+        const int P = -pieces;
+        for (int c = tid; c < n_chunks; c += P) {
+            const int slot = c % n_ring;
+            if (c >= n_ring) mbar_wait(empty + 8 * slot, ((c / n_ring) - 1) & 1);
+            mbar_expect_tx(full + 8 * slot, (uint32_t)chunk_bytes);
+            bulk_load_1d(smem_u32(smem) + (uint32_t)slot * (uint32_t)chunk_bytes, my + (size_t)c * chunk_bytes, (uint32_t)chunk_bytes, full + 8 * slot);
+        }
+    } else if (pieces > 0 && tid == 0) {
+        const uint32_t piece = (uint32_t)(chunk_bytes / pieces);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int slot = c % n_ring;
+            if (c >= n_ring) mbar_wait(empty + 8 * slot, ((c / n_ring) - 1) & 1);
+            mbar_expect_tx(full + 8 * slot, (uint32_t)chunk_bytes);
+            for (int q = 0; q < pieces; ++q)
+                bulk_load_1d(smem_u32(smem) + (uint32_t)slot * (uint32_t)chunk_bytes + (uint32_t)q * piece,
+                             my + (size_t)c * chunk_bytes + (size_t)q * piece, piece, full + 8 * slot);
+        }
+    } else if (tid == 32) {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int slot = c % n_ring;
+            mbar_wait(full + 8 * slot, (c / n_ring) & 1);
+            mbar_arrive(empty + 8 * slot);
+        }
+        if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+    }
+}
+cudaError_t launch_stream_rate(const void* src, long long* cycles, int grid, int total_bytes, int chunk_bytes, int n_ring, int pieces,
+                               int same_src, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_stream_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    k_stream_rate<<<grid, 64, (size_t)n_ring * chunk_bytes + 256, s>>>(reinterpret_cast<const uint8_t*>(src), cycles, total_bytes, chunk_bytes,
+                                                                        n_ring, pieces, same_src);
+    return cudaGetLastError();
+}
+
 }  // namespace flo

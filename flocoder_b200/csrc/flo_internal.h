@@ -175,6 +175,8 @@ cudaError_t launch_umma_micro(const __nv_bfloat16* a, const __nv_bfloat16* b, fl
                               int a_sbo, int a_shift, int b_lbo, int b_sbo, cudaStream_t s);
 
 cudaError_t launch_umma_rate(long long* cycles, int N, int n_mma, int n_acc, cudaStream_t s, int a_mode = 0, int a_shift = 0);
+cudaError_t launch_stream_rate(const void* src, long long* cycles, int grid, int total_bytes, int chunk_bytes, int n_ring, int pieces,
+                               int same_src, cudaStream_t s);
 cudaError_t launch_umma_micro2(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d, long long* cycles, int N, int K, int layout,
                                int row_bytes, int a_sbo, int a_shift, int a_lbo, int use_base_offset, int reps, cudaStream_t s);
 
@@ -267,6 +269,7 @@ struct AttnFusedParams {
     int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
                                             // n_mtiles = 128-row tiles of the dense rows (s*n + p)
     int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)
+    int small;                              // 1: k_attn_small (n = 4 or 16 pixels: 128 / n samples per CTA, attention core on CUDA cores)
     int hc, hsplit;                         // heads per CTA (4, or 2 with the head split) and CTAs per sample (cluster size 1 / 2)
     int fmt;
     unsigned wq_off, wk_off, wv_off, wo_off; // 16-bit weight streams in wblob (N = 128,128,128,C)

@@ -355,44 +355,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
 
     if (warp == W_PROD) {
         // ============================ producer ============================
-        if (lane == 0) {
+        // TWO issuing lanes (chunk cc -> lane cc & 1): the bulk copies of one thread do not overlap and two is what an SM keeps in
+        // flight (profiles/r02_stream_rate.txt: 31.7 -> 55 B/clk for 16 KB chunks)
+        if (lane < 2) {
             const uint32_t ring_base = smem_base + p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
             const uint2* wtab = reinterpret_cast<const uint2*>(smem + p.wtab_off);
             const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.wblob);
             const int n_chunks = p.n_chunks;
-            RingPos rp{0, 0};
             auto issue = [&](int cc) {
                 const uint2 e = wtab[cc];
-                const uint32_t full = bar_full + 8 * rp.slot;
-                if (cc >= n_ring) mbar_wait(bar_empty + 8 * rp.slot, rp.phase ^ 1u);
+                const int slot = cc % n_ring;
+                const uint32_t full = bar_full + 8 * slot;
+                if (cc >= n_ring) mbar_wait(bar_empty + 8 * slot, (uint32_t)((cc / n_ring) - 1) & 1u);
                 if (dbg && cc >= 8 && cc < 16) dbg[104 + (cc - 8) * 3 + 1] = clock64();
                 mbar_expect_tx(full, e.y);
-                // several concurrent bulk copies per chunk: more requests in flight towards L2
-                const uint32_t dst = ring_base + (uint32_t)rp.slot * ring_slot_bytes;
-                const uint8_t* src = wbase + e.x;
-                if (e.y >= 8192u) {
-                    const uint32_t piece = ((e.y >> 2) + 15u) & ~15u;
-                    bulk_load_1d(dst, src, piece, full);
-                    bulk_load_1d(dst + piece, src + piece, piece, full);
-                    bulk_load_1d(dst + 2 * piece, src + 2 * piece, piece, full);
-                    bulk_load_1d(dst + 3 * piece, src + 3 * piece, e.y - 3 * piece, full);
-                } else {
-                    bulk_load_1d(dst, src, e.y, full);
-                }
-                rp.next(n_ring);
+                // ONE bulk copy per chunk: a cp.async.bulk costs ~520 cycles whatever its size (16 KB in one copy 31.7 B/clk, in four
+                // 23.4, in sixteen 11.9), so chunks are as large as the ring allows
+                bulk_load_1d(ring_base + (uint32_t)slot * ring_slot_bytes, wbase + e.x, e.y, full);
             };
             // the weights do not depend on the previous kernel: fill the ring before waiting for it
             const int pre = min(n_ring, n_chunks);
-            for (int cc = 0; cc < pre; ++cc) issue(cc);
+            int cc = lane;
+            for (; cc < pre; cc += 2) issue(cc);
             griddep_wait();
-            if (n_loads > 0) {
+            if (lane == 0 && n_loads > 0) {
                 uint32_t lbytes = 0;
                 for (int i = 0; i < n_loads; ++i) lbytes += (uint32_t)p.load_ncb[i] * plane_bytes;
                 mbar_expect_tx(bar_load, lbytes);
                 const CUtensorMap* maps[4] = {&tm0, &tm1, &tm2, &tm3};
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
-            for (int cc = pre; cc < n_chunks; ++cc) issue(cc);
+            for (; cc < n_chunks; cc += 2) issue(cc);
         }
     } else if (warp == W_MMA) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================

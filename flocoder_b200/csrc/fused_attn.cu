@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             int ph = 0;
             if (!p.full) {
                 // ---- phase 1: context per sample (both operands MN-major, K = pixels), then the Q convolution
-                mbar_wait(bar_epi, ph & 1); ++ph;
+                named_bar_sync(2, n_epi + 32); ++ph;
                 tc_fence_after();
                 if (dbg && lane == 0) dbg[8] = clock64();
                 // M = 128 channel rows are always read (with two heads per CTA rows 64..127 are whatever follows the P slot:
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 if (elect_one()) umma_commit(bar_mma);
                 __syncwarp();
                 // ---- phase 2: out[n][(h,e)] per (sample, tile, head)
-                mbar_wait(bar_epi, ph & 1); ++ph;
+                named_bar_sync(2, n_epi + 32); ++ph;
                 tc_fence_after();
                 if (dbg && lane == 0) dbg[16] = clock64();
                 const uint32_t idesc_out = make_idesc16(128, 32, p.fmt, 0, 0);
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
             // ---- last phase: to_out convolution over the O slot
-            mbar_wait(bar_epi, ph & 1); ++ph;
+            named_bar_sync(2, n_epi + 32); ++ph;
             tc_fence_after();
             if (dbg && lane == 0) dbg[24] = clock64();
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, C, 0u, p.col_proj,
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && r == 0) dbg[4] = clock64();
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_epi);
+            named_bar_arrive(2, n_epi + 32);
             // ================= EPI 1: context normalisation -> B operand; softmax_d(q) -> A operand =================
             mbar_wait(bar_mma, ph & 1); ++ph;
             tc_fence_after();
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && r == 0) dbg[11] = clock64();
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_epi);
+            named_bar_arrive(2, n_epi + 32);
             // ================= EPI 2: attention output -> O slot (dense rows), reuses the V slot =================
             mbar_wait(bar_mma, ph & 1); ++ph;
             tc_fence_after();
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_epi);
+            named_bar_arrive(2, n_epi + 32);
             // head split: the out MMAs (the last readers of this CTA's P slot) completed before this epilogue began, so the peer
             // may use it as its exchange buffer from here on: tell it now, long before it asks
             if (HS > 1 && et == 0) mbar_arrive_cluster(mapa_shared(bar_r, hrank ^ 1u));
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_epi);
+            named_bar_arrive(2, n_epi + 32);
         }
         if (dbg && r == 0) dbg[19] = clock64();
         // ================= last EPI: to_out bias -> GroupNorm(1,C) -> + x2 -> global =================
@@ -719,12 +719,23 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     }
                 }
                 sx += sx2; sq += sq2;
-                rowstat[rd] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                if (n >= 32) {
+                    // a warp's 32 rows lie in one sample: reduce with shuffles, one partial per 32-row block, ONE barrier;
+                    // every thread then adds its sample's n/32 block sums itself (fixed order: deterministic)
+                    if (!valid) { sx = 0.f; sq = 0.f; }
+                    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+                    if (lane == 0) partial[rd >> 5] = make_float2(sx, sq);
+                } else {
+                    rowstat[rd] = valid ? make_float2(sx, sq) : make_float2(0.f, 0.f);
+                }
             }
             // per-sample totals in a fixed order (deterministic)
             int parts = 1;
             while (parts * 2 * p.nb <= 128 && parts < 16) parts *= 2;
             esync();
+            if (n >= 32) {
+                // nothing: the normalisation pass forms mean / rstd from `partial`
+            } else {
             if (et < p.nb * parts) {
                 const int lgp = 31 - __clz(parts);
                 const int part = et & (parts - 1), s = et >> lgp;
@@ -744,6 +755,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 stat[et] = make_float2(mean, rsqrtf(var + 1e-5f));
             }
             esync();
+            }
         }
         const float* gamma = par + 128;
         const float* beta = par + 256;
@@ -784,7 +796,19 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const int b = b0 + s;
-                const float2 ms = s < p.nb ? stat[s] : make_float2(0.f, 1.f);
+                float2 ms = make_float2(0.f, 1.f);
+                if (s < p.nb) {
+                    if (n >= 32) {
+                        const int bps = n >> 5;                 // 32-row blocks per sample
+                        float tx = 0.f, tq = 0.f;
+                        for (int k = 0; k < bps; ++k) { const float2 a = partial[s * bps + k]; tx += a.x; tq += a.y; }
+                        const float icnt = fast_rcp((float)(C * n));
+                        const float mean = tx * icnt;
+                        ms = make_float2(mean, rsqrtf(fmaxf(tq * icnt - mean * mean, 0.f) + 1e-5f));
+                    } else {
+                        ms = stat[s];
+                    }
+                }
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
                 // the residual rows of the NEXT channel chunk are requested before this chunk is processed
                 uint4 xa = make_uint4(0, 0, 0, 0), xb = xa;
@@ -821,15 +845,332 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     if (warp == w_mma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_attn_small: the attention blocks of the 4x4 and 2x2 levels (n = H*W = 16 or 4 pixels per sample), linear
+// (unet.py:125-150) and full (unet.py:99-122).  A sample's n x n interaction is tiny, so only the four 1x1 projections run on
+// the tensor cores and a CTA owns 128 / n SAMPLES (128 dense rows: the M tile is full):
+//   MMA   K, V, Q = to_qkv 1x1 convs (N = 128 each)                                        -> TMEM [0, 384)
+//   EPI-A row r, channel half: k~ = softmax_n(k) (segmented halving shuffles over the n lanes of a sample) and V -> 16-bit
+//         shared-memory rows                                                                  (linear; full: raw k, v)
+//   EPI-B row r = (sample s, pixel i), two heads per thread, on CUDA cores out of shared memory:
+//         linear: q~ = softmax_d(q) * 32^-.5;  S[m] = sum_d q~[d] k~[m][d];  out[e] = sum_m S[m] v[m][e]
+//                 (== sum_d ctx[d][e] q~[d] with ctx = k~ v^T: the same contraction, reassociated)
+//         full:   S[m] = sum_d 32^-.5 q[d] k[m][d];  softmax_m;  out[e] = sum_m S[m] v[m][e]
+//         out -> 16-bit K-major operand slot
+//   MMA   to_out 1x1 conv                                                                      -> TMEM [384, 384 + C)
+//   EPI-C + bias [-> GroupNorm(1, C) per sample] + x2 -> global (normal / unshuffled / upsampled)
+// Two MMA phases instead of four, no context / output MMAs, and 8x (n = 16) / 16x (n = 4) fewer CTAs than two samples per CTA.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SM_KP = 528u;          // row pitch of the fp32 k~ / v staging (128 floats + 16 bytes: conflict-free rows)
+constexpr int SMALL_EW = 16;              // epilogue warps of k_attn_small: one (row, head) task per thread in the attention core
+constexpr int SMALL_THREADS = (SMALL_EW + 2) * 32;
+template <int SEG, bool IS_MAX>
+__device__ __forceinline__ int segred16(float (&v)[16], int lane) {
+    // reduction over the SEG lanes of a segment for 16 values per lane; every level also halves the values a lane keeps
+    // (colmax16's pattern).  Returns the first channel this lane ends up owning; it owns 16 / SEG... see callers.
+    int chan = 0;
+    auto halve = [&](int m, bool upper, int o) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < m / 2) {
+                const float send = upper ? v[j] : v[j + m / 2];
+                const float keep = upper ? v[j + m / 2] : v[j];
+                const float got = __shfl_xor_sync(0xffffffffu, send, o);
+                v[j] = IS_MAX ? fmaxf(keep, got) : keep + got;
+            }
+        }
+    };
+    if (SEG == 16) {
+        halve(16, lane & 8, 8); chan += (lane & 8) ? 8 : 0;
+        halve(8, lane & 4, 4);  chan += (lane & 4) ? 4 : 0;
+        halve(4, lane & 2, 2);  chan += (lane & 2) ? 2 : 0;
+        halve(2, lane & 1, 1);  chan += (lane & 1) ? 1 : 0;
+    } else {   // SEG == 4: four channels per lane remain
+        halve(16, lane & 2, 2); chan += (lane & 2) ? 8 : 0;
+        halve(8, lane & 1, 1);  chan += (lane & 1) ? 4 : 0;
+    }
+    return chan;
+}
+
+template <int NPX, bool LINEAR>
+__global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_constant__ CUtensorMap tm_xh,
+                                                                   const __grid_constant__ AttnFusedParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int LGN = NPX == 16 ? 4 : 2;
+    constexpr int SPW = 32 / NPX;                      // samples per warp
+    constexpr int CNT = 16 / NPX;                      // channels a lane owns after a segmented reduction of 16 (1 or 4)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    constexpr int EW = SMALL_EW, n_epi = EW * 32, w_prod = EW, w_mma = EW + 1;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_base + p.bar_off;
+    const uint32_t bar_empty = bar_full + 8 * MAX_WSTAGES;
+    const uint32_t bar_load = bar_empty + 8 * MAX_WSTAGES;
+    const uint32_t bar_mma = bar_load + 8;
+    const uint32_t tmem_slot = bar_mma + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
+    const int b0 = (int)blockIdx.x * p.nb;
+    const int C = p.C;
+    const uint32_t plane = 2048u;                      // 128 rows x 16 bytes
+    if (warp == w_prod && lane == 0) {
+        for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == w_mma) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
+
+    if (warp == w_prod) {
+        if (lane < 2) {
+            // two issuing lanes (chunk g -> lane g & 1): the bulk copies of one thread do not overlap (profiles/r02_stream_rate.txt)
+            const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(ATTN_RING, total);
+            int g = lane;
+            for (; g < pre; g += 2) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, 0);
+            griddep_wait();          // weights are constants; the activations come from the previous kernel
+            if (lane == 0) {
+                mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * plane);
+                tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
+            }
+            for (; g < total; g += 2) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, 0);
+        }
+    } else if (warp == w_mma) {
+        RingA rs{0};
+        mbar_wait(bar_load, 0);
+        tc_fence_after();
+        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_k, p.qkv_chunks, p.qkv_S);
+        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_v, p.qkv_chunks, p.qkv_S);
+        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_q, p.qkv_chunks, p.qkv_S);
+        if (elect_one()) umma_commit(bar_mma);
+        __syncwarp();
+        named_bar_sync(2, n_epi + 32);       // the attention output is in the operand slot (which reuses the input tile: every
+        tc_fence_after();                    // projection that read it has completed, the epilogue waited for bar_mma)
+        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, C, C, 0u, p.col_proj, p.o_chunks, p.o_S);
+        if (elect_one()) umma_commit(bar_mma);
+        __syncwarp();
+    } else {
+        const int quad = warp & 3, part = warp >> 2;           // TMEM lane quadrant; which quarter of the channels / which head
+        const int half = part & 1;
+        const int r = quad * 32 + lane;                        // dense row = s * NPX + pixel == TMEM lane
+        const int et = tid;
+        const int s_loc = r >> LGN, px = r & (NPX - 1);        // sample within the CTA, pixel
+        const int b = b0 + s_loc;
+        const bool valid = b < p.B;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        auto esync = [&]() { named_bar_sync(1, n_epi); };
+        uint8_t* kst = smem + p.p_off;                         // k~ (linear) / k (full): [128 rows][SM_KP]
+        uint8_t* vst = smem + p.v_off;
+        float* scr = reinterpret_cast<float*>(smem + p.kmax_off) + warp * (2 * SPW * 16);      // per warp: max[SPW][16], sum[SPW][16]
+        float2* hstat = reinterpret_cast<float2*>(smem + p.stats_off);                          // [2 halves][128 / NPX samples]
+        float* par = reinterpret_cast<float*>(hstat + 2 * 64);                                  // [3][128]: bias, gamma, beta
+        for (int c = et; c < C; c += n_epi) {
+            par[c] = p.fblob[p.bo_off + c];
+            par[128 + c] = LINEAR ? p.fblob[p.gamma_off + c] : 1.0f;
+            par[256 + c] = LINEAR ? p.fblob[p.beta_off + c] : 0.0f;
+        }
+        griddep_wait();
+        // the residual rows are requested now: an exposed L2 round trip in the last epilogue otherwise
+        const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+        const int cb0 = half * (C >> 4);                       // this thread's channel blocks in the last epilogue: [cb0, cb0 + C/16)
+        mbar_wait(bar_load, 0);
+        mbar_wait(bar_mma, 0);
+        tc_fence_after();
+        // ================= EPI-A: this thread's 32 channels of row r: k (column softmax over the sample's pixels) and v =================
+        for (int c16 = part * 32; c16 < part * 32 + 32; c16 += 16) {
+            uint32_t ku[16], vu[16];
+            tmem_ld16_issue(tlane + (uint32_t)(p.col_k + c16), ku);
+            tmem_ld16_issue(tlane + (uint32_t)(p.col_v + c16), vu);
+            tmem_ld_wait();
+            float kv[16], vv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); }
+            if (LINEAR) {
+                float red[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) red[j] = kv[j];
+                const int ca = segred16<NPX, true>(red, lane);
+                float* mx = scr + (lane >> LGN) * 16;
+#pragma unroll
+                for (int j = 0; j < CNT; ++j) mx[ca + j] = red[j];
+                __syncwarp();
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 m4 = reinterpret_cast<const float4*>(mx)[k4];
+                    kv[4 * k4] = fast_exp(kv[4 * k4] - m4.x); kv[4 * k4 + 1] = fast_exp(kv[4 * k4 + 1] - m4.y);
+                    kv[4 * k4 + 2] = fast_exp(kv[4 * k4 + 2] - m4.z); kv[4 * k4 + 3] = fast_exp(kv[4 * k4 + 3] - m4.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) red[j] = kv[j];
+                const int cs = segred16<NPX, false>(red, lane);
+                float* sm = scr + SPW * 16 + (lane >> LGN) * 16;
+#pragma unroll
+                for (int j = 0; j < CNT; ++j) sm[cs + j] = red[j];
+                __syncwarp();
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 s4 = reinterpret_cast<const float4*>(sm)[k4];
+                    kv[4 * k4] *= fast_rcp(s4.x); kv[4 * k4 + 1] *= fast_rcp(s4.y); kv[4 * k4 + 2] *= fast_rcp(s4.z); kv[4 * k4 + 3] *= fast_rcp(s4.w);
+                }
+                __syncwarp();                                   // the scratch rows are rewritten by the next chunk
+            }
+            float4* kd = reinterpret_cast<float4*>(kst + (uint32_t)r * SM_KP + (uint32_t)c16 * 4u);
+            float4* vd = reinterpret_cast<float4*>(vst + (uint32_t)r * SM_KP + (uint32_t)c16 * 4u);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                kd[k4] = make_float4(kv[4 * k4], kv[4 * k4 + 1], kv[4 * k4 + 2], kv[4 * k4 + 3]);
+                vd[k4] = make_float4(vv[4 * k4], vv[4 * k4 + 1], vv[4 * k4 + 2], vv[4 * k4 + 3]);
+            }
+        }
+        esync();
+        // ================= EPI-B: head `part` of row r =================
+        const int row_s0 = s_loc << LGN;                        // first row of this row's sample
+        {
+            const int h = part;
+            float q[32];
+            {
+                uint32_t qa[16], qb[16];
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_q + h * 32), qa);
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_q + h * 32 + 16), qb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { q[j] = __uint_as_float(qa[j]); q[16 + j] = __uint_as_float(qb[j]); }
+            }
+            if (LINEAR) {                                       // softmax over the 32 head channels, then * 32^-0.5 (unet.py:141-143)
+                float m4[4] = {q[0], q[1], q[2], q[3]};
+#pragma unroll
+                for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], q[j]);
+                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { q[j] = fast_exp(q[j] - m); s4[j & 3] += q[j]; }
+                const float inv = 0.17677669529663687f * fast_rcp((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) q[j] *= inv;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) q[j] *= 0.17677669529663687f;       // q * scale (unet.py:113)
+            }
+            float S[NPX];
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4* kr = reinterpret_cast<const float4*>(kst + (uint32_t)(row_s0 + m) * SM_KP + (uint32_t)h * 128u);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 kk = kr[c4];
+                    a0 = fmaf(q[c4 * 4], kk.x, a0); a1 = fmaf(q[c4 * 4 + 1], kk.y, a1);
+                    a0 = fmaf(q[c4 * 4 + 2], kk.z, a0); a1 = fmaf(q[c4 * 4 + 3], kk.w, a1);
+                }
+                S[m] = a0 + a1;
+            }
+            if (!LINEAR) {                                      // softmax over the key pixels (unet.py:116-118)
+                float m = S[0];
+#pragma unroll
+                for (int j = 1; j < NPX; ++j) m = fmaxf(m, S[j]);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) { S[j] = fast_exp(S[j] - m); sum += S[j]; }
+                const float inv = fast_rcp(sum);
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) S[j] *= inv;
+            }
+            float o[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = 0.f;
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4* vr = reinterpret_cast<const float4*>(vst + (uint32_t)(row_s0 + m) * SM_KP + (uint32_t)h * 128u);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 vv = vr[c4];
+                    o[c4 * 4] = fmaf(S[m], vv.x, o[c4 * 4]); o[c4 * 4 + 1] = fmaf(S[m], vv.y, o[c4 * 4 + 1]);
+                    o[c4 * 4 + 2] = fmaf(S[m], vv.z, o[c4 * 4 + 2]); o[c4 * 4 + 3] = fmaf(S[m], vv.w, o[c4 * 4 + 3]);
+                }
+            }
+            // channel = h*32 + e ('b h c (x y) -> b (h c) x y', unet.py:149 / 121), as the K-major A operand of the to_out conv
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+                *reinterpret_cast<uint4*>(smem + p.xh_off + (uint32_t)(4 * h + cb) * plane + (uint32_t)r * 16u) = pack8(o + cb * 8, p.fmt);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_arrive(2, n_epi + 32);
+        // ================= EPI-C: to_out bias [-> GroupNorm(1, C)] -> + x2 -> global; warps 0..7: channels [half*C/2, +C/2) of row r =================
+        if (part < 2) {
+        mbar_wait(bar_mma, 1);
+        tc_fence_after();
+        griddep_launch();            // PDL: the next stage kernel may become resident during the last epilogue
+        const float* bias = par;
+        const float* gamma = par + 128;
+        const float* beta = par + 256;
+        // two warp groups split the channels when each half is a whole number of 16-channel chunks; otherwise group 0 takes all
+        const bool csplit = ((C >> 1) & 15) == 0;
+        const int c_lo = csplit ? half * (C >> 1) : 0, c_hi = csplit ? c_lo + (C >> 1) : (half == 0 ? C : 0);
+        float mean = 0.f, rstd = 1.f;
+        if (LINEAR) {
+            float sx = 0.f, sq = 0.f;
+            for (int c16 = c_lo; c16 < c_hi; c16 += 16) {
+                float v[16];
+                tmem_ld16(tlane + (uint32_t)(p.col_proj + c16), v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float x = v[j] + bias[c16 + j]; sx += x; sq = fmaf(x, x, sq); }
+            }
+            if (!valid) { sx = 0.f; sq = 0.f; }
+#pragma unroll
+            for (int o = NPX >> 1; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+            if (px == 0) hstat[half * 64 + s_loc] = make_float2(sx, sq);
+            named_bar_sync(3, 256);
+            const float2 a = hstat[s_loc], bq = hstat[64 + s_loc];
+            const float icnt = fast_rcp((float)(C * NPX));
+            mean = (a.x + bq.x) * icnt;
+            rstd = rsqrtf(fmaxf((a.y + bq.y) * icnt - mean * mean, 0.f) + 1e-5f);
+        }
+        for (int c16 = c_lo; c16 < c_hi; c16 += 16) {
+            float v[16], x2[16];
+            tmem_ld16(tlane + (uint32_t)(p.col_proj + c16), v);
+            if (!valid) continue;
+            const uint4 xa = xsrc[(size_t)((c16 >> 3) * p.B + b) * NPX + px];
+            const uint4 xb = xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * NPX + px];
+            unpack8(xa, x2, p.fmt);
+            unpack8(xb, x2 + 8, p.fmt);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float y = v[j] + bias[c16 + j];
+                if (LINEAR) y = (y - mean) * rstd * gamma[c16 + j] + beta[c16 + j];
+                v[j] = y + x2[j];
+            }
+            attn_write_out(p, b, px, c16, v);
+        }
+        }
+        (void)cb0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == w_mma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 cudaError_t attn_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_attn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
 }
 
 cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStream_t s, void** args, int cluster);
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
     void* args[2] = {(void*)&xh_map, (void*)&p};
+    if (p.small) {
+        const void* fn = p.n == 16 ? (p.full ? (const void*)k_attn_small<16, false> : (const void*)k_attn_small<16, true>)
+                                   : (p.full ? (const void*)k_attn_small<4, false> : (const void*)k_attn_small<4, true>);
+        return launch_pdl(fn, grid, SMALL_THREADS, (size_t)p.smem_bytes, s, args, 1);
+    }
     return launch_pdl(p.hc == 2 ? (const void*)k_attn<2> : (const void*)k_attn<4>, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
 }
 

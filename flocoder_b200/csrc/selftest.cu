@@ -255,6 +255,31 @@ extern "C" int flo_selftest_umma(char* report, int report_cap, void* stream) {
                 }
                 rep.text += buf; rep.text += "\n";
             }
+        // weight streaming from L2 into one CTA's shared-memory ring (1 MiB per CTA, warm in L2): bytes per SM clock
+        {
+            const int total = 1 << 20;
+            uint8_t* dsrc = nullptr;
+            ST_CUDA(cudaMalloc(&dsrc, (size_t)148 * total));
+            ST_CUDA(cudaMemset(dsrc, 1, (size_t)148 * total));
+            // {CTAs, chunk bytes, ring slots, copies per chunk (< 0: that many issuing lanes, one copy per chunk), same source}
+            const int cfgs[14][5] = {{1, 16384, 4, 4, 1}, {1, 16384, 8, 1, 1}, {1, 16384, 8, 16, 1}, {1, 4096, 32, 1, 1}, {1, 32768, 4, 1, 1},
+                                     {1, 65536, 2, 1, 1}, {1, 16384, 8, -2, 1}, {1, 16384, 8, -4, 1}, {1, 16384, 8, -8, 1}, {1, 4096, 32, -8, 1},
+                                     {1, 4096, 32, -32, 1}, {128, 16384, 8, 1, 1}, {128, 16384, 8, -4, 1}, {128, 16384, 8, -4, 0}};
+            for (int k = 0; k < 14; ++k) {
+                long long best = 1LL << 60;
+                for (int rep2 = 0; rep2 < 3; ++rep2) {
+                    ST_CUDA(launch_stream_rate(dsrc, dc, cfgs[k][0], total, cfgs[k][1], cfgs[k][2], cfgs[k][3], cfgs[k][4], st));
+                    ST_CUDA(cudaStreamSynchronize(st));
+                    ST_CUDA(cudaMemcpy(hc, dc, 8, cudaMemcpyDeviceToHost));
+                    if (hc[0] < best) best = hc[0];
+                }
+                char buf[256];
+                snprintf(buf, sizeof(buf), "INFO stream_rate ctas=%-3d chunk=%-5d ring=%-2d pieces=%-2d same_src=%d : %lld cycles per MiB -> %.1f B/clk",
+                         cfgs[k][0], cfgs[k][1], cfgs[k][2], cfgs[k][3], cfgs[k][4], best, (double)total / (double)best);
+                rep.text += buf; rep.text += "\n";
+            }
+            cudaFree(dsrc);
+        }
         cudaFree(dc);
     }
     auto flush = [&]() { if (report && report_cap > 0) snprintf(report, report_cap, "%s", rep.text.c_str()); };
