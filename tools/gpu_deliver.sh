@@ -13,7 +13,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 echo "launch-list rc=$?"
 timeout 100 python tools/one_forward.py bf16 256 > /dev/null 2>&1 && \
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_chain|k_attn" --launch-skip 19 --launch-count 19 \
-    -o gpurun_out/r01_full_forward -f python tools/one_forward.py bf16 256 > gpurun_out/ncu_full.log 2>&1
+    -o gpurun_out/r02_full_forward -f python tools/one_forward.py bf16 256 > gpurun_out/ncu_full.log 2>&1
 echo "full-capture rc=$?"
 timeout 200 python tools/gpu_profile.py bf16 4096 layerwise > gpurun_out/layerwise_b4096.txt 2>&1
 timeout 300 python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu > gpurun_out/bench_b1024.json 2> gpurun_out/bench_b1024.err; echo "b1024 rc=$?"
