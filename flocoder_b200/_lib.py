@@ -29,7 +29,7 @@ EXPORTS = (
     "flo_unet_destroy", "flo_unet_set_time_freqs", "flo_workspace_bytes", "flo_unet_forward", "flo_integrate", "flo_integrate_host",
     "flo_integrate_nfe", "flo_unet_num_ops", "flo_unet_op_name", "flo_unet_launches_per_forward",
     "flo_unet_launch_count", "flo_unet_read_activation", "flo_selftest_umma", "flo_describe_plan",
-    "flo_unet_op_info", "flo_unet_profile_ops", "flo_unet_read_timeline",
+    "flo_unet_op_info", "flo_unet_profile_ops", "flo_unet_read_timeline", "flo_unet_set_mask",
 )
 
 
@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
                                 c_void_p, c_float, c_void_p, c_int, c_void_p]
     L.flo_integrate_host.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_float), c_int, c_int, c_float,
                                      c_float, c_void_p, c_float, c_int, c_void_p]
+    L.flo_unet_set_mask.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.flo_integrate_nfe.argtypes = [c_int, c_int]
     L.flo_unet_num_ops.argtypes = [c_void_p]
     L.flo_unet_op_name.argtypes = [c_void_p, c_int, c_char_p, c_int]
@@ -103,7 +104,7 @@ def check(status: int, what: str = "") -> None:
 
 
 def make_cfg(dim, channels, dim_mults, groups, n_classes, height, width, compute_dtype, device_index,
-             flags=0) -> FloUnetCfg:
+             flags=0, mask_cond=False) -> FloUnetCfg:
     if len(dim_mults) > 8:
         raise ValueError("at most 8 resolution levels are supported")
     cfg = FloUnetCfg()
@@ -112,7 +113,7 @@ def make_cfg(dim, channels, dim_mults, groups, n_classes, height, width, compute
         cfg.mults[i] = int(m)
     cfg.groups, cfg.n_classes, cfg.height, cfg.width = groups, n_classes, height, width
     cfg.compute_dtype = {"fp32": FLO_F32, "bf16": FLO_BF16, "fp16": FLO_F16}[compute_dtype]
-    cfg.mask_cond, cfg.flags, cfg.device = 0, flags, device_index
+    cfg.mask_cond, cfg.flags, cfg.device = int(bool(mask_cond)), flags, device_index
     return cfg
 
 
@@ -139,7 +140,7 @@ class Engine:
     """Owns one ``flo_unet_t`` (packed weights + workspaces) for one module state on one device."""
 
     def __init__(self, *, dim, channels, dim_mults, groups, n_classes, height, width, compute_dtype,
-                 device, state_dict: Dict[str, torch.Tensor], flags: int = 0):
+                 device, state_dict: Dict[str, torch.Tensor], flags: int = 0, mask_cond: bool = False):
         self.L = lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -148,8 +149,10 @@ class Engine:
         self.device = torch.device("cuda", index)
         self.channels, self.height, self.width = channels, height, width
         self.compute_dtype = compute_dtype
+        self.mask_cond = bool(mask_cond)
+        self._mask_state = {}                       # batch size -> (weakref to the mask tensor, version) last handed to the library
         self.cfg = make_cfg(dim, channels, dim_mults, groups, n_classes, height, width, compute_dtype,
-                            index, flags)
+                            index, flags, mask_cond)
         manifest = param_manifest(self.cfg)
         tensors = []
         for name, shape in manifest:
@@ -208,6 +211,29 @@ class Engine:
         if c.numel() != b:
             raise ValueError(f"class_cond must have {b} elements, got {c.numel()}")
         return c, c.data_ptr()
+
+    def set_mask(self, mask: Optional[torch.Tensor], b: int) -> None:
+        """cond['mask_cond'] for the following calls at batch size ``b`` (``flo_unet_set_mask``): resized to every level
+        and tested against the reference's all-ones bypass on the device.  ``None`` switches every mask branch off.
+        Re-sending the same tensor object (same version counter) is skipped, so the per-evaluation ``forward`` calls of the
+        generic ``rk4_step`` composition prepare the mask once."""
+        if not self.mask_cond:
+            return                                   # unet.py:298: no mask_fusion_conv -> cond['mask_cond'] is ignored
+        key = None if mask is None else (weakref.ref(mask), mask._version)
+        old = self._mask_state.get(b, "unset")
+        if old != "unset" and ((old is None and key is None) or
+                               (old is not None and key is not None and old[0]() is mask and old[1] == key[1])):
+            return
+        ptr = None
+        if mask is not None:
+            if tuple(mask.shape) != (b, self.channels, self.height, self.width):
+                raise ValueError(f"mask_cond must be [{b},{self.channels},{self.height},{self.width}] (the latent shape, "
+                                 f"unet.py:302), got {tuple(mask.shape)}")
+            keep = mask.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            ptr = keep.data_ptr()
+        with torch.cuda.device(self.device):
+            check(self.L.flo_unet_set_mask(self.handle, ptr, b, _stream_ptr(self.device)), "flo_unet_set_mask")
+        self._mask_state[b] = key
 
     def forward(self, x: torch.Tensor, time: torch.Tensor, class_ids: Optional[torch.Tensor]) -> torch.Tensor:
         b = x.shape[0]

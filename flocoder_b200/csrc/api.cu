@@ -61,6 +61,7 @@ struct Spec {
     bool bf16;                 // 16-bit tensor-core operand path (bf16 or fp16)
     bool f16;                  // operands are fp16 instead of bf16 (fused path only)
     bool fused;                // fused stage kernels (default for the 16-bit paths)
+    bool mask_cond;            // inpainting U-Net: mask-fusion branches (unet.py:214-235), fp32 path only
     int flags, device;
     std::vector<int> dims;     // [dim, dim*m0, dim*m1, ...]   (unet.py:189)
     int time_dim;              // dim*8                         (unet.py:197)
@@ -78,8 +79,9 @@ struct ParamInfo {
 
 static int make_spec(const flo_unet_cfg* c, Spec& s) {
     if (!c) { set_error("cfg is NULL"); return FLO_ERR_INVALID; }
-    if (c->mask_cond) {
-        set_error("mask_cond=1 (inpainting U-Net, unet.py:214-235) is outside the B200 sampling path");
+    if (c->mask_cond && c->compute_dtype != FLO_F32) {
+        set_error("mask_cond=1 (inpainting U-Net, unet.py:214-235) runs on the fp32 path only: its 5x5 / (dim+channels)-input "
+                  "fusion convolutions have no tcgen05 stage kernels; use compute_dtype fp32");
         return FLO_ERR_UNSUPPORTED;
     }
     if (c->n_mults < 1 || c->n_mults > 8) { set_error("n_mults must be in 1..8"); return FLO_ERR_INVALID; }
@@ -90,12 +92,14 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
         set_error("the bf16 tcgen05 path needs dim %% 16 == 0 (K slices of 16 channels), got %d", c->dim);
         return FLO_ERR_UNSUPPORTED;
     }
+    if (c->mask_cond && c->channels > 8) { set_error("mask_cond needs channels <= 8"); return FLO_ERR_UNSUPPORTED; }
     if (c->channels < 1 || c->channels > 16) { set_error("channels must be in 1..16"); return FLO_ERR_UNSUPPORTED; }
     if (c->dim > 64) { set_error("dim > 64 is not supported by the final-conv kernel"); return FLO_ERR_UNSUPPORTED; }
     if (c->n_classes < 0) { set_error("n_classes < 0"); return FLO_ERR_INVALID; }
     s.dim = c->dim; s.channels = c->channels; s.n_levels = c->n_mults; s.groups = c->groups;
     s.n_classes = c->n_classes; s.H = c->height; s.W = c->width; s.bf16 = c->compute_dtype != FLO_F32;
     s.f16 = c->compute_dtype == FLO_F16;
+    s.mask_cond = c->mask_cond != 0;
     // fused stage kernels: latent channels <= 4 (registers of the final epilogue); otherwise the layer-wise tcgen05 path
     s.fused = s.bf16 && !(c->flags & FLO_FLAG_LAYERWISE) && c->channels <= 4;
     s.flags = c->flags; s.device = c->device;
@@ -117,7 +121,8 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
         const int C = s.dims[i];
         if (C % s.groups) { set_error("channels %d not divisible by groups %d", C, s.groups); return FLO_ERR_INVALID; }
         const int cpg = C / s.groups;
-        if (cpg != 4 && cpg % 8) { set_error("channels per group must be 4 or a multiple of 8, got %d", cpg); return FLO_ERR_UNSUPPORTED; }
+        // the fp32 path has a generic GroupNorm kernel (k_gn_any); the 16-bit paths pack whole sectors per group
+        if (s.bf16 && cpg != 4 && cpg % 8) { set_error("channels per group must be 4 or a multiple of 8 on the 16-bit paths, got %d", cpg); return FLO_ERR_UNSUPPORTED; }
     }
     return FLO_OK;
 }
@@ -162,6 +167,13 @@ static std::vector<ParamInfo> manifest(const Spec& s) {
         v.push_back({"class_cond_mlp.0.weight", {s.n_classes, td}});
         add_linear(v, "class_cond_mlp.1", td, td);
         add_linear(v, "class_cond_mlp.3", td, td);
+    }
+    if (s.mask_cond) {                      // unet.py:214-235 (registered before downs / ups)
+        add_conv(v, "mask_fusion_conv.0", 2 * s.dim, s.dim + s.channels, 5);
+        add_conv(v, "mask_fusion_conv.2", 2 * s.dim, 2 * s.dim, 3);
+        add_conv(v, "mask_fusion_conv.4", s.dim, 2 * s.dim, 3);
+        for (int i = 0; i < std::min(2, n); ++i) add_conv(v, "down_mask_fusions." + std::to_string(i) + ".0", s.dims[i], s.dims[i] + s.channels, 3);
+        for (int i = 0; i < std::min(2, n); ++i) add_conv(v, "up_mask_fusions." + std::to_string(i) + ".0", s.dims[n - i], s.dims[n - i] + s.channels, 3);
     }
     for (int l = 0; l < n; ++l) {
         const int din = s.dims[l], dout = s.dims[l + 1];
@@ -217,6 +229,7 @@ struct Op {
     size_t w_simt = NONE, w_umma = NONE, bias = NONE;
     int n_tile = 0;
     int res = -1, out_m = -1, out_o = -1;
+    int act_silu = 0, need_mode = 0, bypass = -1;   // mask-fusion convs (fp32 path)
     // gn
     int gn_in = -1, C = 0, groups = 0, film_off = -1, silu = 0, out_un = -1, out_up = -1;
     size_t gamma = NONE, beta = NONE;
@@ -250,6 +263,7 @@ struct Plan {
     float *y = nullptr, *acc = nullptr, *xs = nullptr, *vcond = nullptr, *film_ps = nullptr;
     int64_t* cls = nullptr;
     Ctrl* ctrl = nullptr;
+    int* mask_mode = nullptr;          // 0 no mask (default), 1 mask of all ones, 2 mask in use (flo_unet_set_mask)
     std::vector<void*> buf_ptr;
     std::vector<ConvUmmaParams> umma;   // per op (valid for conv ops on the bf16 path)
     std::vector<CUtensorMap> tmA0, tmA1;
@@ -306,6 +320,7 @@ struct Handle {
     cudaStream_t capture_stream = nullptr;
     int64_t launches = 0;
     Val r_val;
+    int mask_buf[8] = {-1, -1, -1, -1, -1, -1, -1, -1};   // per-level blocked mask tensors (mask_cond)
     std::vector<FTensor> ftensors;
     std::vector<FStage> fstages;            // variant 0: N-split of the low-resolution chain stages up to 4 CTAs
     std::vector<FStage> fstages_alt[2];     // variants 1, 2: N-split capped at 2 / none (picked per batch size so the
@@ -371,9 +386,15 @@ struct Builder {
     }
 
     // conv with optional second (concatenated) source; perm maps OUR input-channel order to the reference's
+    struct ConvExtra {          // mask-fusion convs: C1 holds c1_real reference channels (the rest of the block is padding)
+        int c1_real = -1; bool silu = false; int need_mode = 0; int bypass = -1; bool want_un = false, want_up = false;
+    };
     Val conv(const std::string& pname, const std::string& vname, int in0, int C0, int in1, int C1, int H, int W,
-             int cout, int ksize, bool bias, bool need_m, bool need_o, int res_m = -1, const std::vector<int>* perm = nullptr) {
+             int cout, int ksize, bool bias, bool need_m, bool need_o, int res_m = -1, const std::vector<int>* perm = nullptr,
+             const ConvExtra* ex = nullptr) {
         Op op; op.kind = OP_CONV; op.name = vname; op.pname = pname; op.unshuf_in = perm != nullptr;
+        const int c1_real = (ex && ex->c1_real >= 0) ? ex->c1_real : C1, cin_ref = C0 + c1_real;
+        if (ex) { op.act_silu = ex->silu; op.need_mode = ex->need_mode; op.bypass = ex->bypass; }
         op.in0 = in0; op.in1 = in1; op.ncb0 = C0 / 8; op.ncb1 = C1 / 8; op.cout = cout; op.ksize = ksize; op.H = H; op.W = W;
         const int cin = C0 + C1, taps = ksize * ksize;
         const auto& w = P(pname + ".weight");
@@ -382,8 +403,9 @@ struct Builder {
             for (int co = 0; co < cout; ++co)
                 for (int ci = 0; ci < cin; ++ci) {
                     const int cref = perm ? (*perm)[ci] : ci;
+                    if (cref >= cin_ref) continue;                    // padding channels of the mask block: zero weights
                     for (int tp = 0; tp < taps; ++tp)
-                        t[((size_t)tp * cin + ci) * cout + co] = w[((size_t)co * cin + cref) * taps + tp];
+                        t[((size_t)tp * cin + ci) * cout + co] = w[((size_t)co * cin_ref + cref) * taps + tp];
                 }
             op.w_simt = put_f32(t.data(), t.size());
         }
@@ -401,9 +423,12 @@ struct Builder {
         }
         if (bias) op.bias = put_param(pname + ".bias");
         Val out = newval(vname, cout, H, W, need_m, need_o);
-        use(in0); use(in1); use(res_m);
+        if (ex && ex->want_un) out.un = newbuf(vname + ":unshuf", cout * 4, H / 2, W / 2, s.bf16);
+        if (ex && ex->want_up) out.up = newbuf(vname + ":up", cout, H * 2, W * 2, s.bf16);
+        use(in0); use(in1); use(res_m); use(op.bypass);
         op.res = res_m; op.out_m = out.m; op.out_o = (out.o != out.m) ? out.o : -1;
-        def(out.m); def(out.o);
+        op.out_un = out.un; op.out_up = out.up;
+        def(out.m); def(out.o); def(out.un); def(out.up);
         h.ops.push_back(op);
         return out;
     }
@@ -483,6 +508,19 @@ struct Builder {
             def(x.m); def(x.o);
             h.ops.push_back(op);
         }
+        const int n_mask = s.mask_cond ? std::min(2, n) : 0;      // levels with a down / up mask fusion (unet.py:225,232)
+        if (s.mask_cond) {
+            // per-level blocked copies of cond['mask_cond'] (8-channel block, zero padded), filled by flo_unet_set_mask;
+            // never (re)defined by an op, so the arena keeps them for the whole program
+            for (int l = 0; l < n; ++l) h.mask_buf[l] = newbuf("mask_cond:" + std::to_string(l), 8, s.H >> l, s.W >> l, false);
+            // x = mask_fusion_conv(cat(x, mask))   (unet.py:298-305; no residual; skipped when the mask is all ones)
+            ConvExtra e0; e0.c1_real = s.channels; e0.silu = true; e0.need_mode = 2;
+            Val f0 = conv("mask_fusion_conv.0", "mask_fusion_conv.0", x.o, s.dim, h.mask_buf[0], 8, s.H, s.W, 2 * s.dim, 5, true, true, true, -1, nullptr, &e0);
+            ConvExtra e1; e1.silu = true; e1.need_mode = 2;
+            Val f1 = conv("mask_fusion_conv.2", "mask_fusion_conv.2", f0.o, 2 * s.dim, -1, 0, s.H, s.W, 2 * s.dim, 3, true, true, true, -1, nullptr, &e1);
+            ConvExtra e2; e2.need_mode = 2; e2.bypass = x.m;
+            x = conv("mask_fusion_conv.4", "mask_fusion_conv", f1.o, 2 * s.dim, -1, 0, s.H, s.W, s.dim, 3, true, true, true, -1, nullptr, &e2);
+        }
         Val r = x;
         Val none;
         std::vector<Val> skips;
@@ -494,8 +532,15 @@ struct Builder {
             Val x1 = resblock(p + ".0", x, none, din, true, true, film_layout);
             skips.push_back(x1);
             Val x2 = resblock(p + ".1", x1, none, din, true, false, film_layout);
-            Val x3 = linattn(p + ".2", x2, false, true, !last, false);
+            const bool fuse = l < n_mask;
+            Val x3 = linattn(p + ".2", x2, fuse, true, !last && !fuse, false);
             skips.push_back(x3);
+            if (fuse) {
+                // x = x + SiLU(conv3x3(cat(x, resize(mask))))   (unet.py:336-340); the skip above keeps the un-fused x
+                ConvExtra e; e.c1_real = s.channels; e.silu = true; e.need_mode = 1; e.bypass = x3.m; e.want_un = !last;
+                const std::string mp = "down_mask_fusions." + std::to_string(l) + ".0";
+                x3 = conv(mp, mp, x3.o, din, h.mask_buf[l], 8, H, W, din, 3, true, true, true, x3.m, nullptr, &e);
+            }
             if (!last) {
                 // our unshuffled channel order is (p1 p2 c); the reference's is (c p1 p2)  (unet.py:52)
                 std::vector<int> perm(din * 4);
@@ -518,7 +563,14 @@ struct Builder {
             x = resblock(p + ".0", x, sk, dout, false, true, film_layout);
             sk = skips.back(); skips.pop_back();
             x = resblock(p + ".1", x, sk, dout, true, false, film_layout);
-            x = linattn(p + ".2", x, false, last, false, !last);
+            const bool fuse = i < n_mask;
+            x = linattn(p + ".2", x, fuse, last || fuse, false, !last && !fuse);
+            if (fuse) {
+                // unet.py:360-364, at the resolution of this up level (mask level l)
+                ConvExtra e; e.c1_real = s.channels; e.silu = true; e.need_mode = 1; e.bypass = x.m; e.want_up = !last;
+                const std::string mp = "up_mask_fusions." + std::to_string(i) + ".0";
+                x = conv(mp, mp, x.o, dout, h.mask_buf[l], 8, H, W, dout, 3, true, true, true, x.m, nullptr, &e);
+            }
             if (!last) {
                 x = conv(p + ".3.1", p + ".3", x.up, dout, -1, 0, H * 2, W * 2, din, 3, true, false, true);
                 H *= 2; W *= 2;
@@ -707,6 +759,8 @@ static int launch_op(Handle& h, Plan& pl, int i, cudaStream_t st) {
                 p.w = f32c(op.w_simt); p.bias = f32c(op.bias); p.res = (const float*)ptr(op.res);
                 p.out_m = (float*)ptr(op.out_m); p.out_o = nullptr; p.o_is_bf16 = 0;
                 p.B = pl.B; p.H = op.H; p.W = op.W; p.cout = op.cout; p.ksize = op.ksize;
+                p.act_silu = op.act_silu; p.out_unshuf = ptr(op.out_un); p.out_up = ptr(op.out_up);
+                if (op.need_mode) { p.mask_mode = pl.mask_mode; p.need_mode = op.need_mode; p.bypass = (const float*)ptr(op.bypass); }
                 e = launch_conv_simt(p, st);
             }
         } break;
@@ -775,7 +829,7 @@ static int get_plan(Handle& h, int B, Plan** out, cudaStream_t st) {
     const size_t cls_bytes = al((size_t)B * 8);
     pl->arena_bytes = s.fused ? 256 : al(h.arena_ps * (size_t)B);     // layer-by-layer activations
     const size_t farena_bytes = s.fused ? al(h.farena_ps * (size_t)B) : 0;   // stage-boundary tensors of the fused path
-    pl->total_bytes = pl->arena_bytes + farena_bytes + 4 * state_bytes + film_bytes + cls_bytes + 256;
+    pl->total_bytes = pl->arena_bytes + farena_bytes + 4 * state_bytes + film_bytes + cls_bytes + 512;
     cudaError_t e = cudaMalloc((void**)&pl->base, pl->total_bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes for B=%d failed: %s", pl->total_bytes, B, cudaGetErrorString(e)); cudaGetLastError(); return FLO_ERR_NOMEM; }
     uint8_t* q = pl->base;
@@ -787,7 +841,8 @@ static int get_plan(Handle& h, int B, Plan** out, cudaStream_t st) {
     pl->vcond = (float*)q; q += state_bytes;
     pl->film_ps = (float*)q; q += film_bytes;
     pl->cls = (int64_t*)q; q += cls_bytes;
-    pl->ctrl = (Ctrl*)q;
+    pl->ctrl = (Ctrl*)q; q += 256;
+    pl->mask_mode = (int*)q;
     pl->buf_ptr.resize(h.bufs.size());
     for (size_t i = 0; i < h.bufs.size(); ++i) pl->buf_ptr[i] = s.fused ? nullptr : pl->arena + h.bufs[i].off_ps * (size_t)B;
     // halo / padding rows of the arena are never read as data, but keep everything finite.  On the CALLER's stream: the
@@ -1043,6 +1098,30 @@ int flo_unet_forward(flo_unet_t* hh, const float* x, const float* time, const in
     CUDA_TRY(launch_setup_ctrl(pl->ctrl, c, h->d_stages, &s0, st));
     h->launches += 2;
     return run_forward(*h, *pl, st);
+}
+
+int flo_unet_set_mask(flo_unet_t* hh, const float* mask, int B, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hh);
+    if (!h) { set_error("NULL handle"); return FLO_ERR_INVALID; }
+    const Spec& s = h->spec;
+    if (!s.mask_cond) {
+        if (!mask) return FLO_OK;           // unet.py:298: hasattr(self, 'mask_fusion_conv') is False -> cond['mask_cond'] is ignored
+        set_error("this U-Net was built with mask_cond=0: it has no mask-fusion branches");
+        return FLO_ERR_INVALID;
+    }
+    CUDA_TRY(cudaSetDevice(s.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = enter_stream(*h, st);
+    if (rc) return rc;
+    Plan* pl = nullptr;
+    rc = get_plan(*h, B, &pl, st);
+    if (rc) return rc;
+    MaskPrepParams mp{};
+    mp.mask = mask; mp.n_levels = s.n_levels; mp.B = B; mp.ch = s.channels; mp.H = s.H; mp.W = s.W; mp.mode = pl->mask_mode;
+    for (int l = 0; l < s.n_levels; ++l) mp.out[l] = (float*)pl->buf_ptr[h->mask_buf[l]];
+    CUDA_TRY(launch_mask_prep(mp, st));
+    h->launches += mask ? 2 : 1;
+    return FLO_OK;
 }
 
 int flo_integrate_nfe(int method, int n_ts) {

@@ -83,6 +83,22 @@ struct ConvSimtParams {
     float* out_m; void* out_o;          // fp32 blocked / operand blocked (either may be null)
     int o_is_bf16;
     int B, H, W, cout, ksize;
+    // inpainting mask branches (unet.py:298-305,336-340,360-364): out = res + SiLU(conv + bias), the pixel-unshuffled /
+    // nearest-x2 copies the following Downsample / Upsample conv reads, and the run-time bypass
+    int act_silu;                       // SiLU on (conv + bias) before the residual is added
+    void* out_unshuf; void* out_up;     // operand copies as in GnParams, or null
+    const int* mask_mode;               // device flag (0 no mask, 1 mask all ones, 2 mask in use), or null
+    int need_mode;                      // the op runs when *mask_mode >= need_mode ...
+    const float* bypass;                // ... else out = bypass (fp32 blocked, same shape), or nothing is written if null
+};
+
+// cond['mask_cond'] [B,ch,H,W] (NCHW fp32) -> one blocked 8-channel fp32 tensor per resolution level (bilinear,
+// F.interpolate(..., mode='bilinear'), unet.py:338,362) + the "mask in use" flag (unet.py:301 torch.allclose)
+struct MaskPrepParams {
+    const float* mask;
+    float* out[8];
+    int n_levels, B, ch, H, W;
+    int* mode;
 };
 
 struct GnParams {
@@ -167,6 +183,8 @@ cudaError_t launch_linattn(const AttnParams& p, cudaStream_t s);
 cudaError_t launch_midattn(const AttnParams& p, cudaStream_t s);
 cudaError_t launch_temb(const TembParams& p, cudaStream_t s);
 cudaError_t launch_final(const FinalParams& p, cudaStream_t s);
+cudaError_t launch_mask_prep(const MaskPrepParams& p, cudaStream_t s);   // p.mask == null: *mode = 0 only
+cudaError_t launch_gn_any(const GnParams& p, cudaStream_t s);            // any channels-per-group (fp32 path)
 cudaError_t launch_conv_umma(const ConvUmmaParams& p, const CUtensorMap& a0, const CUtensorMap& a1,
                              cudaStream_t s);
 cudaError_t conv_umma_configure();   // one-time cudaFuncSetAttribute calls

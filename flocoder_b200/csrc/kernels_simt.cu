@@ -143,45 +143,70 @@ __global__ void __launch_bounds__(128) k_conv_simt(ConvSimtParams p) {
     const int b = idx / HW, px = idx % HW, h = px / p.W, w = px % p.W;
     const int co0 = blockIdx.y * 8;
     const int cin = (p.ncb0 + p.ncb1) * 8;
+    const size_t off = ((size_t)(blockIdx.y * p.B + b) * HW + px) * 8;
     float acc[8];
+    // mask branches that are switched off at run time (no mask / all-ones mask): pass the bypass tensor through
+    const bool live = !p.mask_mode || *p.mask_mode >= p.need_mode;
+    if (!live && !p.bypass) return;
+    if (live) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const int taps = p.ksize * p.ksize, r = p.ksize >> 1;
-    for (int t = 0; t < taps; ++t) {
-        const int hh = h + t / p.ksize - r, ww = w + t % p.ksize - r;
-        if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
-        const int q = hh * p.W + ww;
-        const float* wt = p.w + (size_t)t * cin * p.cout + co0;
-        for (int src = 0; src < 2; ++src) {
-            const TI* in = reinterpret_cast<const TI*>(src ? p.in1 : p.in0);
-            const int ncb = src ? p.ncb1 : p.ncb0;
-            const int cbase = src ? p.ncb0 * 8 : 0;
-            for (int cb = 0; cb < ncb; ++cb) {
-                float xv[8];
-                load8(in + ((size_t)(cb * p.B + b) * HW + q) * 8, xv);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const int taps = p.ksize * p.ksize, r = p.ksize >> 1;
+        for (int t = 0; t < taps; ++t) {
+            const int hh = h + t / p.ksize - r, ww = w + t % p.ksize - r;
+            if (hh < 0 || hh >= p.H || ww < 0 || ww >= p.W) continue;
+            const int q = hh * p.W + ww;
+            const float* wt = p.w + (size_t)t * cin * p.cout + co0;
+            for (int src = 0; src < 2; ++src) {
+                const TI* in = reinterpret_cast<const TI*>(src ? p.in1 : p.in0);
+                const int ncb = src ? p.ncb1 : p.ncb0;
+                const int cbase = src ? p.ncb0 * 8 : 0;
+                for (int cb = 0; cb < ncb; ++cb) {
+                    float xv[8];
+                    load8(in + ((size_t)(cb * p.B + b) * HW + q) * 8, xv);
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    float wv[8];
-                    load8(wt + (size_t)(cbase + cb * 8 + c8) * p.cout, wv);
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float wv[8];
+                        load8(wt + (size_t)(cbase + cb * 8 + c8) * p.cout, wv);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[c8], wv[j], acc[j]);
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[c8], wv[j], acc[j]);
+                    }
                 }
             }
         }
-    }
-    const size_t off = ((size_t)(blockIdx.y * p.B + b) * HW + px) * 8;
-    if (p.bias) {
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += p.bias[co0 + j];
-    }
-    if (p.res) {
-        float rv[8];
-        load8(p.res + off, rv);
+            for (int j = 0; j < 8; ++j) acc[j] += p.bias[co0 + j];
+        }
+        if (p.act_silu) {                                  // nn.SiLU of the mask-fusion convs (unet.py:217-235)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+            for (int j = 0; j < 8; ++j) acc[j] = acc[j] / (1.0f + expf(-acc[j]));
+        }
+        if (p.res) {
+            float rv[8];
+            load8(p.res + off, rv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += rv[j];
+        }
+    } else {
+        load8(p.bypass + off, acc);
     }
     if (p.out_m) store8(p.out_m + off, acc);
     if (p.out_o) store8(reinterpret_cast<TO*>(p.out_o) + off, acc);
+    if (p.out_unshuf) {      // 'b c (h p1) (w p2) -> b (c p1 p2) h w' in our (p1 p2 c) channel order, as k_gn writes it
+        const int ncb = p.cout >> 3;
+        const int plane = ((h & 1) * 2 + (w & 1)) * ncb + (int)blockIdx.y;
+        const int q = (h >> 1) * (p.W >> 1) + (w >> 1);
+        store8(reinterpret_cast<TO*>(p.out_unshuf) + ((size_t)(plane * p.B + b) * (HW >> 2) + q) * 8, acc);
+    }
+    if (p.out_up) {          // nearest x2
+        const int W2 = p.W * 2;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int q = (2 * h + (d >> 1)) * W2 + 2 * w + (d & 1);
+            store8(reinterpret_cast<TO*>(p.out_up) + ((size_t)(blockIdx.y * p.B + b) * (HW * 4) + q) * 8, acc);
+        }
+    }
 }
 cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t s) {
     dim3 grid((p.B * p.H * p.W + 127) / 128, p.cout / 8);
@@ -660,6 +685,7 @@ static void launch_gn_warp(const GnParams& p, int nvec, int pair, cudaStream_t s
 }
 cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
     const int cpg = p.C / p.groups, HW = p.H * p.W;
+    if (cpg != 4 && (cpg & 7)) return launch_gn_any(p, s);
     const int pair = cpg == 4 ? 1 : 0;
     const int nvec_w = pair ? HW * 2 : cpg * HW / 4;                     // float4 per warp-team unit
     const int n_chunks = pair ? 1 : cpg / 8, unit_bytes = n_chunks * HW * 32;
@@ -683,6 +709,113 @@ cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
     const int grid = p.B * p.groups;
     if (p.o_is_bf16) k_gn<__nv_bfloat16><<<grid, nt, 0, s>>>(p);
     else k_gn<float><<<grid, nt, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm + FiLM + SiLU + residual for ANY channels-per-group (fp32 path; e.g. dim = 8 with 4 groups: 2 channels
+// per group, the midi_inpainting U-Net).  One CTA per (sample, group), two-pass statistics, scalar accesses.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gn_any(GnParams p) {
+    __shared__ float red[32];
+    const int G = p.groups, cpg = p.C / G, HW = p.H * p.W, n = cpg * HW;
+    const int b = blockIdx.x / G, g = blockIdx.x % G;
+    auto addr = [&](int e) -> size_t {
+        const int c = g * cpg + e / HW, px = e % HW;
+        return ((size_t)((c >> 3) * p.B + b) * HW + px) * 8 + (c & 7);
+    };
+    float sum = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) sum += p.in[addr(e)];
+    const float mean = block_sum(sum, red) / (float)n;
+    float sq = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) { const float d = p.in[addr(e)] - mean; sq += d * d; }
+    const float var = block_sum(sq, red) / (float)n;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float* film = nullptr;
+    if (p.film_off >= 0) {
+        const Ctrl* c = p.ctrl;
+        const int row = c->film_per_sample ? b : c->stages[c->step].film_row;
+        film = c->film + (size_t)row * p.film_dim + p.film_off;
+    }
+    float* out_o = reinterpret_cast<float*>(p.out_o);
+    float* out_un = reinterpret_cast<float*>(p.out_unshuf);
+    float* out_up = reinterpret_cast<float*>(p.out_up);
+    const int ncb = p.C >> 3;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int c = g * cpg + e / HW, px = e % HW;
+        const size_t o = addr(e);
+        float y = (p.in[o] - mean) * rstd * p.gamma[c] + p.beta[c];
+        if (film) y = y * (film[c] + 1.0f) + film[p.C + c];
+        if (p.silu) y = y / (1.0f + expf(-y));
+        if (p.res) y += p.res[o];
+        if (p.out_m) p.out_m[o] = y;
+        if (out_o) out_o[o] = y;
+        const int h = px / p.W, w = px % p.W, cb = c >> 3, sub = c & 7;
+        if (out_un) {
+            const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
+            const int q = (h >> 1) * (p.W >> 1) + (w >> 1);
+            out_un[((size_t)(plane * p.B + b) * (HW >> 2) + q) * 8 + sub] = y;
+        }
+        if (out_up) {
+            const int W2 = p.W * 2;
+            for (int d = 0; d < 4; ++d) {
+                const int q = (2 * h + (d >> 1)) * W2 + 2 * w + (d & 1);
+                out_up[((size_t)(cb * p.B + b) * (HW * 4) + q) * 8 + sub] = y;
+            }
+        }
+    }
+}
+cudaError_t launch_gn_any(const GnParams& p, cudaStream_t s) {
+    if (p.o_is_bf16) return cudaErrorInvalidValue;
+    k_gn_any<<<p.B * p.groups, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// inpainting mask: NCHW fp32 [B,ch,H,W] -> per-level blocked 8-channel tensors (channels >= ch are zero) by the
+// bilinear rule of F.interpolate(mask, size=(h,w), mode='bilinear') (align_corners=False, no antialias; unet.py:338,362):
+// src = (dst + 0.5) * in/out - 0.5 clamped at 0, i1 = min(i0 + 1, in - 1).  Level 0 is a copy and also evaluates the
+// reference's bypass test torch.allclose(mask, 1) (unet.py:301: |m - 1| <= 1e-8 + 1e-5): *mode = 2 if any element fails.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mask_mode(int* mode, int value) { if (threadIdx.x == 0 && blockIdx.x == 0) *mode = value; }
+__global__ void __launch_bounds__(128) k_mask_prep(MaskPrepParams p) {
+    const int lvl = blockIdx.y, h = p.H >> lvl, w = p.W >> lvl, hw = h * w;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.B * hw) return;
+    const int b = idx / hw, px = idx % hw, oy = px / w, ox = px % w;
+    const float sy = (float)p.H / (float)h, sx = (float)p.W / (float)w;
+    float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < p.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.W - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.0f - ly1, lx1 = fx - (float)x0, lx0 = 1.0f - lx1;
+    float o[8];
+    bool not_ones = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        o[c] = 0.f;
+        if (c < p.ch) {
+            const float* m = p.mask + ((size_t)b * p.ch + c) * p.H * p.W;
+            if (lvl == 0) {
+                o[c] = m[px];
+                if (!(fabsf(o[c] - 1.0f) <= 1e-8f + 1e-5f)) not_ones = true;
+            } else {
+                const float t0 = __fadd_rn(__fmul_rn(lx0, m[y0 * p.W + x0]), __fmul_rn(lx1, m[y0 * p.W + x1]));
+                const float t1 = __fadd_rn(__fmul_rn(lx0, m[y1 * p.W + x0]), __fmul_rn(lx1, m[y1 * p.W + x1]));
+                o[c] = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+            }
+        }
+    }
+    store8(p.out[lvl] + ((size_t)b * hw + px) * 8, o);
+    if (not_ones) atomicMax(p.mode, 2);
+}
+cudaError_t launch_mask_prep(const MaskPrepParams& p, cudaStream_t s) {
+    k_mask_mode<<<1, 32, 0, s>>>(p.mode, p.mask ? 1 : 0);
+    if (p.mask) {
+        dim3 grid((p.B * p.H * p.W + 127) / 128, p.n_levels);
+        k_mask_prep<<<grid, 128, 0, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

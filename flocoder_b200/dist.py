@@ -29,8 +29,9 @@ def shard_cond(cond, lo: int, hi: int):
     if cond is None:
         return None
     out = dict(cond)
-    if out.get("class_cond") is not None:
-        out["class_cond"] = out["class_cond"][lo:hi]
+    for key in ("class_cond", "mask_cond"):          # the per-sample conditioning tensors (sampling.py:219-221)
+        if out.get(key) is not None:
+            out[key] = out[key][lo:hi]
     return out
 
 

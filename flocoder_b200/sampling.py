@@ -120,6 +120,7 @@ def generate_latents_rk4(model, shape, n_steps=50, cond=None, cfg_strength=3.0, 
         state = state.clone()                      # never integrate in place on the caller's tensor
     cls = _class_ids(model, cond)
     cfg = float(cfg_strength) if (cls is not None and cfg_strength) else 0.0
+    eng.set_mask(model.mask_of(cond), b)           # inpainting: the same mask for every evaluation (sampling.py:63,73)
     grid = ts.tolist()
     if len(grid) >= 2:
         if jitter_strength > 0:
@@ -166,6 +167,7 @@ def euler_latents(model, shape, sample_N, cond=None, source=None, eps=1e-3):
     out_dtype = x.dtype
     state = x.to(device=eng.device, dtype=torch.float32).contiguous().clone()
     cls = _class_ids(model, cond)
+    eng.set_mask(model.mask_of(cond), b)
     # the legacy loop feeds fl32(num_t) (ones*num_t in fp32) and multiplies the velocity by fl32(dt)
     ts32 = torch.tensor(times, dtype=torch.float64).to(torch.float32).tolist()
     eng.integrate(state, ts32, _lib.FLO_EULER_LEGACY, dt=dt, class_ids=cls, cfg_strength=0.0)

@@ -85,9 +85,7 @@ class Unet(nn.Module):
     def __init__(self, dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=4,
                  n_classes=10, mask_cond=False, use_checkpoint=False, compute_dtype: Optional[str] = None):
         super().__init__()
-        if mask_cond:
-            raise NotImplementedError(
-                "mask_cond=True (inpainting U-Net) is outside the B200 sampling path (SURVEY.md 8f N3)")
+        self.mask_cond = bool(mask_cond)              # inpainting U-Net (unet.py:214-235): fp32 kernels only
         self.use_checkpoint = use_checkpoint          # accepted for signature parity; inference only
         self.dim = dim
         self.dim_mults = tuple(int(m) for m in dim_mults)
@@ -112,6 +110,22 @@ class Unet(nn.Module):
             self.class_cond_mlp.put("0", nn.Embedding(n_classes, time_dim))
             self.class_cond_mlp.put("1", nn.Linear(time_dim, time_dim))
             self.class_cond_mlp.put("3", nn.Linear(time_dim, time_dim))
+
+        if self.mask_cond:                            # unet.py:214-235: nn.Sequential indices 0, 2, 4 / 0 hold the convs
+            self.mask_fusion_conv = _Holder()
+            self.mask_fusion_conv.put("0", nn.Conv2d(dim + channels, 2 * dim, 5, padding=2))
+            self.mask_fusion_conv.put("2", nn.Conv2d(2 * dim, 2 * dim, 3, padding=1))
+            self.mask_fusion_conv.put("4", nn.Conv2d(2 * dim, dim, 3, padding=1))
+            self.down_mask_fusions = nn.ModuleList()
+            for d_in, _ in in_out[:2]:
+                fuse = _Holder()
+                fuse.put("0", nn.Conv2d(d_in + channels, d_in, 3, padding=1))
+                self.down_mask_fusions.append(fuse)
+            self.up_mask_fusions = nn.ModuleList()
+            for _, d_out in list(reversed(in_out))[:2]:
+                fuse = _Holder()
+                fuse.put("0", nn.Conv2d(d_out + channels, d_out, 3, padding=1))
+                self.up_mask_fusions.append(fuse)
 
         # registration order (downs, ups, mid, final) fixes the state_dict order; construction
         # order (downs, mid, ups, final) fixes the RNG stream -- both as in unet.py:238-286
@@ -195,7 +209,7 @@ class Unet(nn.Module):
             self._engine = _lib.Engine(
                 dim=self.dim, channels=self.channels, dim_mults=self.dim_mults, groups=self.groups,
                 n_classes=self.n_classes, height=height, width=width, compute_dtype=key[1],
-                device=dev, state_dict=sd, flags=self.engine_flags)
+                device=dev, state_dict=sd, flags=self.engine_flags, mask_cond=self.mask_cond)
             self._engine_key = key
         return self._engine
 
@@ -207,15 +221,16 @@ class Unet(nn.Module):
     @staticmethod
     def split_cond(cond):
         """Returns the class-id tensor (or None) exactly as unet.py:298,313-320 would consume ``cond``."""
-        if key_usable(cond, "mask_cond"):
-            raise NotImplementedError("cond['mask_cond'] needs the inpainting U-Net (mask_cond=True), "
-                                      "which is outside the B200 sampling path")
         if cond is None:
             return None
         if not isinstance(cond, dict):
             # the reference's non-dict branch dies on warnings.DeprecationWarning (unet.py:318)
             raise TypeError("non-dict cond is not supported; use cond={'class_cond': LongTensor[B]}")
         return cond.get("class_cond")
+
+    def mask_of(self, cond):
+        """cond['mask_cond'] if this module consumes it (unet.py:298: key_usable and hasattr(self, 'mask_fusion_conv'))."""
+        return cond["mask_cond"] if (self.mask_cond and key_usable(cond, "mask_cond")) else None
 
     # ----------------------------------------------------------------- forward
     @torch.no_grad()
@@ -233,6 +248,7 @@ class Unet(nn.Module):
         time = time.to(device=x.device, dtype=torch.float32).reshape(-1)
         if time.numel() != b:
             raise ValueError(f"time must have {b} elements, got {time.numel()}")
+        eng.set_mask(self.mask_of(cond), b)
         v = eng.forward(x.to(torch.float32).contiguous(), time.contiguous(), cls)
         return v.to(x.dtype)
 
@@ -259,7 +275,10 @@ def infer_unet_config(state_dict) -> dict:
     if not mults:
         raise ValueError("state_dict has no 'downs.*' levels: not a flocoder U-Net checkpoint")
     emb = state_dict.get("class_cond_mlp.0.weight")
-    return {"dim": dim, "channels": channels, "dim_mults": mults, "n_classes": int(emb.shape[0]) if emb is not None else 0}
+    cfg = {"dim": dim, "channels": channels, "dim_mults": mults, "n_classes": int(emb.shape[0]) if emb is not None else 0}
+    if "mask_fusion_conv.0.weight" in state_dict:          # inpainting checkpoint (train_flow.py:291 mask_cond=inpainting)
+        cfg["mask_cond"] = True
+    return cfg
 
 
 def unet_from_checkpoint(checkpoint, device=None, compute_dtype=None, strict=False, **overrides) -> "Unet":

@@ -79,7 +79,8 @@ typedef struct flo_unet_cfg {
     int32_t height, width; /* latent H, W                           */
     int32_t compute_dtype; /* flo_dtype: FLO_F32 = fp32 CUDA-core path (<=1e-5 parity),
                               FLO_BF16 / FLO_F16 = 16-bit tcgen05 operands, fp32 accumulate */
-    int32_t mask_cond;     /* must be 0 (inpainting U-Net is out of scope) */
+    int32_t mask_cond;     /* Unet(mask_cond=...): 1 builds the inpainting U-Net with its mask-fusion branches
+                              (unet.py:214-235); FLO_F32 only */
     int32_t flags;         /* FLO_FLAG_*                            */
     int32_t device;        /* CUDA device ordinal                   */
 } flo_unet_cfg;
@@ -114,6 +115,14 @@ FLO_API size_t flo_workspace_bytes(flo_unet_t* h, int B);
  * class_ids: [B] int64 or NULL (cond['class_cond'], unet.py:315-316). */
 FLO_API int flo_unet_forward(flo_unet_t* h, const float* x, const float* time, const int64_t* class_ids, float* v,
                      int B, void* stream);
+
+/* cond['mask_cond'] for every following flo_unet_forward / flo_integrate call at batch size B (unet.py:298-305,
+ * 336-340,360-364).  mask: [B,C,H,W] fp32 NCHW (latent-shaped, as MaskEncoder produces it, inpainting.py:180-245) or
+ * NULL = no mask (every mask branch is skipped, as when key_usable(cond,'mask_cond') is false).  The call resizes the
+ * mask to every resolution level (F.interpolate bilinear) and evaluates the reference's all-ones bypass
+ * (torch.allclose(mask, 1), unet.py:301) on the device; no host synchronisation.  The state is per batch size and
+ * persists until the next call.  Handles built with mask_cond=0 accept only NULL. */
+FLO_API int flo_unet_set_mask(flo_unet_t* h, const float* mask, int B, void* stream);
 
 /* Whole trajectory on the device, no host synchronisation (replaces the loop of
  * generate_latents_rk4, sampling.py:116-117, with v_func_cfg, sampling.py:51-76, inside).

@@ -224,8 +224,6 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
                  cond: Optional[dict] = None, prec: Precision = FP32,
                  trace: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """unet.py:289-372.  ``time`` is already scaled by 999 (sampling.py:63)."""
-    if key_usable(cond, "mask_cond"):
-        raise NotImplementedError("mask_cond (inpainting) is outside the hot path (SURVEY.md 8f N3)")
     g = spec.groups
     tr = trace
     n_res = len(spec.in_out)
@@ -233,6 +231,17 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
     x = prec.act(_conv(sd, "init_conv", x, 0, prec, tensor_core=False))   # unet.py:295
     if tr is not None:
         tr["init_conv"] = x
+    # inpainting: the mask branches exist iff the module was built with mask_cond=True, i.e. iff the
+    # state dict holds their weights (unet.py:298 hasattr(self, 'mask_fusion_conv'))
+    use_mask = key_usable(cond, "mask_cond") and "mask_fusion_conv.0.weight" in sd
+    mask = cond["mask_cond"] if use_mask else None
+    if use_mask and not torch.allclose(mask, torch.ones_like(mask)):    # unet.py:301: all-ones mask bypasses the fusion
+        xf = torch.cat([x, mask], dim=1)                                # unet.py:302
+        xf = F.silu(_conv(sd, "mask_fusion_conv.0", xf, 2, prec))       # unet.py:215-221 (5x5, 3x3, 3x3; SiLU between)
+        xf = F.silu(_conv(sd, "mask_fusion_conv.2", xf, 1, prec))
+        x = _conv(sd, "mask_fusion_conv.4", xf, 1, prec)                # unet.py:305: no residual
+        if tr is not None:
+            tr["mask_fusion_conv"] = x
     r = x                                                              # unet.py:308 (clone)
     t = time_conditioning(sd, spec, time, cond)
     if tr is not None:
@@ -246,6 +255,11 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         x = resnet_block(sd, p + ".1", x, t, g, prec, tr)
         x = residual_prenorm(sd, p + ".2", x, linear_attention, prec, tr)
         skips.append(x)
+        if use_mask and i < 2 and f"down_mask_fusions.{i}.0.weight" in sd:          # unet.py:336-340
+            m = F.interpolate(mask, size=x.shape[-2:], mode="bilinear")
+            x = x + F.silu(_conv(sd, f"down_mask_fusions.{i}.0", torch.cat([x, m], dim=1), 1, prec))
+            if tr is not None:
+                tr[f"down_mask_fusions.{i}.0"] = x
         if i < n_res - 1:
             x = prec.act(downsample(sd, p + ".3", x, prec))
         else:
@@ -264,6 +278,11 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         x = torch.cat((x, skips.pop()), dim=1)
         x = resnet_block(sd, p + ".1", x, t, g, prec, tr)
         x = residual_prenorm(sd, p + ".2", x, linear_attention, prec, tr)
+        if use_mask and i < 2 and f"up_mask_fusions.{i}.0.weight" in sd:            # unet.py:360-364
+            m = F.interpolate(mask, size=x.shape[-2:], mode="bilinear")
+            x = x + F.silu(_conv(sd, f"up_mask_fusions.{i}.0", torch.cat([x, m], dim=1), 1, prec))
+            if tr is not None:
+                tr[f"up_mask_fusions.{i}.0"] = x
         if i < n_res - 1:
             x = prec.act(upsample(sd, p + ".3", x, prec))
         else:

@@ -55,8 +55,7 @@ def test_manifest_generic_dims():
 
 def test_unsupported_configs_are_explicit_errors():
     L = _lib.lib()
-    cfg = _lib.make_cfg(16, 4, (1, 2, 4, 8), 4, 0, 16, 16, "fp32", 0)
-    cfg.mask_cond = 1
+    cfg = _lib.make_cfg(16, 4, (1, 2, 4, 8), 4, 0, 16, 16, "bf16", 0, mask_cond=True)   # inpainting U-Net: fp32 path only
     with pytest.raises(NotImplementedError):
         _lib.check(L.flo_param_count(ctypes.byref(cfg)))
     assert b"mask_cond" in L.flo_last_error()
@@ -69,6 +68,22 @@ def test_unsupported_configs_are_explicit_errors():
     cfg = _lib.make_cfg(24, 4, (1, 2), 4, 0, 16, 16, "bf16", 0)       # bf16 path needs dim % 16 == 0
     with pytest.raises(NotImplementedError):
         _lib.check(L.flo_param_count(ctypes.byref(cfg)))
+
+
+def test_inpainting_manifest_matches_the_module():
+    """mask_cond=1: the mask-fusion parameters in the reference's registration order (unet.py:214-235), for the
+    midi_inpainting shape (dim = 8: two channels per GroupNorm group) as well."""
+    for dim, hw in ((16, 16), (8, 8)):
+        m = Unet(dim=dim, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, mask_cond=True)
+        cfg = _lib.make_cfg(dim, 4, (1, 2, 4, 8), 4, 0, hw, hw, "fp32", 0, mask_cond=True)
+        manifest = _lib.param_manifest(cfg)
+        sd = m.state_dict()
+        assert [n for n, _ in manifest] == list(sd.keys())
+        assert all(tuple(sd[n].shape) == shp for n, shp in manifest)
+        text = _lib.describe_plan(cfg, 8)
+        for op in ("mask_fusion_conv.0", "mask_fusion_conv.2", "mask_fusion_conv ", "down_mask_fusions.0.0", "down_mask_fusions.1.0",
+                   "up_mask_fusions.0.0", "up_mask_fusions.1.0"):
+            assert op in text, op
 
 
 def test_nfe_counts():

@@ -134,3 +134,32 @@ def test_generic_dims_equal_reference():
     t = torch.tensor([10.0, 900.0])
     with torch.no_grad():
         assert rel_l2(unet_forward(sd, spec, x, t), ref(x, t)) < 2e-6
+
+
+# ---- inpainting U-Net (mask_cond=True): the oracle's mask branches against the frozen reference outputs ----
+def inpaint_case(name):
+    import os
+    from conftest import GOLDEN_DIR
+    from flocoder_b200.unet import Unet
+    g = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
+    torch.manual_seed(g["model_seed"])
+    m = Unet(dim=g["dim"], channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, mask_cond=True)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return g, sd, UnetSpec(dim=g["dim"], dim_mults=(1, 2, 4, 8), channels=4, groups=4, n_classes=0)
+
+
+@pytest.mark.parametrize("name", ["inpaint_16", "midi_inpainting"])
+def test_inpainting_forward_and_integrators_match_golden(name):
+    g, sd, spec = inpaint_case(name)
+    shape = tuple(g["x0"].shape)
+    cond = {"mask_cond": g["mask_latents"]}
+    with torch.no_grad():
+        assert rel_l2(unet_forward(sd, spec, g["x0"], g["fwd_t"], cond=cond), g["fwd_v_mask"]) < 2e-6
+        assert rel_l2(unet_forward(sd, spec, g["x0"], g["fwd_t"]), g["fwd_v_nomask"]) < 2e-6
+        assert rel_l2(unet_forward(sd, spec, g["x0"], g["fwd_t"], cond={"mask_cond": torch.ones(shape)}), g["fwd_v_ones"]) < 2e-6
+        assert rel_l2(unet_forward(sd, spec, g["x0"], g["fwd_t"], cond={"mask_cond": g["mask_half"]}), g["fwd_v_half"]) < 2e-6
+    model = OracleModel(sd, spec)
+    x1, _ = oracle.generate_latents_rk4(model, shape, n_steps=10, cond=cond, source=g["x0"].clone())
+    assert rel_l2(x1, g["rk4_10_mask"]) < 2e-6
+    x1, _ = oracle.euler_sampler(model, shape, 10, cond=cond, source=g["x0"])
+    assert rel_l2(x1, g["euler_10_mask"]) < 2e-6

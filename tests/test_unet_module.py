@@ -37,16 +37,41 @@ def test_param_counts_match_survey():
         assert len(m.state_dict()) == n_tensors
 
 
-def test_mask_cond_is_an_explicit_error():
-    with pytest.raises(NotImplementedError):
-        Unet(dim=8, channels=4, mask_cond=True)
-    m = Unet(dim=16, channels=4, n_classes=0)
-    with pytest.raises(NotImplementedError):
-        Unet.split_cond({"mask_cond": torch.ones(1, 4, 16, 16)})
+def test_cond_handling_matches_the_reference():
     with pytest.raises(TypeError):
         Unet.split_cond(torch.arange(4))
     assert Unet.split_cond(None) is None
     assert Unet.split_cond({"class_cond": None}) is None
+    # unet.py:298: a mask is consumed only by a module built with mask_cond=True
+    m = Unet(dim=16, channels=4, n_classes=0)
+    assert m.mask_of({"mask_cond": torch.ones(1, 4, 16, 16)}) is None
+    mm = Unet(dim=16, channels=4, n_classes=0, mask_cond=True)
+    mask = torch.rand(1, 4, 16, 16)
+    assert mm.mask_of({"mask_cond": mask}) is mask and mm.mask_of({"mask_cond": None}) is None and mm.mask_of(None) is None
+
+
+@pytest.mark.parametrize("name", ["inpaint_16", "midi_inpainting"])
+def test_inpainting_unet_and_mask_encoder_seeded_init_match_reference(name):
+    """mask_cond=True: the mask-fusion parameters sit where the reference registers them (unet.py:214-235) and draw the
+    same RNG stream; MaskEncoder (inpainting.py:180-245) likewise."""
+    import os
+    from conftest import GOLDEN_DIR
+    from flocoder_b200.inpainting import MaskEncoder
+    g = torch.load(os.path.join(GOLDEN_DIR, f"{name}.pt"), weights_only=False)
+    torch.manual_seed(g["model_seed"])
+    m = Unet(dim=g["dim"], channels=4, dim_mults=[1, 2, 4, 8], n_classes=0, mask_cond=True)
+    assert list(m.state_dict().keys()) == g["sd_names"]
+    assert sum(p.numel() for p in m.parameters()) == g["n_params"]
+    torch.manual_seed(g["model_seed"] + 1)
+    enc = MaskEncoder().eval()
+    assert list(enc.state_dict().keys()) == g["enc_sd_names"]
+    if torch.__version__ != g["torch_version"]:
+        pytest.skip("torch version differs from the one the goldens were frozen with")
+    assert fingerprint(m.state_dict()) == g["sd_sha256"]
+    assert fingerprint(enc.state_dict()) == g["enc_sd_sha256"]
+    with torch.no_grad():
+        lat = enc(g["mask_pixels"])
+    assert torch.allclose(lat, g["mask_latents"], atol=1e-6, rtol=1e-6)
 
 
 def test_no_cpu_fallback():
