@@ -260,3 +260,38 @@ def test_sharded_sampler_over_nccl_uneven_shards(tmp_path, batch):
         assert rel_l2(full, ref) <= 2e-6, tag
         lo, hi = shard_bounds(batch, 2, 0)
         assert torch.equal(local, full[lo:hi])
+
+
+def test_generate_samples_flow_checkpoint_to_decoded_batch(tmp_path):
+    """SURVEY.md 8(f) N2, generate_samples.py:61-118,141-159: a {'model_state_dict': ...} checkpoint on disk ->
+    load_models_once (U-Net arguments from the tensors + the config's flow section) -> generate_batch -> sampler ->
+    latents and decoded images; the latents match the CPU oracle on the same noise."""
+    import flocoder_b200.generate as gen
+    from flocoder_b200.unet import Unet
+    torch.manual_seed(4321)
+    src = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=0)
+    sd = {k: v.detach().clone() for k, v in src.state_dict().items()}
+    path = tmp_path / "flow_test.pt"
+    torch.save({"model_state_dict": sd, "epoch": 1}, path)
+
+    class Codec(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.full((1,), 0.5))
+
+        def decode(self, z):
+            return torch.nn.functional.interpolate(z[:, :3] * self.w, scale_factor=8, mode="nearest")
+
+    config = {"image_size": 128, "codec": {"choice": "sd"}, "flow": {"dim_mults": [1, 2, 4, 8], "unet": {"n_classes": 0}}}
+    codec, vmodel = gen.load_models_once(str(path), config, device="cuda", codec=Codec(), compute_dtype="fp32")
+    assert gen.load_models(str(path), config, "cuda")[1] is vmodel          # cached: same path and config
+    latent_shape = gen.infer_latent_shape(config)
+    assert latent_shape == (4, 16, 16)
+    torch.manual_seed(7)
+    decoded, latents, nfe = gen.generate_batch(vmodel, codec, latent_shape, "rk4", 8, 3.0, "cuda", 6)
+    torch.manual_seed(7)
+    noise = torch.randn((6,) + latent_shape, device="cuda")
+    want, _ = oracle.generate_latents_rk4(OracleModel(sd, spec_for(0)), (6,) + latent_shape, n_steps=8, source=noise.cpu())
+    assert nfe == 32 and decoded.shape == (6, 3, 128, 128)
+    assert rel_l2(latents, want) <= 1e-5
+    assert torch.allclose(decoded.cpu(), torch.nn.functional.interpolate(latents.cpu()[:, :3] * 0.5, scale_factor=8, mode="nearest"))

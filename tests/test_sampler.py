@@ -97,3 +97,17 @@ def test_sampler_matches_unmodified_reference():
     assert torch.allclose(a[0], b[0], atol=1e-6) and torch.allclose(a[1], b[1], atol=1e-6) and a[2] == b[2]
     z = torch.rand(6, 1, 8, 8)
     assert torch.equal(sampling.g2rgb(z), ref_sampling.g2rgb(z)) and torch.equal(sampling.g2rgb(z, True), ref_sampling.g2rgb(z, True))
+
+
+def test_generate_samples_config_helpers():
+    """generate_samples.py:120-138 / general.py:50-75 without Hydra: section precedence and the latent shapes of the
+    BASELINE configs (sd: image_size // 8; vqgan: image_size // 2^num_downsamples)."""
+    from flocoder_b200.generate import infer_latent_shape, ldcfg
+    cfg = {"image_size": 128, "codec": {"choice": "sd", "num_downsamples": 3}, "flow": {"dim_mults": [1, 2, 4, 8], "unet": {"n_classes": 102}}}
+    assert infer_latent_shape(cfg) == (4, 16, 16)
+    assert ldcfg(cfg, "dim_mults") == [1, 2, 4, 8] and ldcfg(cfg, "num_downsamples") == 3 and ldcfg(cfg, "nope", 5) == 5
+    cfg = {"image_size": 128, "codec": {"choice": "vqgan", "num_downsamples": 4, "vq_embedding_dim": 4}}
+    assert infer_latent_shape(cfg) == (4, 8, 8)                  # configs/midi_inpainting.yaml
+    assert infer_latent_shape({"image_size": 32, "codec": {"choice": "resize"}}) == (3, 32, 32)
+    with pytest.raises(ValueError):
+        infer_latent_shape({"codec": {"choice": "other"}})
