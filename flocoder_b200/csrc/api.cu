@@ -263,6 +263,9 @@ struct Plan {
     float *y = nullptr, *acc = nullptr, *xs = nullptr, *vcond = nullptr, *film_ps = nullptr;
     int64_t* cls = nullptr;
     Ctrl* ctrl = nullptr;
+    int* pair_flags = nullptr;         // [B] arrival counters of the single-pass CFG combine (SF_CFG_2B; this plan's batch = 2 x caller's)
+    cudaGraphExec_t graph_c = nullptr, graph_c4 = nullptr;   // k_temb (stage time from the control block) + one / four forwards
+    int graph_c_cond = -1;             // conditional rows the captured k_temb node was built for
     int* mask_mode = nullptr;          // 0 no mask (default), 1 mask of all ones, 2 mask in use (flo_unet_set_mask)
     std::vector<void*> buf_ptr;
     std::vector<ConvUmmaParams> umma;   // per op (valid for conv ops on the bf16 path)
@@ -286,6 +289,8 @@ struct Plan {
     ~Plan() {                               // every exit path of get_plan releases what it has allocated so far
         if (graph) cudaGraphExecDestroy(graph);
         if (graph4) cudaGraphExecDestroy(graph4);
+        if (graph_c) cudaGraphExecDestroy(graph_c);
+        if (graph_c4) cudaGraphExecDestroy(graph_c4);
         if (base) cudaFree(base);
         if (dbg) cudaFree(dbg);
     }
@@ -829,7 +834,8 @@ static int get_plan(Handle& h, int B, Plan** out, cudaStream_t st) {
     const size_t cls_bytes = al((size_t)B * 8);
     pl->arena_bytes = s.fused ? 256 : al(h.arena_ps * (size_t)B);     // layer-by-layer activations
     const size_t farena_bytes = s.fused ? al(h.farena_ps * (size_t)B) : 0;   // stage-boundary tensors of the fused path
-    pl->total_bytes = pl->arena_bytes + farena_bytes + 4 * state_bytes + film_bytes + cls_bytes + 512;
+    const size_t flag_bytes = al((size_t)B * 4);
+    pl->total_bytes = pl->arena_bytes + farena_bytes + 4 * state_bytes + film_bytes + cls_bytes + flag_bytes + 512;
     cudaError_t e = cudaMalloc((void**)&pl->base, pl->total_bytes);
     if (e != cudaSuccess) { set_error("cudaMalloc of %zu workspace bytes for B=%d failed: %s", pl->total_bytes, B, cudaGetErrorString(e)); cudaGetLastError(); return FLO_ERR_NOMEM; }
     uint8_t* q = pl->base;
@@ -841,6 +847,7 @@ static int get_plan(Handle& h, int B, Plan** out, cudaStream_t st) {
     pl->vcond = (float*)q; q += state_bytes;
     pl->film_ps = (float*)q; q += film_bytes;
     pl->cls = (int64_t*)q; q += cls_bytes;
+    pl->pair_flags = (int*)q; q += flag_bytes;
     pl->ctrl = (Ctrl*)q; q += 256;
     pl->mask_mode = (int*)q;
     pl->buf_ptr.resize(h.bufs.size());
@@ -922,6 +929,7 @@ static TembParams temb_params(Handle& h) {
         p.wc3t = h.d_f32 + h.o_wc3t; p.bc3 = h.d_f32 + h.o_bc3;
     }
     p.wft = h.d_f32 + h.o_wft; p.bf = h.d_f32 + h.o_bf;
+    p.n_cond = -1;
     return p;
 }
 
@@ -1167,6 +1175,76 @@ static int integrate_impl(Handle* h, Plan* pl, float* y, const float* ts, int n_
     }
     const int n_eval = (int)evs.size();
     if (n_eval == 0) return FLO_OK;
+    // ---- classifier-free guidance as ONE forward over 2B samples per evaluation (fused path): rows [0,B) carry the class FiLM,
+    // rows [B,2B) the unconditional one; the final epilogue combines the halves (SF_CFG_2B).  Twice the CTAs per launch, half
+    // the launches, and the time embedding becomes a node of the replayed graph (it reads the stage time on the device).
+    if (use_cfg && s.fused && !getenv("FLO_CFG_TWO_PASS")) {
+        Plan* p2 = nullptr;
+        int rc2 = get_plan(*h, 2 * B, &p2, st);
+        if (rc2) return rc2;
+        const FStage& last = h->stages(p2->fvar).back();
+        if (last.kind == 0 && last.cp.nsplit == 1) {
+            rc2 = ensure_stage_capacity(*h, n_eval);
+            if (rc2) return rc2;
+            rc2 = ensure_host_staging(*h, n_eval);
+            if (rc2) return rc2;
+            const int slot = h->h_next;
+            h->h_next = (h->h_next + 1) & 3;
+            CUDA_TRY(cudaEventSynchronize(h->h_ev[slot]));
+            Stage* hs = h->h_stages[slot];
+            for (int e = 0; e < n_eval; ++e) {
+                Stage a{};
+                a.t_scaled = evs[e].t * t_scale; a.dt = evs[e].dt; a.dt6 = evs[e].dt6; a.kind = evs[e].kind; a.film_row = 0;
+                a.flags = SF_CFG_2B; a.eval_idx = e;
+                hs[e] = a;
+            }
+            CUDA_TRY(cudaMemcpyAsync(h->d_stages, hs, (size_t)n_eval * sizeof(Stage), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaEventRecord(h->h_ev[slot], st));
+            const size_t n = (size_t)B * s.channels * s.H * s.W;
+            CUDA_TRY(cudaMemcpyAsync(p2->xs, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(p2->xs + n, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(p2->cls, class_ids, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+            Ctrl c{};
+            c.step = 0; c.done_ctr = 0; c.film_per_sample = 1; c.n_stages = n_eval; c.cfg = cfg_strength; c.cfg_half = B;
+            c.y = y; c.acc = p2->acc; c.xs = p2->xs; c.vcond = p2->vcond; c.vout = nullptr; c.vtrace = v_trace;
+            c.film = p2->film_ps; c.stages = h->d_stages; c.pair_flags = p2->pair_flags;
+            CUDA_TRY(launch_setup_ctrl(p2->ctrl, c, nullptr, nullptr, st));
+            h->launches += 1;
+            TembParams tp = temb_params(*h);
+            tp.ctrl = p2->ctrl; tp.t = nullptr; tp.t_stride = 0; tp.cls = p2->cls; tp.n_cond = B; tp.n_rows = 2 * B; tp.film = p2->film_ps;
+            auto one_pass = [&](cudaStream_t ss) -> int {
+                if (launch_temb(tp, ss) != cudaSuccess) { set_error("k_temb launch failed"); return FLO_ERR_CUDA; }
+                for (int i = 0; i < n_units(*h); ++i) {
+                    int r = launch_unit(*h, *p2, i, ss);
+                    if (r) return r;
+                }
+                return FLO_OK;
+            };
+            const bool graphs = !(s.flags & FLO_FLAG_NO_GRAPH);
+            if (graphs && (!p2->graph_c || p2->graph_c_cond != B)) {
+                if (p2->graph_c) { cudaGraphExecDestroy(p2->graph_c); p2->graph_c = nullptr; }
+                if (p2->graph_c4) { cudaGraphExecDestroy(p2->graph_c4); p2->graph_c4 = nullptr; }
+                for (int reps = 1; reps <= 4; reps += 3) {
+                    cudaGraph_t g = nullptr;
+                    CUDA_TRY(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+                    int r = FLO_OK;
+                    for (int k = 0; k < reps && r == FLO_OK; ++k) r = one_pass(h->capture_stream);
+                    cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
+                    if (r == FLO_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(reps == 1 ? &p2->graph_c : &p2->graph_c4, g, 0);
+                    if (g) cudaGraphDestroy(g);
+                    if (r || ce != cudaSuccess) { if (!r) set_error("graph capture (CFG) failed: %s", cudaGetErrorString(ce)); return r ? r : FLO_ERR_CUDA; }
+                }
+                p2->graph_c_cond = B;
+            }
+            for (int e = 0; e < n_eval; ++e) {
+                if (graphs && e + 3 < n_eval) { CUDA_TRY(cudaGraphLaunch(p2->graph_c4, st)); e += 3; h->launches += 4 * (int64_t)(n_units(*h) + 1); continue; }
+                if (graphs) { CUDA_TRY(cudaGraphLaunch(p2->graph_c, st)); }
+                else { rc2 = one_pass(st); if (rc2) return rc2; }
+                h->launches += (int64_t)(n_units(*h) + 1);
+            }
+            return FLO_OK;
+        }
+    }
     const int n_pass = use_cfg ? 2 * n_eval : n_eval;
     int rc = ensure_stage_capacity(*h, n_pass);
     if (rc) return rc;

@@ -30,7 +30,9 @@ enum StageKind : int {
     ST_CFG_COND = 6   // vcond = k (conditional pass of classifier-free guidance, sampling.py:63)
 };
 enum StageFlags : int {
-    SF_CFG_COMBINE = 1   // this pass is the unconditional one: k = k + cfg*(vcond - k)  (sampling.py:74)
+    SF_CFG_COMBINE = 1,  // this pass is the unconditional one: k = k + cfg*(vcond - k)  (sampling.py:74)
+    SF_CFG_2B = 2        // ONE pass over 2B samples: [0,B) conditional, [B,2B) unconditional (ctrl.cfg_half = B); the later of
+                         // the two CTAs holding a sample's halves combines them and does the integrator update
 };
 
 struct Stage {
@@ -50,7 +52,7 @@ struct Ctrl {
     int film_per_sample;  // 1: FiLM row = sample index (per-sample time / class conditioning)
     int n_stages;
     float cfg;
-    int pad0;
+    int cfg_half;         // SF_CFG_2B: B (the forward runs on 2B samples); else 0
     float* y;             // [B,C,H,W] integrator state
     float* acc;           // [B,C,H,W] running k1+2k2+2k3+k4
     float* xs;            // [B,C,H,W] input of the current U-Net evaluation
@@ -59,6 +61,7 @@ struct Ctrl {
     float* vtrace;        // optional [n_eval,B,C,H,W]
     const float* film;    // FiLM table [rows][film_dim]
     const Stage* stages;
+    int* pair_flags;      // SF_CFG_2B: [B] arrival counters of the sample halves (zero between passes)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +128,9 @@ struct AttnParams {
 };
 
 struct TembParams {
+    const Ctrl* ctrl;                    // non-null: every row's time is the current ODE stage's (ctrl->stages[ctrl->step].t_scaled),
+                                         // so the launch can sit inside the replayed forward graph
+    int n_cond;                          // rows [0, n_cond) use their class id, the rest are unconditional (< 0: all rows)
     const float* t; int t_stride;        // time per row (already scaled); stride 0 = same for all rows
     const int64_t* cls;                  // class id per row or null
     int n_rows;
@@ -262,6 +268,7 @@ struct ChainParams {
     int max_c;                              // largest per-step channel count (sizes gpar and the tables of the warp-shuffle GroupNorm path)
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
+    int prod_lanes;                         // lanes of the producer warp that issue weight chunks (chunk cc -> lane cc % prod_lanes)
     int ring_off, ring_slot_bytes, n_ring, n_ring_deep;   // n_ring_deep: depth when one CTA owns the SM (chosen per plan)
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start

@@ -357,7 +357,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
         // ============================ producer ============================
         // TWO issuing lanes (chunk cc -> lane cc & 1): the bulk copies of one thread do not overlap and two is what an SM keeps in
         // flight (profiles/r02_stream_rate.txt: 31.7 -> 55 B/clk for 16 KB chunks)
-        if (lane < 2) {
+        if (dbg && lane == 8) {
+            // timeline only: the cycle at which weight chunks 8..15 LAND in the ring (the MMA warp only sees them when it gets there);
+            // walks every chunk in order so that the parity waits cannot alias an earlier phase of the same slot
+            for (int cc = 0; cc < 16 && cc < p.n_chunks; ++cc) {
+                mbar_wait(bar_full + 8 * (cc % n_ring), (uint32_t)(cc / n_ring) & 1u);
+                if (cc >= 8) dbg[104 + (cc - 8) * 3] = clock64();
+            }
+        }
+        const int NL = p.prod_lanes;
+        if (lane < NL) {
             const uint32_t ring_base = smem_base + p.ring_off, ring_slot_bytes = p.ring_slot_bytes;
             const uint2* wtab = reinterpret_cast<const uint2*>(smem + p.wtab_off);
             const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.wblob);
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
             // the weights do not depend on the previous kernel: fill the ring before waiting for it
             const int pre = min(n_ring, n_chunks);
             int cc = lane;
-            for (; cc < pre; cc += 2) issue(cc);
+            for (; cc < pre; cc += NL) issue(cc);
             griddep_wait();
             if (lane == 0 && n_loads > 0) {
                 uint32_t lbytes = 0;
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                 const CUtensorMap* maps[4] = {&tm0, &tm1, &tm2, &tm3};
                 for (int i = 0; i < n_loads; ++i) tma_load_5d(smem_base + p.load_off[i], maps[i], bar_load, 0, -1, -1, b0, 0);
             }
-            for (; cc < n_chunks; cc += 2) issue(cc);
+            for (; cc < n_chunks; cc += NL) issue(cc);
         }
     } else if (warp == W_MMA) {
         // ============================ MMA issuer (whole warp, warp-uniform; one elected lane issues) ============================
@@ -560,6 +569,72 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                             } break;
                             default: break;
                         }
+                    }
+                }
+            };
+            // ---- classifier-free guidance as ONE pass over 2B samples (SF_CFG_2B): rows [0,B) are the conditional evaluations, rows
+            // [B,2B) the unconditional ones of the same latents.  Every CTA publishes its velocities; of the two CTAs that hold the
+            // halves of a sample the LATER one (a per-sample arrival counter) forms v_nc + cfg (v_c - v_nc) (sampling.py:69-74) and
+            // does the integrator update, writing the next evaluation's input for both halves.  Barriers: all epilogue threads.
+            auto final_update_2b = [&](const float (&kacc)[(MT + 1) / 2][FINAL_MAX_CH], bool has_rows) {
+                float* const Y = ctrl->y; float* const ACC = ctrl->acc; float* const XS = ctrl->xs; float* const VC = ctrl->vcond;
+                float* const VT = ctrl->vtrace;
+                const float cfg_s = ctrl->cfg;
+                const int Bh = ctrl->cfg_half, nch = p.channels, dim = p.dim;
+                int* const arrived = reinterpret_cast<int*>(smem + p.xpart_off);      // [nb] (the N-split exchange area: unused here)
+                float kv[(MT + 1) / 2][FINAL_MAX_CH];
+#pragma unroll
+                for (int k = 0; k < (MT + 1) / 2; ++k) {
+#pragma unroll
+                    for (int co = 0; co < FINAL_MAX_CH; ++co) kv[k][co] = 0.f;
+                    if (!has_rows || (MT > 1 && wg + 2 * k >= MT) || !ri[k].valid) continue;
+                    const int b = b0 + ri[k].s;
+#pragma unroll
+                    for (int co = 0; co < FINAL_MAX_CH; ++co) {
+                        if (co >= nch) continue;
+                        kv[k][co] = kacc[k][co] + cpar[nch * dim + co];
+                        __stcg(VC + ((size_t)b * nch + co) * HW + ri[k].px, kv[k][co]);
+                    }
+                }
+                __threadfence();
+                epi_sync();
+                if (et < geo.nb) {
+                    int old = 0;
+                    const int b = b0 + et;
+                    if (b < geo.B) {
+                        const int bs = b >= Bh ? b - Bh : b;
+                        old = atomicAdd(ctrl->pair_flags + bs, 1);
+                        if (old == 1) { ctrl->pair_flags[bs] = 0; __threadfence(); }      // both halves are in: re-arm for the next pass
+                    }
+                    arrived[et] = old;
+                }
+                epi_sync();
+                const size_t plane = (size_t)Bh * nch * HW;
+#pragma unroll
+                for (int k = 0; k < (MT + 1) / 2; ++k) {
+                    if (!has_rows || (MT > 1 && wg + 2 * k >= MT) || !ri[k].valid) continue;
+                    if (arrived[ri[k].s] != 1) continue;
+                    const int b = b0 + ri[k].s;
+                    const bool uncond = b >= Bh;
+                    const int bs = uncond ? b - Bh : b, bp = uncond ? bs : bs + Bh;
+#pragma unroll
+                    for (int co = 0; co < FINAL_MAX_CH; ++co) {
+                        if (co >= nch) continue;
+                        const float other = __ldcg(VC + ((size_t)bp * nch + co) * HW + ri[k].px);
+                        const float vc = uncond ? other : kv[k][co], vnc = uncond ? kv[k][co] : other;
+                        const float v = __fadd_rn(vnc, __fmul_rn(cfg_s, __fsub_rn(vc, vnc)));
+                        const size_t o = ((size_t)bs * nch + co) * HW + ri[k].px;
+                        if (VT && sg.eval_idx >= 0) VT[(size_t)sg.eval_idx * plane + o] = v;
+                        float xn = 0.f;
+                        switch (sg.kind) {
+                            case ST_RK1: ACC[o] = v; xn = __fadd_rn(Y[o], __fmul_rn(__fmul_rn(sg.dt, v), 0.5f)); break;
+                            case ST_RK2: ACC[o] = __fadd_rn(ACC[o], __fmul_rn(2.0f, v)); xn = __fadd_rn(Y[o], __fmul_rn(__fmul_rn(sg.dt, v), 0.5f)); break;
+                            case ST_RK3: ACC[o] = __fadd_rn(ACC[o], __fmul_rn(2.0f, v)); xn = __fadd_rn(Y[o], __fmul_rn(sg.dt, v)); break;
+                            case ST_RK4: xn = __fadd_rn(Y[o], __fmul_rn(sg.dt6, __fadd_rn(ACC[o], v))); Y[o] = xn; break;
+                            case ST_EULER: xn = __fadd_rn(Y[o], __fmul_rn(v, sg.dt)); Y[o] = xn; break;
+                            default: break;
+                        }
+                        XS[o] = xn; XS[o + plane] = xn;
                     }
                 }
             };
@@ -980,7 +1055,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                     });
                 }
                 }
-                if (is_final && cend > cbeg) final_update(kacc);
+                if (is_final) {
+                    if (sg.flags & SF_CFG_2B) final_update_2b(kacc, cend > cbeg);
+                    else if (cend > cbeg) final_update(kacc);
+                }
                 if (is_final) {
                     // the last CTA to finish advances the stage counter (every CTA has read ctrl->step by now)
                     epi_sync();

@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(128) k_temb(TembParams p) {
     float* t = h + p.time_dim;           // [time_dim]
     float* c = t + p.time_dim;           // [time_dim]
     const int row = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-    const float tv = p.t[(size_t)row * p.t_stride];
+    const float tv = p.ctrl ? p.ctrl->stages[p.ctrl->step].t_scaled : p.t[(size_t)row * p.t_stride];
     const int half = p.dim >> 1;
     for (int j = tid; j < half; j += NT) {           // unet.py:28-29: [sin | cos]
         const float a = tv * p.freqs[j];
@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(128) k_temb(TembParams p) {
         for (int i = 0; i < p.time_dim; ++i) a = fmaf(h[i], p.w2t[i * p.time_dim + j], a);
         t[j] = a;
     }
-    if (p.cls != nullptr && p.n_classes > 0) {       // class_cond_mlp (unet.py:207-212,316)
+    if (p.cls != nullptr && p.n_classes > 0 && (p.n_cond < 0 || row < p.n_cond)) {       // class_cond_mlp (unet.py:207-212,316)
         __syncthreads();
         long long id = p.cls[row];
         if (id < 0) id = 0;

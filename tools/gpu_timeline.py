@@ -44,7 +44,7 @@ for i, name in enumerate(names):
         continue
     if tl[105]:
         print("   weight chunks 8..15 (cycles rel. kernel start): " + " | ".join(
-            f"wait {tl[104+3*k]-start} issue {tl[105+3*k]-start} full {tl[106+3*k]-start}" for k in range(8) if tl[105+3*k]))
+            f"issue {tl[105+3*k]-start} landed {tl[104+3*k]-start if tl[104+3*k] else -1} seen {tl[106+3*k]-start}" for k in range(8) if tl[105+3*k]))
     for s in range(8):
         row = tl[s * 8: s * 8 + 8]
         if row[2] == 0:
