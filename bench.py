@@ -556,7 +556,9 @@ def torch_eager_cuda(cfg, dev, batch):
         sd32 = seeded_state_dict(cfg["n_classes"])
         x0 = torch.randn(batch, *LATENT, generator=torch.Generator().manual_seed(5678))
         old_tf32 = torch.backends.cudnn.allow_tf32
-        for tag, dt in (("fp32_tf32_off", torch.float32), ("bf16", torch.bfloat16)):
+        # the *_no_host_syncs rows drop the reference's per-evaluation .item() / empty_cache() / synchronize(): eager PyTorch at its best
+        for tag, dt, synced in (("fp32_tf32_off", torch.float32, True), ("bf16", torch.bfloat16, True),
+                                ("fp32_tf32_off_no_host_syncs", torch.float32, False), ("bf16_no_host_syncs", torch.bfloat16, False)):
             torch.backends.cudnn.allow_tf32 = False
             sd = {k: (v.to(dev).to(dt) if v.is_floating_point() else v.to(dev)) for k, v in sd32.items()}
             inner = OracleModel(sd, spec)
@@ -564,9 +566,10 @@ def torch_eager_cuda(cfg, dev, batch):
             class Synced:
                 def __call__(self, x, tt, cond=None):
                     v = inner(x, tt, cond=cond)
-                    _ = v.sum().item()
-                    torch.cuda.empty_cache()
-                    torch.cuda.synchronize()
+                    if synced:
+                        _ = v.sum().item()
+                        torch.cuda.empty_cache()
+                        torch.cuda.synchronize()
                     return v
 
                 def parameters(self):

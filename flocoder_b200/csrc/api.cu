@@ -115,7 +115,10 @@ static int make_spec(const flo_unet_cfg* c, Spec& s) {
         set_error("latent %dx%d is not divisible by 2^(levels-1)=%d", s.H, s.W, div);
         return FLO_ERR_INVALID;
     }
-    if (s.H * s.W > 256) { set_error("latents larger than 256 pixels are not supported by the attention kernel"); return FLO_ERR_UNSUPPORTED; }
+    if (s.H * s.W > 256 && (s.bf16 || (s.H * s.W) % 256 || s.H * s.W > 4096)) {
+        set_error("latents larger than 256 pixels run on the fp32 path only (tiled linear attention), with H*W a multiple of 256 up to 4096");
+        return FLO_ERR_UNSUPPORTED;
+    }
     if (s.groups < 1) { set_error("groups < 1"); return FLO_ERR_INVALID; }
     for (size_t i = 0; i < s.dims.size(); ++i) {
         const int C = s.dims[i];
@@ -1034,7 +1037,7 @@ int flo_unet_create(flo_unet_t** out, const flo_unet_cfg* cfg, const void* const
     rc = b.build();
     if (rc) return rc;
     // the layer-wise GroupNorm kernel (fp32 path, FLO_FLAG_LAYERWISE) keeps one (sample, group) unit in the registers of a CTA
-    if (!h->spec.fused)
+    if (!h->spec.fused && h->spec.bf16)
         for (const Op& op : h->ops)
             if (op.kind == OP_GN && (op.C / op.groups) * op.H * op.W > 8192) {
                 set_error("GroupNorm '%s' normalises %d elements per (sample, group); the layer-wise path holds at most 8192 "
@@ -1178,12 +1181,15 @@ static int integrate_impl(Handle* h, Plan* pl, float* y, const float* ts, int n_
     // ---- classifier-free guidance as ONE forward over 2B samples per evaluation (fused path): rows [0,B) carry the class FiLM,
     // rows [B,2B) the unconditional one; the final epilogue combines the halves (SF_CFG_2B).  Twice the CTAs per launch, half
     // the launches, and the time embedding becomes a node of the replayed graph (it reads the stage time on the device).
-    if (use_cfg && s.fused && !getenv("FLO_CFG_TWO_PASS")) {
+    // Class conditioning WITHOUT guidance takes the same route with B rows: its per-sample FiLM table is then also built by
+    // the in-graph k_temb, so the four-pass graph is kept (the host-launched k_temb per pass is what broke it).
+    if (use_cls && s.fused && !getenv("FLO_CFG_TWO_PASS")) {
         Plan* p2 = nullptr;
-        int rc2 = get_plan(*h, 2 * B, &p2, st);
+        const int Bf = use_cfg ? 2 * B : B;
+        int rc2 = get_plan(*h, Bf, &p2, st);
         if (rc2) return rc2;
         const FStage& last = h->stages(p2->fvar).back();
-        if (last.kind == 0 && last.cp.nsplit == 1) {
+        if (last.kind == 0 && (last.cp.nsplit == 1 || !use_cfg)) {
             rc2 = ensure_stage_capacity(*h, n_eval);
             if (rc2) return rc2;
             rc2 = ensure_host_staging(*h, n_eval);
@@ -1195,23 +1201,23 @@ static int integrate_impl(Handle* h, Plan* pl, float* y, const float* ts, int n_
             for (int e = 0; e < n_eval; ++e) {
                 Stage a{};
                 a.t_scaled = evs[e].t * t_scale; a.dt = evs[e].dt; a.dt6 = evs[e].dt6; a.kind = evs[e].kind; a.film_row = 0;
-                a.flags = SF_CFG_2B; a.eval_idx = e;
+                a.flags = use_cfg ? SF_CFG_2B : 0; a.eval_idx = e;
                 hs[e] = a;
             }
             CUDA_TRY(cudaMemcpyAsync(h->d_stages, hs, (size_t)n_eval * sizeof(Stage), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaEventRecord(h->h_ev[slot], st));
             const size_t n = (size_t)B * s.channels * s.H * s.W;
             CUDA_TRY(cudaMemcpyAsync(p2->xs, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(p2->xs + n, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (use_cfg) CUDA_TRY(cudaMemcpyAsync(p2->xs + n, y, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(p2->cls, class_ids, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
             Ctrl c{};
-            c.step = 0; c.done_ctr = 0; c.film_per_sample = 1; c.n_stages = n_eval; c.cfg = cfg_strength; c.cfg_half = B;
+            c.step = 0; c.done_ctr = 0; c.film_per_sample = 1; c.n_stages = n_eval; c.cfg = cfg_strength; c.cfg_half = use_cfg ? B : 0;
             c.y = y; c.acc = p2->acc; c.xs = p2->xs; c.vcond = p2->vcond; c.vout = nullptr; c.vtrace = v_trace;
             c.film = p2->film_ps; c.stages = h->d_stages; c.pair_flags = p2->pair_flags;
             CUDA_TRY(launch_setup_ctrl(p2->ctrl, c, nullptr, nullptr, st));
             h->launches += 1;
             TembParams tp = temb_params(*h);
-            tp.ctrl = p2->ctrl; tp.t = nullptr; tp.t_stride = 0; tp.cls = p2->cls; tp.n_cond = B; tp.n_rows = 2 * B; tp.film = p2->film_ps;
+            tp.ctrl = p2->ctrl; tp.t = nullptr; tp.t_stride = 0; tp.cls = p2->cls; tp.n_cond = B; tp.n_rows = Bf; tp.film = p2->film_ps;
             auto one_pass = [&](cudaStream_t ss) -> int {
                 if (launch_temb(tp, ss) != cudaSuccess) { set_error("k_temb launch failed"); return FLO_ERR_CUDA; }
                 for (int i = 0; i < n_units(*h); ++i) {

@@ -705,7 +705,7 @@ cudaError_t launch_gn(const GnParams& p, cudaStream_t s) {
     while (nt < 256 && nt * GN_VPT < nvec) nt <<= 1;
     // prefer ~4 vectors per thread when the unit is big enough to fill more warps
     while (nt < 256 && nvec / nt > 4) nt <<= 1;
-    if (nt * GN_VPT < nvec) return cudaErrorInvalidValue;
+    if (nt * GN_VPT < nvec) return p.o_is_bf16 ? cudaErrorInvalidValue : launch_gn_any(p, s);   // unit larger than a CTA's registers
     const int grid = p.B * p.groups;
     if (p.o_is_bf16) k_gn<__nv_bfloat16><<<grid, nt, 0, s>>>(p);
     else k_gn<float><<<grid, nt, 0, s>>>(p);
@@ -910,10 +910,124 @@ __global__ void __launch_bounds__(LA_THREADS) k_linattn(AttnParams p) {
         }
     }
 }
+// Same block for n > 256 pixels (fp32 path; e.g. the 32x32 "latents" of configs/flowers_resize.yaml): the sample does not fit in
+// shared memory, so the pixels stream through in tiles of 256.  Pass 1: per-channel max of k over all pixels; pass 2: per tile
+// exp(k - max) and the running sums  ksum[d] += sum_n e,  ctx[d][e] += sum_n e v[e,n]  (ctx / ksum == softmax_n(k) v^T, unet.py:142-146);
+// pass 3: per tile softmax_d(q) * 32^-0.5 and out[e][n] = sum_d ctx[d][e] q[d,n]  (unet.py:141,143,148).
+constexpr int LA_TILE = 256;
+__global__ void __launch_bounds__(LA_THREADS) k_linattn_big(AttnParams p) {
+    extern __shared__ float sm[];
+    const int n = p.n, ld = LA_TILE + 1;
+    float* sq = sm;                 // [32][ld]  (k tile in pass 2, q tile in pass 3)
+    float* sv = sq + 32 * ld;       // [32][ld]
+    float* ctx = sv + 32 * ld;      // [32][33]
+    float* kmax = ctx + 32 * 33;    // [32]
+    float* ksum = kmax + 32;        // [32]
+    float* red = ksum + 32;         // [8][32]
+    const int b = blockIdx.x >> 2, head = blockIdx.x & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* qkv = reinterpret_cast<const float*>(p.qkv);
+    auto src = [&](int which, int cbl, int px) { return qkv + ((size_t)((which * 16 + head * 4 + cbl) * p.B + b) * n + px) * 8; };
+    // ---- pass 1: kmax[d]
+    {
+        float m[32];
+#pragma unroll
+        for (int d = 0; d < 32; ++d) m[d] = -INFINITY;
+        for (int px = tid; px < n; px += LA_THREADS)
+#pragma unroll
+            for (int cbl = 0; cbl < 4; ++cbl) {
+                float x[8];
+                load8(src(1, cbl, px), x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[cbl * 8 + j] = fmaxf(m[cbl * 8 + j], x[j]);
+            }
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+            const float w = warp_max(m[d]);
+            if (lane == 0) red[warp * 32 + d] = w;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float w = red[tid];
+            for (int k = 1; k < LA_THREADS / 32; ++k) w = fmaxf(w, red[k * 32 + tid]);
+            kmax[tid] = w;
+        }
+        __syncthreads();
+    }
+    // ---- pass 2: ksum, ctx over the tiles; warp w owns d = 4w..4w+3, lane = e
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, ks[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t0 = 0; t0 < n; t0 += LA_TILE) {
+        for (int it = tid; it < 8 * LA_TILE; it += LA_THREADS) {
+            const int which = 1 + it / (4 * LA_TILE), rem = it % (4 * LA_TILE), cbl = rem / LA_TILE, px = rem % LA_TILE;
+            float x[8];
+            load8(src(which, cbl, t0 + px), x);
+            float* dst = (which == 1 ? sq : sv) + (cbl * 8) * ld + px;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j * ld] = which == 1 ? expf(x[j] - kmax[cbl * 8 + j]) : x[j];
+        }
+        __syncthreads();
+        const float* k0 = sq + (warp * 4) * ld;
+        const float* vv = sv + lane * ld;
+        for (int px = 0; px < LA_TILE; ++px) {
+            const float x = vv[px];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = fmaf(k0[j * ld + px], x, a[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float sacc = 0.f;
+            for (int px = lane; px < LA_TILE; px += 32) sacc += k0[j * ld + px];
+            ks[j] += warp_sum(sacc);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ctx[(warp * 4 + j) * 33 + lane] = a[j] / ks[j];
+    __syncthreads();
+    // ---- pass 3: q softmax over d, out
+    float* out = reinterpret_cast<float*>(p.out);
+    for (int t0 = 0; t0 < n; t0 += LA_TILE) {
+        for (int it = tid; it < 4 * LA_TILE; it += LA_THREADS) {
+            const int cbl = it / LA_TILE, px = it % LA_TILE;
+            float x[8];
+            load8(src(0, cbl, t0 + px), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sq[(cbl * 8 + j) * ld + px] = x[j];
+        }
+        __syncthreads();
+        {
+            const int px = tid;                                   // LA_TILE == LA_THREADS
+            float qv[32], m = -INFINITY, ssum = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) { qv[d] = sq[d * ld + px]; m = fmaxf(m, qv[d]); }
+#pragma unroll
+            for (int d = 0; d < 32; ++d) { qv[d] = expf(qv[d] - m); ssum += qv[d]; }
+#pragma unroll
+            for (int d = 0; d < 32; ++d) qv[d] = (qv[d] / ssum) * 0.17677669529663687f;
+#pragma unroll 1
+            for (int cbl = 0; cbl < 4; ++cbl) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = cbl * 8 + j;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 32; ++d) acc = fmaf(ctx[d * 33 + e], qv[d], acc);
+                    o[j] = acc;
+                }
+                store8(out + ((size_t)((head * 4 + cbl) * p.B + b) * n + t0 + px) * 8, o);
+            }
+        }
+        __syncthreads();
+    }
+}
+static size_t linattn_big_smem() { return (size_t)(2 * 32 * (LA_TILE + 1) + 32 * 33 + 64 + 8 * 32) * sizeof(float); }
 static size_t linattn_smem(int n) { return (size_t)(3 * 32 * (n + 1) + 32 * 33) * sizeof(float); }
 cudaError_t simt_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_gn_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM + 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gn_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GNT_MAX_SMEM + 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_linattn_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)linattn_big_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_linattn<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)linattn_smem(256));
@@ -922,8 +1036,12 @@ cudaError_t simt_configure() {
                                 (int)linattn_smem(256));
 }
 cudaError_t launch_linattn(const AttnParams& p, cudaStream_t s) {
+    if (p.n > 256) {
+        if (p.is_bf16 || p.n % LA_TILE) return cudaErrorInvalidValue;
+        k_linattn_big<<<p.B * 4, LA_THREADS, linattn_big_smem(), s>>>(p);
+        return cudaGetLastError();
+    }
     const size_t smem = linattn_smem(p.n);
-    if (p.n > 256) return cudaErrorInvalidValue;
     if (p.is_bf16) k_linattn<__nv_bfloat16><<<p.B * 4, LA_THREADS, smem, s>>>(p);
     else k_linattn<float><<<p.B * 4, LA_THREADS, smem, s>>>(p);
     return cudaGetLastError();

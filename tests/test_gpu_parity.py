@@ -348,13 +348,32 @@ def test_other_unet_shapes_fused_vs_fp32_path(dim, mults, hw, ncls):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim,mults,hw,dtype", [(16, [1, 2, 4, 8], 32, "fp16"), (32, [1, 2, 4, 8], 16, "fp16"), (64, [1, 2], 16, "fp32")])
+@pytest.mark.parametrize("dim,mults,hw,dtype", [(16, [1, 2, 4, 8], 32, "fp16"), (32, [1, 2, 4, 8], 16, "fp16"), (72, [1, 2], 16, "fp32")])
 def test_unsupported_shapes_fail_loudly(dim, mults, hw, dtype):
     """Outside the supported envelope the library refuses at plan time; it never falls back."""
     from flocoder_b200.unet import Unet
     m = Unet(dim=dim, channels=4, dim_mults=mults, n_classes=0, compute_dtype=dtype).cuda().eval()
     with pytest.raises(NotImplementedError):
         m(torch.randn(2, 4, hw, hw).cuda(), torch.rand(2).cuda() * 999)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,channels,mults,hw", [(32, 3, [1, 2, 4, 8], 32), (64, 4, [1, 2], 16)])
+def test_fp32_path_large_latents_and_groupnorm_units_vs_oracle(dim, channels, mults, hw):
+    """The fp32 path beyond the 16-bit envelope: configs/flowers_resize.yaml (3 x 32 x 32 "latents", Unet(dim=32): 1024 pixels ->
+    tiled linear attention, GroupNorm(1, 32) over 32768 elements -> the generic GroupNorm kernel) and dim = 64 at 16 x 16."""
+    from flocoder_b200.unet import Unet
+    torch.manual_seed(11)
+    m = Unet(dim=dim, channels=channels, dim_mults=mults, n_classes=0, compute_dtype="fp32")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    spec = UnetSpec(dim=dim, dim_mults=tuple(mults), channels=channels, groups=4, n_classes=0)
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(3, channels, hw, hw, generator=gen)
+    t = torch.rand(3, generator=gen) * 999
+    with torch.no_grad():
+        want = unet_forward(sd, spec, x, t)
+    assert rel_l2(m(x.cuda(), t.cuda()), want) <= FP32_STEP_TOL
 
 
 @pytest.mark.gpu

@@ -318,6 +318,13 @@ def test_single_pass_cfg_matches_two_pass_and_reference(goldens, compute_dtype, 
     # repeated calls re-use the captured graphs and the re-armed arrival counters
     again, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, cond=cond, cfg_strength=3.0, source=x0)
     assert torch.equal(again, one)
+    # class conditioning without guidance: B rows through the same in-graph time embedding
+    x1, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, cond=cond, cfg_strength=0, source=x0)
+    assert rel_l2(x1, g["rk4_10_cls_nocfg"]) <= 1e-2
+    monkeypatch.setenv("FLO_CFG_TWO_PASS", "1")
+    x2, _ = sampling.generate_latents_rk4(m, SHAPE, n_steps=10, cond=cond, cfg_strength=0, source=x0)
+    monkeypatch.delenv("FLO_CFG_TWO_PASS")
+    assert torch.equal(x1, x2)                   # same kernels, same rows, same FiLM table: bit-identical
 
 
 @pytest.mark.parametrize("B", [5, 37, 300])
@@ -336,3 +343,25 @@ def test_single_pass_cfg_ragged_batches_vs_fp32_path(B):
     solo, _ = sampling.generate_latents_rk4(m16, (1, 4, 16, 16), n_steps=5, cond={"class_cond": cls[B // 2: B // 2 + 1]}, cfg_strength=2.5,
                                             source=x[B // 2: B // 2 + 1])
     assert rel_l2(a[B // 2: B // 2 + 1], solo) <= 1e-3
+
+
+@pytest.mark.parametrize("compute_dtype,tol", [("fp32", 1e-5), ("fp16", 2e-3)])
+def test_three_channel_latents_midi_vqgan_3d_gray(compute_dtype, tol):
+    """configs/midi_vqgan_3d_gray.yaml: vq_embedding_dim = 3 -> latents (3, 16, 16), Unet(dim=16, channels=3): the init / final 1x1
+    convolutions with a channel count that is not 4, against the CPU oracle."""
+    from flocoder_b200.unet import Unet
+    torch.manual_seed(77)
+    m = Unet(dim=16, channels=3, dim_mults=[1, 2, 4, 8], n_classes=0, compute_dtype=compute_dtype)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    spec = UnetSpec(dim=16, dim_mults=(1, 2, 4, 8), channels=3, groups=4, n_classes=0)
+    gen = torch.Generator().manual_seed(78)
+    x = torch.randn(6, 3, 16, 16, generator=gen)
+    t = torch.rand(6, generator=gen) * 999
+    with torch.no_grad():
+        want = unet_forward(sd, spec, x, t)
+    assert rel_l2(m(x.cuda(), t.cuda()), want) <= tol
+    from flocoder_b200 import sampling
+    x1, _ = sampling.generate_latents_rk4(m, (6, 3, 16, 16), n_steps=5, source=x.cuda())
+    want1, _ = oracle.generate_latents_rk4(OracleModel(sd, spec), (6, 3, 16, 16), n_steps=5, source=x)
+    assert rel_l2(x1, want1) <= tol

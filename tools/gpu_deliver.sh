@@ -18,3 +18,6 @@ echo "full-capture rc=$?"
 timeout 200 python tools/gpu_profile.py bf16 4096 layerwise > gpurun_out/layerwise_b4096.txt 2>&1
 timeout 300 python bench.py --steps 5 --warmup 3 --batch 1024 --no-cpu > gpurun_out/bench_b1024.json 2> gpurun_out/bench_b1024.err; echo "b1024 rc=$?"
 timeout 300 python bench.py --steps 5 --warmup 3 --dtype fp16 --no-cpu > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err; echo "fp16 rc=$?"
+timeout 300 python bench.py --steps 5 --warmup 3 --cfg 3.0 --no-cpu > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err; echo "cfg3 rc=$?"
+timeout 300 python bench.py --steps 3 --warmup 3 --config c5 --no-cpu > gpurun_out/bench_c5_1gpu.json 2> gpurun_out/bench_c5_1gpu.err; echo "c5 rc=$?"
+timeout 200 python tools/gpu_timeline.py bf16 1024 > gpurun_out/timeline_B1024.txt 2>&1

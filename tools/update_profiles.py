@@ -5,7 +5,9 @@ G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
 for src, dst in [("bench.json", "r02_bench_fused_bf16_B256.json"), ("bench_ref.json", "r02_bench_reference_arm.json"),
                  ("bench_b1024.json", "r02_bench_fused_bf16_B1024.json"), ("bench_fp16.json", "r02_bench_fused_fp16_B256.json"),
                  ("timeline.txt", "r02_stage_timeline_fused_bf16_B256.txt"), ("launches.csv", "r02_launches_fused_bf16_B256.csv"),
-                 ("layerwise_b4096.txt", "r02_event_profile_layerwise_bf16_B4096.txt")]:
+                 ("layerwise_b4096.txt", "r02_event_profile_layerwise_bf16_B4096.txt"),
+                 ("bench_cfg3.json", "r02_bench_fused_bf16_B256_cfg3.json"), ("bench_c5_1gpu.json", "r02_bench_c5_stl_sd_euler100_B4096_1gpu.json"),
+                 ("timeline_B1024.txt", "r02_stage_timeline_fused_bf16_B1024.txt")]:
     if os.path.isfile(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "r02_full_forward.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
