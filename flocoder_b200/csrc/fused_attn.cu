@@ -275,10 +275,16 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             __syncwarp();
         }
     } else {
-        const int quad = warp & 3, half = warp >> 2;           // TMEM lane quadrant; which warp group
+        const int quad = warp & 3, grp = warp >> 2;            // TMEM lane quadrant; which warp group
         const int r = quad * 32 + lane;                        // row inside an M tile == TMEM lane
-        const int et = half * 128 + r;                         // epilogue thread index
-        const int t0 = half, tstep = EW >> 2;                  // M tiles / samples are dealt round-robin to the warp groups
+        const int et = grp * 128 + r;                          // epilogue thread index
+        // EW = 4: one warp group does everything; EW = 8: M tiles / samples are dealt round-robin to two warp groups; EW = 16 (a
+        // sample spans two M tiles): tile = grp & 1 and the two groups of a tile split the q/k/v channels (cpart = grp >> 1) --
+        // the softmax epilogues are chains of TMEM loads, shuffles and MUFU ops, and four warps per scheduler hide what two cannot
+        const int half = EW >= 8 ? (grp & 1) : 0;
+        const int t0 = half, tstep = EW >= 8 ? 2 : 1;
+        const int cpart = EW == 16 ? (grp >> 1) : 0, ncp = EW == 16 ? 2 : 1;
+        const int ch_lo = cpart * (NCH / ncp), ch_hi = ch_lo + NCH / ncp;      // this thread's q/k/v channels in the softmax epilogues
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         auto esync = [&]() { named_bar_sync(1, n_epi); };
         float* kmax = reinterpret_cast<float*>(smem + p.kmax_off);          // [nb][128]
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             for (int t = t0; t < p.n_mtiles; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
-                for (int c32 = 0; c32 < NCH; c32 += 32) {
+                for (int c32 = ch_lo; c32 < ch_hi; c32 += 32) {
                     uint32_t ua[16], ub[16];
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c32), ua);
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c32 + 16), ub);
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
-                for (int c16 = 0; c16 < NCH; c16 += 16) {
+                for (int c16 = ch_lo; c16 < ch_hi; c16 += 16) {
                     uint32_t ku[16], vu[16];
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_k + t * NCH + c16), ku);
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_v + t * NCH + c16), vu);
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
                     *reinterpret_cast<uint4*>(vd + plane) = pack8(vv + 8, p.fmt);
                 }
-                if (valid) {
+                if (valid && cpart == 0) {
                     const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
                     *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)(NCH >> 3) * plane + row_off) = pack8(ones, p.fmt);
                 }
@@ -412,10 +418,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 for (int s = t0; s < p.nb; s += tstep) {
                     if (h >= HC) break;                      // head split: rows 64..127 of the context accumulator are not ours (warp-uniform)
                     uint32_t u0[16], u1[16], us[16];
+                    // (with two channel groups per tile each takes 16 of the row's 32 context columns)
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + h * 32), u0);
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + h * 32 + 16), u1);
                     tmem_ld16_issue(tlane + (uint32_t)(p.col_ctx + s * (NCH + 16) + NCH), us);
                     tmem_ld_wait();
+                    const int e_lo = cpart * (32 / ncp), e_hi = e_lo + 32 / ncp;
                     float c0[16], c1[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { c0[j] = __uint_as_float(u0[j]); c1[j] = __uint_as_float(u1[j]); }
@@ -423,6 +431,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     uint8_t* base = smem + p.ct_off + (uint32_t)(s * HC + h) * 2048u + (uint32_t)(d >> 3) * 512u + (uint32_t)(d & 7) * 2u;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
+                        if (e < e_lo || e >= e_hi) continue;
                         const float val = (e < 16 ? c0[e] : c1[e - 16]) * inv;
                         const uint32_t u = pack2(val, 0.f, p.fmt);
                         *reinterpret_cast<uint16_t*>(base + (uint32_t)(e >> 3) * 128u + (uint32_t)(e & 7) * 16u) = (uint16_t)(u & 0xFFFFu);
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
                 // two heads per iteration (four TMEM loads in flight, two independent softmax chains); max and sum as
                 // 4-way trees instead of 32-long dependent chains
-                for (int h2 = 0; h2 < HC; h2 += 2) {
+                for (int h2 = cpart * (HC / ncp); h2 < (cpart + 1) * (HC / ncp); h2 += 2) {
                     uint32_t qu[2][32];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const int px = t * 128 + r;
                     const bool valid = px < n && b0 + s < p.B;
                     const uint32_t row_off = (uint32_t)(s * n + px) * 16u;
-                    for (int c32 = 0; c32 < NCH; c32 += 32) {
+                    for (int c32 = ch_lo; c32 < ch_hi; c32 += 32) {
                         uint32_t ua[16], ub[16];
                         tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * NCH + c32), ua);
                         tmem_ld16_issue(tlane + (uint32_t)(p.col_out + (s * mtS + t) * NCH + c32 + 16), ub);
@@ -600,6 +609,17 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         }
         if (dbg && r == 0) dbg[19] = clock64();
         // ================= last EPI: to_out bias -> GroupNorm(1,C) -> + x2 -> global =================
+        // the residual rows of this thread's first tile are requested BEFORE waiting for the to_out MMAs: their L2 round trip
+        // (~800 cycles) otherwise sits on the critical path between the statistics barrier and the stores
+        uint4 pre_xa = make_uint4(0, 0, 0, 0), pre_xb = pre_xa;
+        if (!p.full && HS == 1 && t0 < p.n_mtiles && cpart == 0) {
+            const int rd = t0 * 128 + r, s = rd >> lgn, px = rd & (n - 1);
+            if (s < p.nb && b0 + s < p.B) {
+                const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
+                pre_xa = xsrc[(size_t)(0 * p.B + b0 + s) * n + px];
+                pre_xb = xsrc[(size_t)(1 * p.B + b0 + s) * n + px];
+            }
+        }
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
         if (dbg && r == 0) dbg[26] = clock64();
@@ -700,7 +720,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
         } else {
         if (!p.full) {
-            for (int t = t0; t < p.n_mtiles; t += tstep) {
+            // (the C output channels are not split: with 16 epilogue warps the second channel group only keeps the barriers)
+            for (int t = t0; t < p.n_mtiles && cpart == 0; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 float sx = 0.f, sq = 0.f;
@@ -792,7 +813,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
         } else {
-            for (int t = t0; t < p.n_mtiles; t += tstep) {
+            for (int t = t0; t < p.n_mtiles && cpart == 0; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const int b = b0 + s;
@@ -811,8 +832,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
                 // the residual rows of the NEXT channel chunk are requested before this chunk is processed
-                uint4 xa = make_uint4(0, 0, 0, 0), xb = xa;
-                if (valid) { xa = xsrc[(size_t)(0 * p.B + b) * n + px]; xb = xsrc[(size_t)(1 * p.B + b) * n + px]; }
+                uint4 xa = pre_xa, xb = pre_xb;
+                if (valid && t != t0) { xa = xsrc[(size_t)(0 * p.B + b) * n + px]; xb = xsrc[(size_t)(1 * p.B + b) * n + px]; }
                 for (int c16 = 0; c16 < C; c16 += 16) {
                     uint4 na = make_uint4(0, 0, 0, 0), nb4 = na;
                     if (valid && c16 + 16 < C) {

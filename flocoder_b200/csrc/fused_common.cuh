@@ -62,7 +62,7 @@ __device__ __forceinline__ void unpack8t(uint4 u, float* v) {
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
     }
 }
-constexpr int ATTN_MAX_THREADS = 320;   // k_attn with 8 epilogue warps
+constexpr int ATTN_MAX_THREADS = 576;   // k_attn with 16 epilogue warps (16x16 level) + producer + MMA issuer
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, EPI_THREADS); }
 
 

@@ -44,7 +44,7 @@ extern "C" {
 typedef enum flo_status {
     FLO_OK = 0,
     FLO_ERR_INVALID = -1,     /* bad argument (ValueError in Python) */
-    FLO_ERR_UNSUPPORTED = -2, /* feature outside the built path, e.g. mask_cond (NotImplementedError) */
+    FLO_ERR_UNSUPPORTED = -2, /* feature outside the built path, e.g. mask_cond with a 16-bit compute type (NotImplementedError) */
     FLO_ERR_CUDA = -3,        /* CUDA runtime / driver failure (RuntimeError) */
     FLO_ERR_NOMEM = -4
 } flo_status;

@@ -27,6 +27,10 @@ def test_shard_bounds_cover_the_batch():
     c = shard_cond({"class_cond": torch.arange(8)}, 2, 5)
     assert c["class_cond"].tolist() == [2, 3, 4]
     assert shard_cond({"class_cond": None}, 0, 2) == {"class_cond": None}
+    # the inpainting mask is per sample too (sampling.py:221) and is sliced with the noise
+    m = torch.arange(8 * 4 * 2 * 2, dtype=torch.float32).reshape(8, 4, 2, 2)
+    c = shard_cond({"class_cond": torch.arange(8), "mask_cond": m}, 5, 8)
+    assert torch.equal(c["mask_cond"], m[5:8]) and c["class_cond"].tolist() == [5, 6, 7]
 
 
 def _free_port():
