@@ -269,6 +269,8 @@ struct ChainParams {
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
     int prod_lanes;                         // lanes of the producer warp that issue weight chunks (chunk cc -> lane cc % prod_lanes)
+    int early_pdl;                          // 1: griddepcontrol.launch_dependents at kernel start (this grid leaves SMs idle: the next
+                                            // stage's CTAs become resident there and run their prologue / weight prefetch meanwhile)
     int ring_off, ring_slot_bytes, n_ring, n_ring_deep;   // n_ring_deep: depth when one CTA owns the SM (chosen per plan)
     int stats_off, bar_off, smem_bytes, tmem_cols;
     int tab_off, tab_n;                     // per-K16-slice A operand start addresses (>>4), built at kernel start
@@ -291,6 +293,7 @@ struct ChainParams {
 // mid-block full attention (unet.py:99-122), one kernel, `nb` samples per CTA
 struct AttnFusedParams {
     int epi_warps;                          // 4, or 8 when a sample spans two M tiles (one tile per warp group)
+    int early_pdl;                          // 1: launch_dependents at kernel start (see ChainParams)
     int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
                                             // n_mtiles = 128-row tiles of the dense rows (s*n + p)
     int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)

@@ -313,6 +313,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
     const int ones_off = p.ones_off;
     long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
+    // a grid that leaves SMs idle lets the next stage become resident at once: its prologue, TMEM allocation and weight
+    // prefetch run beside this kernel instead of after its last epilogue (every read of our output is behind its griddep_wait)
+    if (p.early_pdl) griddep_launch();
 
     if (warp == W_PROD && lane == 0) {
         for (int i = 0; i < n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }

@@ -102,6 +102,42 @@ __device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, 
 }
 
 
+// Warp-uniform variant (every lane of the warp calls it; `valid` predicates the stores).  The lanes of one image row are W
+// consecutive lanes (px = row index & (n - 1), rows = TMEM lanes), so for the nearest-x2 copy each lane fetches, by shuffle, the
+// blocks of the two source pixels whose copies land at output columns w and w + W: the W lanes of a row then write W * 16
+// CONTIGUOUS bytes per store (whole 32-byte sectors) instead of four half-filled sectors per lane -- the scattered form ran at
+// one sector per cycle and cost 9.5k cycles for the C = 128 output of the 2x2 level (profiles/r02_attn_small_timeline.txt).
+__device__ __forceinline__ void attn_write_out_w(const AttnFusedParams& p, int b, int px, int c16, const float* v, bool valid) {
+    if (!p.out_up || p.W < 2) {
+        if (valid) attn_write_out(p, b, px, c16, v);
+        return;
+    }
+    const int ncb = p.C >> 3;
+    const int lgW = 31 - __clz(p.W), W = p.W, W2 = 2 * W;
+    const int h = px >> lgW, w = px & (W - 1);
+    const int lane = (int)(threadIdx.x & 31), base = lane - w;
+    const int src0 = base + (w >> 1), src1 = base + ((w + W) >> 1);
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        const int cb = (c16 >> 3) + hb;
+        const uint4 u = pack8(v + hb * 8, p.fmt);
+        uint4 a, c;
+        a.x = __shfl_sync(0xffffffffu, u.x, src0); a.y = __shfl_sync(0xffffffffu, u.y, src0);
+        a.z = __shfl_sync(0xffffffffu, u.z, src0); a.w = __shfl_sync(0xffffffffu, u.w, src0);
+        c.x = __shfl_sync(0xffffffffu, u.x, src1); c.y = __shfl_sync(0xffffffffu, u.y, src1);
+        c.z = __shfl_sync(0xffffffffu, u.z, src1); c.w = __shfl_sync(0xffffffffu, u.w, src1);
+        if (!valid) continue;
+        if (p.out) reinterpret_cast<uint4*>(p.out)[(size_t)(cb * p.B + b) * p.n + px] = u;
+        if (p.out_un) {
+            const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
+            const int q = (h >> 1) * (W >> 1) + (w >> 1);
+            reinterpret_cast<uint4*>(p.out_un)[(size_t)(plane * p.B + b) * (p.n >> 2) + q] = u;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out_up) + (size_t)(cb * p.B + b) * (p.n * 4) + (2 * h) * W2;
+        dst[w] = a; dst[w + W] = c; dst[W2 + w] = a; dst[W2 + w + W] = c;
+    }
+}
+
 // Column maximum over the lanes of a segment for 16 channels held per lane.  A butterfly would move all 16 values at
 // every step (16 shuffles x log2(seg)); here every step also halves the channels a lane is responsible for, so the
 // exchange costs 8 + 4 + 2 + 1 (+1) shuffles.  On return lane L holds `CNT` channels starting at channel `chan`.
@@ -163,6 +199,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     const int b0 = (HS > 1 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * p.nb;
     const uint32_t bar_r = tmem_slot + 8, bar_d = bar_r + 8, bar_s = bar_d + 8;      // head split: one-shot cluster hand-offs
     if (p.dbg && tid == 0 && blockIdx.x == 0) p.dbg[100] = global_ns();
+    if (p.early_pdl) griddep_launch();      // see k_chain
     const int n = p.n, n_pad = p.n_pad, C = p.C;
     const uint32_t plane = (uint32_t)p.plane_bytes;
     const uint32_t xh_plane = (uint32_t)(p.nb * n) * 16u;
@@ -850,8 +887,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                             const float y = (v[j] + bias[c16 + j] - ms.x) * ms.y * gamma[c16 + j] + beta[c16 + j];
                             v[j] = y + x2[j];
                         }
-                        attn_write_out(p, b, px, c16, v);
                     }
+                    attn_write_out_w(p, b, px, c16, v, valid);
                     xa = na; xb = nb4;
                 }
             }
@@ -931,7 +968,15 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.bar_off + 16 * MAX_WSTAGES + 24);
     const int b0 = (int)blockIdx.x * p.nb;
     const int C = p.C;
-    const uint32_t plane = 2048u;                      // 128 rows x 16 bytes
+    const uint32_t plane = 2048u;                      // 128 rows x 16 bytes (operand slot of the attention output)
+    // Small batches run FEWER samples per CTA than the 128 / NPX that fill the M tile (planner): the kernel is a latency chain
+    // whose CUDA-core core, staging traffic and global stores are per-SM throughput, so half-empty tiles on four times the SMs
+    // finish sooner.  The input tile is then nb * NPX rows per plane; accumulator rows past it are junk that nobody reads.
+    const uint32_t in_plane = (uint32_t)(p.nb * NPX) * 16u;
+    const int live_rows = p.nb * NPX;
+    long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+    if (dbg && tid == 0) dbg[100] = global_ns();
+    if (p.early_pdl) griddep_launch();                 // see k_chain
     if (warp == w_prod && lane == 0) {
         for (int i = 0; i < p.n_ring; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_load, 1);
@@ -945,48 +990,82 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int qkv_bytes = p.qkv_S * 128 * 32, o_bytes = p.o_S * C * 32;
+    if (dbg && tid == 0) { dbg[64] = clock64(); dbg[101] = global_ns(); }
 
+    // All weights are resident (no ring): the k / v / q streams (C/16 K16 slices x 4 KB each) land in the k~ / v staging area,
+    // which is dead until the projections have completed, the to_out stream in its own 32 KB; four bulk copies from four lanes
+    // at kernel start, i.e. under the previous kernel's tail (programmatic launch).  Streaming them through an 8 KB ring ran
+    // at ~13 B/clk AFTER the input tile had arrived: 7.4k of a 22k-cycle kernel at C = 128 (profiles/r02_attn_small_timeline.txt).
+    const uint32_t qkv_stream = (uint32_t)(p.qkv_chunks * qkv_bytes), o_stream = (uint32_t)(p.o_chunks * o_bytes);
+    const uint32_t wk_smem = smem_base + p.p_off, wv_smem = wk_smem + qkv_stream, wq_smem = wv_smem + qkv_stream;
+    const uint32_t wo_smem = smem_base + p.ring_off;
     if (warp == w_prod) {
-        if (lane < 2) {
-            // two issuing lanes (chunk g -> lane g & 1): the bulk copies of one thread do not overlap (profiles/r02_stream_rate.txt)
-            const int total = 3 * p.qkv_chunks + p.o_chunks, pre = min(ATTN_RING, total);
-            int g = lane;
-            for (; g < pre; g += 2) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, 0);
-            griddep_wait();          // weights are constants; the activations come from the previous kernel
-            if (lane == 0) {
-                mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * plane);
-                tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
-            }
-            for (; g < total; g += 2) attn_issue_chunk(p, smem_base, bar_full, bar_empty, g, qkv_bytes, o_bytes, 0);
+        if (lane < 4) {
+            const uint16_t* src = lane == 0 ? p.wblob + p.wk_off : lane == 1 ? p.wblob + p.wv_off : lane == 2 ? p.wblob + p.wq_off : p.wblob + p.wo_off;
+            const uint32_t dst = lane == 0 ? wk_smem : lane == 1 ? wv_smem : lane == 2 ? wq_smem : wo_smem;
+            const uint32_t bytes = lane == 3 ? o_stream : qkv_stream;
+            mbar_expect_tx(bar_full + 8 * lane, bytes);
+            bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(src), bytes, bar_full + 8 * lane);
+        }
+        griddep_wait();              // weights are constants; the activations come from the previous kernel
+        if (lane == 0) {
+            mbar_expect_tx(bar_load, (uint32_t)(C >> 3) * in_plane);
+            tma_load_5d(smem_base + p.xh_off, &tm_xh, bar_load, 0, 0, 0, b0, 0);
         }
     } else if (warp == w_mma) {
-        RingA rs{0};
+        // 1x1 conv over the K-major operand slot at xh_off (128 rows, planes of 2 KB) with a resident weight stream
+        auto conv = [&](uint32_t w_smem, uint32_t bar, int n, int slices, int col, uint32_t a_plane) {
+            const uint32_t idesc = make_idesc16(128, n, p.fmt, 0, 0);
+            const uint32_t hi = (128u >> 4) | (1u << 14);
+            uint32_t a_lo = (((smem_base + p.xh_off) >> 4) & 0x3FFFu) | (((a_plane >> 4) & 0x3FFFu) << 16);
+            uint32_t b_lo = ((w_smem >> 4) & 0x3FFFu) | ((((uint32_t)n * 16u >> 4) & 0x3FFFu) << 16);
+            const uint32_t a_step = (2u * a_plane) >> 4, b_step = (uint32_t)n * 32u >> 4;
+            mbar_wait(bar, 0);
+            tc_fence_after();
+            if (elect_one()) {
+                for (int sl = 0; sl < slices; ++sl) {
+                    umma_bf16(tmem_base + (uint32_t)col, desc64(a_lo, hi), desc64(b_lo, hi), idesc, sl > 0 ? 1u : 0u);
+                    a_lo += a_step; b_lo += b_step;
+                }
+            }
+            __syncwarp();
+        };
         mbar_wait(bar_load, 0);
         tc_fence_after();
-        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_k, p.qkv_chunks, p.qkv_S);
-        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_v, p.qkv_chunks, p.qkv_S);
-        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, 128, 128, 0u, p.col_q, p.qkv_chunks, p.qkv_S);
+        if (dbg && lane == 0) dbg[0] = clock64();
+        conv(wk_smem, bar_full, 128, C >> 4, p.col_k, in_plane);
+        conv(wv_smem, bar_full + 8, 128, C >> 4, p.col_v, in_plane);
+        conv(wq_smem, bar_full + 16, 128, C >> 4, p.col_q, in_plane);
+        if (dbg && lane == 0) dbg[1] = clock64();
         if (elect_one()) umma_commit(bar_mma);
         __syncwarp();
         named_bar_sync(2, n_epi + 32);       // the attention output is in the operand slot (which reuses the input tile: every
         tc_fence_after();                    // projection that read it has completed, the epilogue waited for bar_mma)
-        attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, plane, C, C, 0u, p.col_proj, p.o_chunks, p.o_S);
+        if (dbg && lane == 0) dbg[24] = clock64();
+        conv(wo_smem, bar_full + 24, C, 8, p.col_proj, plane);
+        if (dbg && lane == 0) dbg[25] = clock64();
         if (elect_one()) umma_commit(bar_mma);
         __syncwarp();
     } else {
         const int quad = warp & 3, part = warp >> 2;           // TMEM lane quadrant; which quarter of the channels / which head
-        const int half = part & 1;
         const int r = quad * 32 + lane;                        // dense row = s * NPX + pixel == TMEM lane
         const int et = tid;
         const int s_loc = r >> LGN, px = r & (NPX - 1);        // sample within the CTA, pixel
         const int b = b0 + s_loc;
-        const bool valid = b < p.B;
+        const bool wact = quad * 32 < live_rows;               // warp-uniform: this warp's rows hold samples
+        const bool valid = r < live_rows && b < p.B;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         auto esync = [&]() { named_bar_sync(1, n_epi); };
         uint8_t* kst = smem + p.p_off;                         // k~ (linear) / k (full): [128 rows][SM_KP]
         uint8_t* vst = smem + p.v_off;
+        // 16-byte column swizzle of the staging rows: EPI-B reads ONE row per sample at a time (the lanes of a sample broadcast),
+        // and the rows of the 32 / NPX samples of a warp are NPX * 528 bytes apart = the same banks (2112 = 64 mod 128 at NPX = 4,
+        // 8448 = 0 at NPX = 16: a 4- / 2-way conflict on every load).  XOR-ing the float4 index with a per-sample code (NPX = 4:
+        // bits 1-2 of the sample index -- odd / even samples already sit 64 bytes apart; NPX = 16: bit 0) puts the samples of a
+        // warp in distinct 16-byte bank groups; the row writes of EPI-A stay conflict-free (four wavefronts per 512-byte store).
+        const uint32_t swz = NPX == 4 ? (uint32_t)((s_loc >> 1) & 3) : (uint32_t)(s_loc & 1);
         float* scr = reinterpret_cast<float*>(smem + p.kmax_off) + warp * (2 * SPW * 16);      // per warp: max[SPW][16], sum[SPW][16]
-        float2* hstat = reinterpret_cast<float2*>(smem + p.stats_off);                          // [2 halves][128 / NPX samples]
+        float2* hstat = reinterpret_cast<float2*>(smem + p.stats_off);                          // [4 channel groups][32]: per-sample partial statistics of the last epilogue
         float* par = reinterpret_cast<float*>(hstat + 2 * 64);                                  // [3][128]: bias, gamma, beta
         for (int c = et; c < C; c += n_epi) {
             par[c] = p.fblob[p.bo_off + c];
@@ -994,14 +1073,16 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
             par[256 + c] = LINEAR ? p.fblob[p.beta_off + c] : 0.0f;
         }
         griddep_wait();
+        if (dbg && et == 0) dbg[5] = clock64();
         // the residual rows are requested now: an exposed L2 round trip in the last epilogue otherwise
         const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
-        const int cb0 = half * (C >> 4);                       // this thread's channel blocks in the last epilogue: [cb0, cb0 + C/16)
         mbar_wait(bar_load, 0);
+        if (dbg && et == 0) dbg[6] = clock64();
         mbar_wait(bar_mma, 0);
         tc_fence_after();
+        if (dbg && et == 0) dbg[2] = clock64();
         // ================= EPI-A: this thread's 32 channels of row r: k (column softmax over the sample's pixels) and v =================
-        for (int c16 = part * 32; c16 < part * 32 + 32; c16 += 16) {
+        for (int c16 = part * 32; c16 < part * 32 + 32 && wact; c16 += 16) {
             uint32_t ku[16], vu[16];
             tmem_ld16_issue(tlane + (uint32_t)(p.col_k + c16), ku);
             tmem_ld16_issue(tlane + (uint32_t)(p.col_v + c16), vu);
@@ -1038,29 +1119,25 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
                 }
                 __syncwarp();                                   // the scratch rows are rewritten by the next chunk
             }
-            float4* kd = reinterpret_cast<float4*>(kst + (uint32_t)r * SM_KP + (uint32_t)c16 * 4u);
-            float4* vd = reinterpret_cast<float4*>(vst + (uint32_t)r * SM_KP + (uint32_t)c16 * 4u);
+            float4* kd = reinterpret_cast<float4*>(kst + (uint32_t)r * SM_KP);
+            float4* vd = reinterpret_cast<float4*>(vst + (uint32_t)r * SM_KP);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-                kd[k4] = make_float4(kv[4 * k4], kv[4 * k4 + 1], kv[4 * k4 + 2], kv[4 * k4 + 3]);
-                vd[k4] = make_float4(vv[4 * k4], vv[4 * k4 + 1], vv[4 * k4 + 2], vv[4 * k4 + 3]);
+                const uint32_t f4 = (uint32_t)((c16 >> 2) + k4) ^ swz;
+                kd[f4] = make_float4(kv[4 * k4], kv[4 * k4 + 1], kv[4 * k4 + 2], kv[4 * k4 + 3]);
+                vd[f4] = make_float4(vv[4 * k4], vv[4 * k4 + 1], vv[4 * k4 + 2], vv[4 * k4 + 3]);
             }
         }
-        esync();
-        // ================= EPI-B: head `part` of row r =================
-        const int row_s0 = s_loc << LGN;                        // first row of this row's sample
-        {
-            const int h = part;
-            float q[32];
-            {
-                uint32_t qa[16], qb[16];
-                tmem_ld16_issue(tlane + (uint32_t)(p.col_q + h * 32), qa);
-                tmem_ld16_issue(tlane + (uint32_t)(p.col_q + h * 32 + 16), qb);
-                tmem_ld_wait();
+        // q of (row r, head `part`) out of tensor memory: softmax over the 32 head channels, then * 32^-0.5 (unet.py:141-143), or
+        // q * scale for the mid attention (unet.py:113)
+        auto load_q = [&](float (&q)[32]) {
+            uint32_t qa[16], qb[16];
+            tmem_ld16_issue(tlane + (uint32_t)(p.col_q + part * 32), qa);
+            tmem_ld16_issue(tlane + (uint32_t)(p.col_q + part * 32 + 16), qb);
+            tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { q[j] = __uint_as_float(qa[j]); q[16 + j] = __uint_as_float(qb[j]); }
-            }
-            if (LINEAR) {                                       // softmax over the 32 head channels, then * 32^-0.5 (unet.py:141-143)
+            for (int j = 0; j < 16; ++j) { q[j] = __uint_as_float(qa[j]); q[16 + j] = __uint_as_float(qb[j]); }
+            if (LINEAR) {
                 float m4[4] = {q[0], q[1], q[2], q[3]};
 #pragma unroll
                 for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], q[j]);
@@ -1073,20 +1150,100 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
                 for (int j = 0; j < 32; ++j) q[j] *= inv;
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) q[j] *= 0.17677669529663687f;       // q * scale (unet.py:113)
+                for (int j = 0; j < 32; ++j) q[j] *= 0.17677669529663687f;
             }
+        };
+        // Quarter tile (32 live rows, the small-batch plan): twelve of the sixteen epilogue warps have no rows, and the attention
+        // core of one (row, head) per thread is a serial chain of 64 (2x2) / 256 (4x4) 16-byte shared-memory loads that the register
+        // budget keeps from overlapping (9k cycles at 4x4 with ONE warp per scheduler).  There the q~ rows go through shared memory
+        // too (staging rows 32.., free in this mode) and FOUR threads share a (row, head): each takes a quarter of the key pixels
+        // for S = q~ . k~, the four exchange S by shuffles, and each produces 8 of the head's 32 output channels.
+        const bool quarter = live_rows == 32;
+        uint8_t* qst = kst + 32u * SM_KP;
+        if (quarter && wact) {
+            float q[32];
+            load_q(q);
+            float4* qd = reinterpret_cast<float4*>(qst + (uint32_t)r * SM_KP);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+                qd[(uint32_t)(part * 8 + k4) ^ swz] = make_float4(q[4 * k4], q[4 * k4 + 1], q[4 * k4 + 2], q[4 * k4 + 3]);
+        }
+        if (dbg && et == 0) dbg[4] = clock64();
+        esync();
+        if (dbg && et == 0) dbg[10] = clock64();
+        // ================= EPI-B: the attention core =================
+        const int row_s0 = s_loc << LGN;                        // first row of this row's sample
+        if (quarter) {
+            constexpr int MPT = NPX / 4;                        // key pixels per thread in the S phase: m = j, j + 4, ...
+            const int j = et & 3, row = (et >> 2) & 31, h = et >> 7;
+            const int s2 = row >> LGN, rs0 = s2 << LGN;
+            const uint32_t sw = NPX == 4 ? (uint32_t)((s2 >> 1) & 3) : (uint32_t)(s2 & 1);
+            float q[32];
+            {
+                const float4* qr = reinterpret_cast<const float4*>(qst + (uint32_t)row * SM_KP + (uint32_t)h * 128u);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 t4 = qr[(uint32_t)c4 ^ sw];
+                    q[4 * c4] = t4.x; q[4 * c4 + 1] = t4.y; q[4 * c4 + 2] = t4.z; q[4 * c4 + 3] = t4.w;
+                }
+            }
+            float Sp[MPT];
+#pragma unroll
+            for (int i = 0; i < MPT; ++i) {
+                const float4* kr = reinterpret_cast<const float4*>(kst + (uint32_t)(rs0 + j + 4 * i) * SM_KP + (uint32_t)h * 128u);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 kk = kr[(uint32_t)c4 ^ sw];
+                    a0 = fmaf(q[c4 * 4], kk.x, a0); a1 = fmaf(q[c4 * 4 + 1], kk.y, a1);
+                    a2 = fmaf(q[c4 * 4 + 2], kk.z, a2); a3 = fmaf(q[c4 * 4 + 3], kk.w, a3);
+                }
+                Sp[i] = (a0 + a1) + (a2 + a3);
+            }
+            float S[NPX];
+#pragma unroll
+            for (int i = 0; i < MPT; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) S[jj + 4 * i] = __shfl_sync(0xffffffffu, Sp[i], (lane & ~3) | jj);
+            if (!LINEAR) {                                      // softmax over the key pixels (unet.py:116-118)
+                float m = S[0];
+#pragma unroll
+                for (int k = 1; k < NPX; ++k) m = fmaxf(m, S[k]);
+                float sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < NPX; ++k) { S[k] = fast_exp(S[k] - m); sum += S[k]; }
+                const float inv = fast_rcp(sum);
+#pragma unroll
+                for (int k = 0; k < NPX; ++k) S[k] *= inv;
+            }
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4* vr = reinterpret_cast<const float4*>(vst + (uint32_t)(rs0 + m) * SM_KP + (uint32_t)h * 128u);
+                const float4 va = vr[(uint32_t)(2 * j) ^ sw], vb = vr[(uint32_t)(2 * j + 1) ^ sw];
+                o[0] = fmaf(S[m], va.x, o[0]); o[1] = fmaf(S[m], va.y, o[1]); o[2] = fmaf(S[m], va.z, o[2]); o[3] = fmaf(S[m], va.w, o[3]);
+                o[4] = fmaf(S[m], vb.x, o[4]); o[5] = fmaf(S[m], vb.y, o[5]); o[6] = fmaf(S[m], vb.z, o[6]); o[7] = fmaf(S[m], vb.w, o[7]);
+            }
+            // channel = h*32 + 8j + e -> plane 4h + j of the K-major A operand of the to_out conv
+            *reinterpret_cast<uint4*>(smem + p.xh_off + (uint32_t)(4 * h + j) * plane + (uint32_t)row * 16u) = pack8(o, p.fmt);
+        } else if (wact) {
+            const int h = part;
+            float q[32];
+            load_q(q);
             float S[NPX];
 #pragma unroll
             for (int m = 0; m < NPX; ++m) {
                 const float4* kr = reinterpret_cast<const float4*>(kst + (uint32_t)(row_s0 + m) * SM_KP + (uint32_t)h * 128u);
-                float a0 = 0.f, a1 = 0.f;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // (the same association as the quarter-tile path: bit-equal results)
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 kk = kr[c4];
+                    const float4 kk = kr[(uint32_t)c4 ^ swz];
                     a0 = fmaf(q[c4 * 4], kk.x, a0); a1 = fmaf(q[c4 * 4 + 1], kk.y, a1);
-                    a0 = fmaf(q[c4 * 4 + 2], kk.z, a0); a1 = fmaf(q[c4 * 4 + 3], kk.w, a1);
+                    a2 = fmaf(q[c4 * 4 + 2], kk.z, a2); a3 = fmaf(q[c4 * 4 + 3], kk.w, a3);
                 }
-                S[m] = a0 + a1;
+                S[m] = (a0 + a1) + (a2 + a3);
             }
             if (!LINEAR) {                                      // softmax over the key pixels (unet.py:116-118)
                 float m = S[0];
@@ -1107,7 +1264,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
                 const float4* vr = reinterpret_cast<const float4*>(vst + (uint32_t)(row_s0 + m) * SM_KP + (uint32_t)h * 128u);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 vv = vr[c4];
+                    const float4 vv = vr[(uint32_t)c4 ^ swz];
                     o[c4 * 4] = fmaf(S[m], vv.x, o[c4 * 4]); o[c4 * 4 + 1] = fmaf(S[m], vv.y, o[c4 * 4 + 1]);
                     o[c4 * 4 + 2] = fmaf(S[m], vv.z, o[c4 * 4 + 2]); o[c4 * 4 + 3] = fmaf(S[m], vv.w, o[c4 * 4 + 3]);
                 }
@@ -1117,60 +1274,86 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
             for (int cb = 0; cb < 4; ++cb)
                 *reinterpret_cast<uint4*>(smem + p.xh_off + (uint32_t)(4 * h + cb) * plane + (uint32_t)r * 16u) = pack8(o + cb * 8, p.fmt);
         }
+        if (dbg && et == 0) dbg[11] = clock64();
+        // ================= EPI-C: to_out bias [-> GroupNorm(1, C)] -> + x2 -> global =================
+        // Up to four warp groups split the channels in whole 16-channel chunks (C = 128: 32 each, C = 64: 16 each, C = 32: two
+        // groups); a thread holds at most two chunks, so the accumulators stay in registers between the statistics and the
+        // normalisation, and the residual rows are requested BEFORE the to_out MMAs are waited for (an exposed L2 round trip per
+        // chunk otherwise: 9.6k cycles for the x2-upsampled C = 128 output, profiles/r02_attn_small_timeline.txt).
+        const int lgparts = (C & 63) == 0 ? 2 : ((C & 31) == 0 ? 1 : 0);
+        const bool act = part < (1 << lgparts);
+        const int cpp = C >> lgparts, c_lo = part * cpp, c_hi = (act && wact) ? c_lo + cpp : c_lo;
+        uint4 xr[4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            xr[2 * k] = make_uint4(0, 0, 0, 0); xr[2 * k + 1] = xr[2 * k];
+            const int c16 = c_lo + 16 * k;
+            if (valid && c16 < c_hi) {
+                xr[2 * k] = xsrc[(size_t)((c16 >> 3) * p.B + b) * NPX + px];
+                xr[2 * k + 1] = xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * NPX + px];
+            }
+        }
         fence_proxy_async();
         tc_fence_before();
         named_bar_arrive(2, n_epi + 32);
-        // ================= EPI-C: to_out bias [-> GroupNorm(1, C)] -> + x2 -> global; warps 0..7: channels [half*C/2, +C/2) of row r =================
-        if (part < 2) {
+        if (act) {
         mbar_wait(bar_mma, 1);
         tc_fence_after();
+        if (dbg && et == 0) dbg[26] = clock64();
         griddep_launch();            // PDL: the next stage kernel may become resident during the last epilogue
         const float* bias = par;
         const float* gamma = par + 128;
         const float* beta = par + 256;
-        // two warp groups split the channels when each half is a whole number of 16-channel chunks; otherwise group 0 takes all
-        const bool csplit = ((C >> 1) & 15) == 0;
-        const int c_lo = csplit ? half * (C >> 1) : 0, c_hi = csplit ? c_lo + (C >> 1) : (half == 0 ? C : 0);
+        float v[2][16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            uint32_t u[16];
+            if (c_lo + 16 * k < c_hi) tmem_ld16_issue(tlane + (uint32_t)(p.col_proj + c_lo + 16 * k), u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[k][j] = (c_lo + 16 * k < c_hi) ? __uint_as_float(u[j]) + bias[c_lo + 16 * k + j] : 0.f;
+        }
         float mean = 0.f, rstd = 1.f;
         if (LINEAR) {
             float sx = 0.f, sq = 0.f;
-            for (int c16 = c_lo; c16 < c_hi; c16 += 16) {
-                float v[16];
-                tmem_ld16(tlane + (uint32_t)(p.col_proj + c16), v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const float x = v[j] + bias[c16 + j]; sx += x; sq = fmaf(x, x, sq); }
-            }
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { sx += v[k][j]; sq = fmaf(v[k][j], v[k][j], sq); }
             if (!valid) { sx = 0.f; sq = 0.f; }
 #pragma unroll
             for (int o = NPX >> 1; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
-            if (px == 0) hstat[half * 64 + s_loc] = make_float2(sx, sq);
-            named_bar_sync(3, 256);
-            const float2 a = hstat[s_loc], bq = hstat[64 + s_loc];
+            if (px == 0) hstat[part * 32 + s_loc] = make_float2(sx, sq);
+            named_bar_sync(3, 128 << lgparts);
+            if (dbg && et == 0) dbg[27] = clock64();
+            sx = 0.f; sq = 0.f;
+            for (int q = 0; q < (1 << lgparts); ++q) { const float2 a = hstat[q * 32 + s_loc]; sx += a.x; sq += a.y; }     // fixed order
             const float icnt = fast_rcp((float)(C * NPX));
-            mean = (a.x + bq.x) * icnt;
-            rstd = rsqrtf(fmaxf((a.y + bq.y) * icnt - mean * mean, 0.f) + 1e-5f);
+            mean = sx * icnt;
+            rstd = rsqrtf(fmaxf(sq * icnt - mean * mean, 0.f) + 1e-5f);
         }
-        for (int c16 = c_lo; c16 < c_hi; c16 += 16) {
-            float v[16], x2[16];
-            tmem_ld16(tlane + (uint32_t)(p.col_proj + c16), v);
-            if (!valid) continue;
-            const uint4 xa = xsrc[(size_t)((c16 >> 3) * p.B + b) * NPX + px];
-            const uint4 xb = xsrc[(size_t)(((c16 >> 3) + 1) * p.B + b) * NPX + px];
-            unpack8(xa, x2, p.fmt);
-            unpack8(xb, x2 + 8, p.fmt);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c16 = c_lo + 16 * k;
+            if (c16 >= c_hi) continue;                 // warp-uniform
+            float x2[16];
+            unpack8(xr[2 * k], x2, p.fmt);
+            unpack8(xr[2 * k + 1], x2 + 8, p.fmt);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float y = v[j] + bias[c16 + j];
+                float y = v[k][j];
                 if (LINEAR) y = (y - mean) * rstd * gamma[c16 + j] + beta[c16 + j];
-                v[j] = y + x2[j];
+                v[k][j] = y + x2[j];
             }
-            attn_write_out(p, b, px, c16, v);
+            attn_write_out_w(p, b, px, c16, v[k], valid);
         }
         }
-        (void)cb0;
+        if (dbg && et == 0) dbg[28] = clock64();
     }
     tc_fence_before();
     __syncthreads();
+    if (dbg && tid == 0) dbg[65] = clock64();
+    if (p.dbg && tid == 0) { if (blockIdx.x == 0) p.dbg[102] = global_ns(); atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 103), (unsigned long long)global_ns()); }
     if (warp == w_mma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
