@@ -269,6 +269,8 @@ struct ChainParams {
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
     int prod_lanes;                         // lanes of the producer warp that issue weight chunks (chunk cc -> lane cc % prod_lanes)
+    int tx_handoff;                         // N-split stages: 1 = the step hand-off rides on the output stores themselves (st.async +
+                                            // mbarrier transaction bytes); 0 = stores, proxy fence, CTA barrier, release-arrive on every CTA
     int early_pdl;                          // 1: griddepcontrol.launch_dependents at kernel start (this grid leaves SMs idle: the next
                                             // stage's CTAs become resident there and run their prologue / weight prefetch meanwhile)
     int ring_off, ring_slot_bytes, n_ring, n_ring_deep;   // n_ring_deep: depth when one CTA owns the SM (chosen per plan)

@@ -175,6 +175,7 @@ template <int N> struct IntTag { static constexpr int value = N; };
 // `gpar[c]` = (gamma, beta); with `has_film`, coef[s*C+c] holds (1+scale, shift) on entry.
 struct XChg {                    // cross-CTA (cluster) reduction of per-sample statistics; nsplit == 1: unused
     int nsplit; uint32_t rank, smem_base, bar_x; int xpart_off; uint32_t* phase; uint8_t* smem;
+    bool tx;                     // the partial sums travel as st.async stores that complete transaction bytes on bar_x
 };
 __device__ __forceinline__ void stats_to_coef(const Geo& g, int R, const float2* rowstat, float2* coef, const float2* gpar, int G, int pm,
                                               int C, int HW, bool has_film, int et, const XChg* xc = nullptr) {
@@ -215,13 +216,22 @@ __device__ __forceinline__ void stats_to_coef(const Geo& g, int R, const float2*
         // G == 1 here: every CTA of the cluster holds the sums over ITS channels; publish them to all CTAs, then
         // add the parts in rank order (deterministic, identical in every CTA)
         n_parts = xc->nsplit;
-        if (active && li == 0)
-            for (int q = 0; q < n_parts; ++q)
-                st_cluster_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
-                              make_float2(sx, sq));
-        epi_sync();                      // the publishing lanes' remote stores are ordered before the release-arrives below
-        if (et == 0)
-            for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
+        if (xc->tx) {
+            // every CTA receives nsplit x nb (sum, sumsq) pairs of 8 bytes; one thread posts the expectation, the stores signal
+            if (et == 0) mbar_expect_tx(xc->bar_x, (uint32_t)(n_parts * g.nb * 8));
+            if (active && li == 0)
+                for (int q = 0; q < n_parts; ++q)
+                    st_async_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
+                                make_float2(sx, sq), mapa_shared(xc->bar_x, (uint32_t)q));
+        } else {
+            if (active && li == 0)
+                for (int q = 0; q < n_parts; ++q)
+                    st_cluster_f2(mapa_shared(xc->smem_base + (uint32_t)xc->xpart_off + (uint32_t)((int)xc->rank * g.nb + s) * 8u, (uint32_t)q),
+                                  make_float2(sx, sq));
+            epi_sync();                      // the publishing lanes' remote stores are ordered before the release-arrives below
+            if (et == 0)
+                for (int q = 0; q < n_parts; ++q) mbar_arrive_cluster(mapa_shared(xc->bar_x, (uint32_t)q));
+        }
         mbar_wait_cluster(xc->bar_x, *xc->phase & 1u);
         ++*xc->phase;
         if (active) {
@@ -301,6 +311,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
     const uint32_t bar_epi = bar_mma + 8;
     const uint32_t tmem_slot = bar_epi + 8;
     const uint32_t bar_x = tmem_slot + 8;
+    const uint32_t bar_epi2 = bar_x + 8;         // transaction hand-off: steps alternate between bar_epi and bar_epi2
+    const bool txh = SPLIT && p.tx_handoff != 0;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 24);
     const Geo geo = make_geo(p);
     // N-split: the Q CTAs of a cluster own the same samples and 1/Q of every step's output channels
@@ -322,8 +334,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         // N-split: one elected thread per CTA arrives (after a CTA-local barrier) on the barriers of every CTA of the cluster
-        mbar_init(bar_epi, SPLIT ? Q : EPI_THREADS);
-        mbar_init(bar_x, SPLIT ? Q : EPI_THREADS);
+        mbar_init(bar_epi, txh ? 1 : (SPLIT ? Q : EPI_THREADS));
+        mbar_init(bar_epi2, 1);
+        mbar_init(bar_x, txh ? 1 : (SPLIT ? Q : EPI_THREADS));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -416,7 +429,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
             if (i > 0) {
                 // epilogue -> MMA hand-off: inside one CTA a named barrier the 256 epilogue threads arrive on (no 256
                 // serialised mbarrier arrivals); across a cluster the mbarrier with cluster-scope release / acquire
-                if (Q > 1) { mbar_wait_cluster(bar_epi, (i - 1) & 1); fence_proxy_async_all(); }
+                if (txh) {
+                    // every CTA of the cluster stores step i-1's 16-bit outputs into our slot with st.async: the barrier completes when
+                    // all of them have landed -- (live rows) x (channel blocks of the step) x 16 bytes; steps alternate between two
+                    // barriers, so a peer that is one step ahead signals the other one
+                    const int live = min(geo.nb, geo.B - b0) * geo.H * geo.W;
+                    const uint32_t bar = ((i - 1) & 1) ? bar_epi2 : bar_epi;
+                    if (elect_one()) mbar_expect_tx(bar, (uint32_t)(live * (p.st[i - 1].C >> 3) * 16));
+                    __syncwarp();
+                    mbar_wait_cluster(bar, ((i - 1) >> 1) & 1);
+                    fence_proxy_async_all();
+                } else if (Q > 1) { mbar_wait_cluster(bar_epi, (i - 1) & 1); fence_proxy_async_all(); }
                 else named_bar_sync(2, EPI_THREADS + 32);
             }
             tc_fence_after();
@@ -472,7 +495,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
         uint32_t xphase = 0;
         XChg xc;
         xc.nsplit = Q; xc.rank = qrank; xc.smem_base = smem_base; xc.bar_x = bar_x; xc.xpart_off = p.xpart_off; xc.phase = &xphase;
-        xc.smem = smem;
+        xc.smem = smem; xc.tx = txh;
 
         for (int i = 0; i < n_steps; ++i) {
             // ---- step parameters into registers
@@ -496,8 +519,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                 if (out_slot_off >= 0) {
                     const uint32_t soff = (uint32_t)out_slot_off + (uint32_t)cb * plane_bytes + (uint32_t)R.pp * 16u;
                     if (!SPLIT) *reinterpret_cast<uint4*>(smem + soff) = u;
-                    else
+                    else if (!txh)
                         for (int q = 0; q < Q; ++q) st_cluster_v4(mapa_shared(smem_base + soff, (uint32_t)q), u);
+                    else if (i + 1 < n_steps) {
+                        const uint32_t bar = (i & 1) ? bar_epi2 : bar_epi;
+                        for (int q = 0; q < Q; ++q) st_async_v4(mapa_shared(smem_base + soff, (uint32_t)q), u, mapa_shared(bar, (uint32_t)q));
+                    } else {
+                        *reinterpret_cast<uint4*>(smem + soff) = u;      // last step: only this CTA reads the slot again (fused PreNorm)
+                    }
                 }
                 if (og) og[(size_t)(cb * geo.B + b0 + R.s) * HW + R.px] = u;
                 return u;
@@ -1078,7 +1107,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
             }
             if (dbg && et == 0) dbg[i * 8 + 5] = clock64();
             tc_fence_before();
-            if (SPLIT) {
+            if (SPLIT && txh) {
+                // nothing: the stores of write8 complete the consumers' barriers as they land
+            } else if (SPLIT) {
                 fence_proxy_async_all();     // local and remote shared-memory results -> visible to every CTA's next tcgen05.mma
                 epi_sync();                  // every thread's stores are ordered before the elected thread's release-arrives
                 if (et == 0)

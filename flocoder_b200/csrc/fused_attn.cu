@@ -1082,50 +1082,83 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
         tc_fence_after();
         if (dbg && et == 0) dbg[2] = clock64();
         // ================= EPI-A: this thread's 32 channels of row r: k (column softmax over the sample's pixels) and v =================
-        for (int c16 = part * 32; c16 < part * 32 + 32 && wact; c16 += 16) {
-            uint32_t ku[16], vu[16];
-            tmem_ld16_issue(tlane + (uint32_t)(p.col_k + c16), ku);
-            tmem_ld16_issue(tlane + (uint32_t)(p.col_v + c16), vu);
-            tmem_ld_wait();
-            float kv[16], vv[16];
+        // Both 16-channel chunks go through the segmented reductions together (independent shuffle chains in flight; the second
+        // chunk's scratch rows live in the input tile, which is dead once the projections have completed).
+        if (wact) {
+            const int cA = part * 32;
+            float kv[2][16];
+            {
+                uint32_t ku[2][16];
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_k + cA), ku[0]);
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_k + cA + 16), ku[1]);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { kv[j] = __uint_as_float(ku[j]); vv[j] = __uint_as_float(vu[j]); }
+                for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) kv[h2][j] = __uint_as_float(ku[h2][j]);
+            }
             if (LINEAR) {
-                float red[16];
+                float* const scr2[2] = {scr, reinterpret_cast<float*>(smem + p.xh_off) + warp * (2 * SPW * 16)};
+                float red[2][16];
+                int ch[2];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) red[j] = kv[j];
-                const int ca = segred16<NPX, true>(red, lane);
-                float* mx = scr + (lane >> LGN) * 16;
+                for (int h2 = 0; h2 < 2; ++h2) {
 #pragma unroll
-                for (int j = 0; j < CNT; ++j) mx[ca + j] = red[j];
+                    for (int j = 0; j < 16; ++j) red[h2][j] = kv[h2][j];
+                    ch[h2] = segred16<NPX, true>(red[h2], lane);
+                    float* mx = scr2[h2] + (lane >> LGN) * 16;
+#pragma unroll
+                    for (int j = 0; j < CNT; ++j) mx[ch[h2] + j] = red[h2][j];
+                }
                 __syncwarp();
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 m4 = reinterpret_cast<const float4*>(mx)[k4];
-                    kv[4 * k4] = fast_exp(kv[4 * k4] - m4.x); kv[4 * k4 + 1] = fast_exp(kv[4 * k4 + 1] - m4.y);
-                    kv[4 * k4 + 2] = fast_exp(kv[4 * k4 + 2] - m4.z); kv[4 * k4 + 3] = fast_exp(kv[4 * k4 + 3] - m4.w);
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const float4* mx = reinterpret_cast<const float4*>(scr2[h2] + (lane >> LGN) * 16);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 m4 = mx[k4];
+                        kv[h2][4 * k4] = fast_exp(kv[h2][4 * k4] - m4.x); kv[h2][4 * k4 + 1] = fast_exp(kv[h2][4 * k4 + 1] - m4.y);
+                        kv[h2][4 * k4 + 2] = fast_exp(kv[h2][4 * k4 + 2] - m4.z); kv[h2][4 * k4 + 3] = fast_exp(kv[h2][4 * k4 + 3] - m4.w);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) red[h2][j] = kv[h2][j];
+                    ch[h2] = segred16<NPX, false>(red[h2], lane);
+                    float* sm = scr2[h2] + SPW * 16 + (lane >> LGN) * 16;
+#pragma unroll
+                    for (int j = 0; j < CNT; ++j) sm[ch[h2] + j] = red[h2][j];
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) red[j] = kv[j];
-                const int cs = segred16<NPX, false>(red, lane);
-                float* sm = scr + SPW * 16 + (lane >> LGN) * 16;
-#pragma unroll
-                for (int j = 0; j < CNT; ++j) sm[cs + j] = red[j];
                 __syncwarp();
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 s4 = reinterpret_cast<const float4*>(sm)[k4];
-                    kv[4 * k4] *= fast_rcp(s4.x); kv[4 * k4 + 1] *= fast_rcp(s4.y); kv[4 * k4 + 2] *= fast_rcp(s4.z); kv[4 * k4 + 3] *= fast_rcp(s4.w);
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const float4* sm = reinterpret_cast<const float4*>(scr2[h2] + SPW * 16 + (lane >> LGN) * 16);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 s4 = sm[k4];
+                        kv[h2][4 * k4] *= fast_rcp(s4.x); kv[h2][4 * k4 + 1] *= fast_rcp(s4.y);
+                        kv[h2][4 * k4 + 2] *= fast_rcp(s4.z); kv[h2][4 * k4 + 3] *= fast_rcp(s4.w);
+                    }
                 }
-                __syncwarp();                                   // the scratch rows are rewritten by the next chunk
             }
             float4* kd = reinterpret_cast<float4*>(kst + (uint32_t)r * SM_KP);
             float4* vd = reinterpret_cast<float4*>(vst + (uint32_t)r * SM_KP);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                const uint32_t f4 = (uint32_t)((c16 >> 2) + k4) ^ swz;
-                kd[f4] = make_float4(kv[4 * k4], kv[4 * k4 + 1], kv[4 * k4 + 2], kv[4 * k4 + 3]);
-                vd[f4] = make_float4(vv[4 * k4], vv[4 * k4 + 1], vv[4 * k4 + 2], vv[4 * k4 + 3]);
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    kd[(uint32_t)(((cA + 16 * h2) >> 2) + k4) ^ swz] =
+                        make_float4(kv[h2][4 * k4], kv[h2][4 * k4 + 1], kv[h2][4 * k4 + 2], kv[h2][4 * k4 + 3]);
+            {
+                uint32_t vu[2][16];
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_v + cA), vu[0]);
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_v + cA + 16), vu[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        vd[(uint32_t)(((cA + 16 * h2) >> 2) + k4) ^ swz] =
+                            make_float4(__uint_as_float(vu[h2][4 * k4]), __uint_as_float(vu[h2][4 * k4 + 1]),
+                                        __uint_as_float(vu[h2][4 * k4 + 2]), __uint_as_float(vu[h2][4 * k4 + 3]));
             }
         }
         // q of (row r, head `part`) out of tensor memory: softmax over the 32 head channels, then * 32^-0.5 (unet.py:141-143), or

@@ -166,6 +166,18 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16-byte store into the shared memory of a CTA of the cluster that, when it lands, completes 16 transaction bytes on an mbarrier
+// of the SAME CTA: data and signal travel together (no fence + release-arrive round trip behind the stores)
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_f2(uint32_t raddr, float2 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(rbar)
+                 : "memory");
+}
 __device__ __forceinline__ void st_cluster_f2(uint32_t raddr, float2 v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(v.x), "f"(v.y) : "memory");
 }
