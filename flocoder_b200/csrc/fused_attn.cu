@@ -318,9 +318,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         // EW = 4: one warp group does everything; EW = 8: M tiles / samples are dealt round-robin to two warp groups; EW = 16 (a
         // sample spans two M tiles): tile = grp & 1 and the two groups of a tile split the q/k/v channels (cpart = grp >> 1) --
         // the softmax epilogues are chains of TMEM loads, shuffles and MUFU ops, and four warps per scheduler hide what two cannot
-        const int half = EW >= 8 ? (grp & 1) : 0;
-        const int t0 = half, tstep = EW >= 8 ? 2 : 1;
-        const int cpart = EW == 16 ? (grp >> 1) : 0, ncp = EW == 16 ? 2 : 1;
+        // One M tile per CTA (8x8 level, two samples) with EW = 8: both groups work on tile 0 and split the channels the same way
+        // (four warps per SM left every scheduler idle most of the time: 6 k-cycle softmax epilogues on 16 k exponentials).
+        const bool one_tile_split = EW == 8 && p.n_mtiles == 1;
+        const int half = (EW >= 8 && !one_tile_split) ? (grp & 1) : 0;
+        const int t0 = half, tstep = (EW >= 8 && !one_tile_split) ? 2 : 1;
+        const int cpart = EW == 16 ? (grp >> 1) : (one_tile_split ? grp : 0), ncp = (EW == 16 || one_tile_split) ? 2 : 1;
         const int ch_lo = cpart * (NCH / ncp), ch_hi = ch_lo + NCH / ncp;      // this thread's q/k/v channels in the softmax epilogues
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         auto esync = [&]() { named_bar_sync(1, n_epi); };
@@ -790,7 +793,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             // per-sample totals in a fixed order (deterministic)
             int parts = 1;
             while (parts * 2 * p.nb <= 128 && parts < 16) parts *= 2;
+            if (dbg && et == 0) dbg[27] = clock64();
             esync();
+            if (dbg && et == 0) dbg[28] = clock64();
             if (n >= 32) {
                 // nothing: the normalisation pass forms mean / rstd from `partial`
             } else {
@@ -893,6 +898,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
         }
+        if (dbg && et == 0) dbg[29] = clock64();
     }
     }
     tc_fence_before();
