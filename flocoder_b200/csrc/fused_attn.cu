@@ -215,8 +215,14 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == w_mma) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    for (int i = tid * 16; i < p.zero_bytes; i += n_thr * 16)
-        *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
+    // The P / V / context slots must read as zero wherever no epilogue writes them: padding rows (n < 16), rows of samples past the
+    // end of the batch, rows past the last sample of a partly filled M tile.  A CTA whose rows are all live skips the clear
+    // (152 KB of shared-memory stores at the 16x16 level, on the critical path of every CTA that is not in the first wave):
+    // every contraction runs over the rows of ONE sample, and what the unwritten planes feed are accumulator columns nobody loads.
+    const bool all_live = !p.full && HS == 1 && p.n_pad == p.n && ((p.nb * p.n) & 127) == 0 && b0 + p.nb <= p.B;
+    if (!all_live)
+        for (int i = tid * 16; i < p.zero_bytes; i += n_thr * 16)
+            *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     if (HS > 1) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive
