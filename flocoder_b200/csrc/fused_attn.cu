@@ -878,6 +878,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                         ms = stat[s];
                     }
                 }
+                if (dbg && et == 0) dbg[30] = clock64();
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
                 // the residual rows of the NEXT channel chunk are requested before this chunk is processed
                 uint4 xa = pre_xa, xb = pre_xb;

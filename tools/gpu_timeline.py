@@ -46,7 +46,7 @@ for i, name in enumerate(names):
         d = lambda k: (tl[k] - start) if tl[k] else -1   # noqa: E731
         print(f"   attn: load+mma0_start +{d(0)} kvconv_issued +{d(1)} | epi0_start +{d(2)} maxpass_done +{d(3)} epi0_end +{d(4)} | "
               f"mma1_start +{d(8)} ctx+q_issued +{d(9)} | epi1_start +{d(10)} epi1_end +{d(11)} | mma2_start +{d(16)} | "
-              f"epi2_start +{d(18)} epi2_end +{d(19)} | mma3_start +{d(24)} | epi3_start +{d(26)} stats_own_done +{d(27)} stats_barrier +{d(28)} written +{d(29)} end +{end - start}")
+              f"epi2_start +{d(18)} epi2_end +{d(19)} | mma3_start +{d(24)} | epi3_start +{d(26)} stats_own_done +{d(27)} stats_barrier +{d(28)} ms_done +{d(30)} written +{d(29)} end +{end - start}")
         continue
     if tl[105]:
         print("   weight chunks 8..15 (cycles rel. kernel start): " + " | ".join(
