@@ -722,6 +722,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                     }
                     coef[idx] = f;
                 }
+                // the PreNorm affine of the last step too: fetched from global memory behind the statistics it was an exposed L2
+                // round trip on the tail of the kernel
+                if (pn_g >= 0)
+                    for (int c = et; c < C; c += EPI_THREADS) pnpar[c] = make_float2(fblob[p.st[i].pn_gamma_off + c0 + c], fblob[p.st[i].pn_beta_off + c0 + c]);
             }
             mbar_wait(bar_mma, i & 1);
             tc_fence_after();
@@ -1054,8 +1058,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                 if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
                     const int pm2 = (MT == 1) ? 2 : 1;
-                    const float* g2 = fblob + p.st[i].pn_gamma_off;
-                    const float* b2 = fblob + p.st[i].pn_beta_off;
                     // (rowstat and gpar were last read before the final barrier of the block-norm stats_to_coef; coef is
                     // rewritten only behind the first barrier of the next one, which every thread reaches after its pass 2)
 #pragma unroll
@@ -1064,8 +1066,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                         const int t = tile_of(k);
                         rowstat[(size_t)(t * 128 + r) * pm2 + (pm2 == 2 ? wg : 0)] = ri[k].valid ? make_float2(psx[k], psq[k]) : make_float2(0.f, 0.f);
                     }
-                    for (int c = et; c < C; c += EPI_THREADS) gpar[c] = make_float2(g2[c0 + c], b2[c0 + c]);
-                    stats_to_coef(geo, MT * 128, rowstat, coef, gpar, 1, pm2, C, HW, false, et, &xc);
+                    stats_to_coef(geo, MT * 128, rowstat, coef, pnpar, 1, pm2, C, HW, false, et, &xc);
                     uint4* dst = reinterpret_cast<uint4*>(p.gt[pn_g]);
                     for_chunks([&](int k, int c, auto tag) {
                         constexpr int CW = decltype(tag)::value;

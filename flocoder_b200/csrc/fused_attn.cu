@@ -1097,6 +1097,10 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
         // ================= EPI-A: this thread's 32 channels of row r: k (column softmax over the sample's pixels) and v =================
         // Both 16-channel chunks go through the segmented reductions together (independent shuffle chains in flight; the second
         // chunk's scratch rows live in the input tile, which is dead once the projections have completed).
+        // quarter tile (32 live rows): twelve of the sixteen warps own no rows.  The four that do only MOVE k and v to the staging rows
+        // and then turn to q; the column softmax of k runs out of shared memory on the others meanwhile (see below)
+        const bool quarter = live_rows == 32;
+        const bool qsm = quarter && LINEAR;
         if (wact) {
             const int cA = part * 32;
             float kv[2][16];
@@ -1110,7 +1114,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 16; ++j) kv[h2][j] = __uint_as_float(ku[h2][j]);
             }
-            if (LINEAR) {
+            if (LINEAR && !qsm) {
                 float* const scr2[2] = {scr, reinterpret_cast<float*>(smem + p.xh_off) + warp * (2 * SPW * 16)};
                 float red[2][16];
                 int ch[2];
@@ -1204,8 +1208,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
         // budget keeps from overlapping (9k cycles at 4x4 with ONE warp per scheduler).  There the q~ rows go through shared memory
         // too (staging rows 32.., free in this mode) and FOUR threads share a (row, head): each takes a quarter of the key pixels
         // for S = q~ . k~, the four exchange S by shuffles, and each produces 8 of the head's 32 output channels.
-        const bool quarter = live_rows == 32;
         uint8_t* qst = kst + 32u * SM_KP;
+        if (qsm) esync();                                       // the raw k rows are in the staging area
         if (quarter && wact) {
             float q[32];
             load_q(q);
@@ -1213,6 +1217,48 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4)
                 qd[(uint32_t)(part * 8 + k4) ^ swz] = make_float4(q[4 * k4], q[4 * k4 + 1], q[4 * k4 + 2], q[4 * k4 + 3]);
+        } else if (qsm) {
+            // k~ = softmax over the sample's pixels, in place: thread (sample s, float4 column f, row quarter rq) of the first 256
+            // threads of the row-less warps.  The rows a thread takes and the order of the additions reproduce the halving
+            // exchange of the full-tile path -- pixel i pairs with i ^ (NPX/2), then i ^ (NPX/4), ... -- so k~ is bit-identical
+            // whichever plan runs: a thread owns pixels {rq, rq ^ 8, rq ^ 4, rq ^ 12} (NPX = 16; the xor-2 and xor-1 levels are two
+            // shuffles over the four rq lanes) or {0, 2, 1, 3} (NPX = 4).
+            constexpr int RQ = NPX / 4;
+            const int u = ((warp >> 2) * 3 + (warp & 3) - 1) * 32 + lane;          // dense index over the twelve row-less warps
+            if (u < 256) {
+                const int rq = u % RQ, f = (u / RQ) & 31, s2 = u / (RQ * 32);
+                const uint32_t sw = NPX == 4 ? (uint32_t)((s2 >> 1) & 3) : (uint32_t)(s2 & 1);
+                const uint32_t col = ((uint32_t)f ^ sw) * 16u;
+                const int px[4] = {rq, rq ^ (NPX / 2), rq ^ (NPX / 4), rq ^ (NPX / 2) ^ (NPX / 4)};
+                float4* rows[4];
+                float4 x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    rows[k] = reinterpret_cast<float4*>(kst + (uint32_t)(s2 * NPX + px[k]) * SM_KP + col);
+                    x[k] = *rows[k];
+                }
+                float4 m = make_float4(fmaxf(fmaxf(x[0].x, x[1].x), fmaxf(x[2].x, x[3].x)), fmaxf(fmaxf(x[0].y, x[1].y), fmaxf(x[2].y, x[3].y)),
+                                       fmaxf(fmaxf(x[0].z, x[1].z), fmaxf(x[2].z, x[3].z)), fmaxf(fmaxf(x[0].w, x[1].w), fmaxf(x[2].w, x[3].w)));
+#pragma unroll
+                for (int o = RQ >> 1; o > 0; o >>= 1) {
+                    m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, o)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, o));
+                    m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, o)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, o));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    x[k].x = fast_exp(x[k].x - m.x); x[k].y = fast_exp(x[k].y - m.y); x[k].z = fast_exp(x[k].z - m.z); x[k].w = fast_exp(x[k].w - m.w);
+                }
+                float4 sum = make_float4((x[0].x + x[1].x) + (x[2].x + x[3].x), (x[0].y + x[1].y) + (x[2].y + x[3].y),
+                                         (x[0].z + x[1].z) + (x[2].z + x[3].z), (x[0].w + x[1].w) + (x[2].w + x[3].w));
+#pragma unroll
+                for (int o = RQ >> 1; o > 0; o >>= 1) {
+                    sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                    sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+                }
+                const float4 inv = make_float4(fast_rcp(sum.x), fast_rcp(sum.y), fast_rcp(sum.z), fast_rcp(sum.w));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) *rows[k] = make_float4(x[k].x * inv.x, x[k].y * inv.y, x[k].z * inv.z, x[k].w * inv.w);
+            }
         }
         if (dbg && et == 0) dbg[4] = clock64();
         esync();

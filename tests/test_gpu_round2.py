@@ -365,3 +365,33 @@ def test_three_channel_latents_midi_vqgan_3d_gray(compute_dtype, tol):
     x1, _ = sampling.generate_latents_rk4(m, (6, 3, 16, 16), n_steps=5, source=x.cuda())
     want1, _ = oracle.generate_latents_rk4(OracleModel(sd, spec), (6, 3, 16, 16), n_steps=5, source=x)
     assert rel_l2(x1, want1) <= tol
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the small-batch plan (quarter-filled k_attn_small tiles with four threads per (row, head); st.async hand-off of the N-split
+# stages) against the full-tile / fence-and-arrive forms of the same kernels: the arithmetic is the same in the same order
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [37, 256])
+def test_plan_switches_are_bit_identical(B, monkeypatch):
+    from flocoder_b200.unet import Unet
+
+    def forward_with(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        torch.manual_seed(1234)
+        m = Unet(dim=16, channels=4, dim_mults=[1, 2, 4, 8], n_classes=10, compute_dtype="bf16").cuda().eval()   # a fresh engine reads the switches
+        x = torch.randn(B, 4, 16, 16, generator=torch.Generator().manual_seed(7)).cuda()
+        t = torch.linspace(10.0, 900.0, B).cuda()
+        cls = (torch.arange(B) % 10).cuda()
+        with torch.no_grad():
+            v = m(x, t, {"class_cond": cls}).clone()
+        m.invalidate()
+        for k in env:
+            monkeypatch.delenv(k)
+        return v
+
+    base = forward_with({})
+    assert torch.isfinite(base).all()
+    assert torch.equal(base, forward_with({"FLO_SMALL_DIV": "1"}))        # full k_attn_small tiles, one thread per (row, head)
+    assert torch.equal(base, forward_with({"FLO_SMALL_DIV": "2"}))        # half tiles
+    assert torch.equal(base, forward_with({"FLO_TX_HANDOFF": "0"}))       # stores -> fence -> barrier -> release-arrive hand-off
