@@ -299,6 +299,8 @@ struct AttnFusedParams {
     int B, H, W, C, nb, n, n_pad, n_mtiles; // n = H*W; n_pad = max(n,16) rows per sample in the P/V/Q slots;
                                             // n_mtiles = 128-row tiles of the dense rows (s*n + p)
     int full;                               // 1: softmax(QK^T)V mid attention (no GroupNorm after to_out)
+    int ktrans;                             // 1: K and V are projected TRANSPOSED (weights as the A operand, the CTA's pixels as N): tensor-
+                                            // memory lanes = channels, columns = pixels, so the softmax over pixels is a loop per thread
     int small;                              // 1: k_attn_small (n = 4 or 16 pixels: 128 / n samples per CTA, attention core on CUDA cores)
     int hc, hsplit;                         // heads per CTA (4, or 2 with the head split) and CTAs per sample (cluster size 1 / 2)
     int fmt;

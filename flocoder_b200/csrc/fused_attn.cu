@@ -252,8 +252,35 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && lane == 0) dbg[0] = clock64();
             // ---- phase 0: K and V convolutions (and Q for the mid attention)
             const uint32_t wb_off = hrank * (uint32_t)NCH * 16u;      // this CTA's channels inside every 128-channel weight tile
+            const bool tr = p.ktrans != 0;
+            // transposed projection D[channel lanes][pixel columns] = W (A operand: the K-major weight tile, 128 rows x 16 B per K half)
+            // x x^ (B operand: the CTA's nb * n pixel rows of the input tile, planes of 8 channels)
+            auto conv_T = [&](int col) {
+                const uint32_t idesc = make_idesc16(128, p.nb * n, p.fmt, 0, 0);
+                for (int ci = 0; ci < p.qkv_chunks; ++ci) {
+                    const int slot = rs.cc & (ATTN_RING - 1);
+                    mbar_wait(bar_full + 8 * slot, (rs.cc / ATTN_RING) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        for (int sl = 0; sl < p.qkv_S; ++sl) {
+                            const uint32_t a_addr = smem_base + p.ring_off + (uint32_t)slot * (uint32_t)p.ring_slot_bytes + (uint32_t)sl * 4096u;
+                            const uint32_t b_addr = smem_base + p.xh_off + (uint32_t)(ci * p.qkv_S + sl) * 2u * xh_plane;
+                            umma_bf16(tmem_base + (uint32_t)col, make_smem_desc(a_addr, 2048u, 128u), make_smem_desc(b_addr, xh_plane, 128u), idesc,
+                                      (ci * p.qkv_S + sl) > 0 ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * slot);
+                    }
+                    __syncwarp();
+                    ++rs.cc;
+                }
+            };
+            if (tr) {
+                conv_T(p.col_k);
+                conv_T(p.col_v);
+            } else {
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_k, p.qkv_chunks, p.qkv_S);
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_v, p.qkv_chunks, p.qkv_S);
+            }
             if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_q, p.qkv_chunks, p.qkv_S);
             if (dbg && lane == 0) dbg[1] = clock64();
             if (elect_one()) umma_commit(bar_mma);
@@ -270,7 +297,18 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 {
                     const int nb = p.nb, col_ctx = p.col_ctx;
                     const uint32_t p_off = p.p_off, v_off = p.v_off;
-                    if (elect_one())
+                    if (tr) {
+                        // k~ [128 channel rows][pixels] and v [144 rows: channels, then the ones row][pixels], both K-major: planes of
+                        // eight pixels, 2048 / 2304 bytes each
+                        const uint32_t idesc_t = make_idesc16(128, NCH + 16, p.fmt, 0, 0);
+                        if (elect_one())
+                            for (int s = 0; s < nb; ++s)
+                                for (int ks = 0; ks < n / 16; ++ks) {
+                                    const uint32_t pl = (uint32_t)(s * (n >> 3) + 2 * ks);
+                                    umma_bf16(tmem_base + (uint32_t)(col_ctx + s * (NCH + 16)), make_smem_desc(smem_base + p_off + pl * 2048u, 2048u, 128u),
+                                              make_smem_desc(smem_base + v_off + pl * 2304u, 2304u, 128u), idesc_t, ks > 0 ? 1u : 0u);
+                                }
+                    } else if (elect_one())
                         for (int s = 0; s < nb; ++s)
                             for (int ks = 0; ks < n_pad / 16; ++ks) {
                                 const uint32_t roff = (uint32_t)(s * n_pad + ks * 16) * 16u;
@@ -354,6 +392,56 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         tc_fence_after();
         if (dbg && r == 0) dbg[2] = clock64();
         if (!p.full) {
+          if (p.ktrans) {
+            // ================= EPI 0, transposed: tensor-memory lane = channel, columns = the CTA's pixels =================
+            // A warp group owns 64 pixel columns of one sample; the softmax over pixels is a loop per thread (no shuffles), the
+            // groups of a sample exchange one maximum per channel through shared memory, and k~ / v go to the operand slots K-major
+            // (planes of eight pixels: a thread's eight consecutive pixels are one 16-byte row).
+            const int d = r;                                  // channel (h, d') = TMEM lane
+            const int col0 = grp * 64, s = col0 >> lgn, gps = n >> 6;      // this group's columns, their sample, groups per sample
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t ua[16], ub[16];
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_k + col0 + c), ua);
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_k + col0 + c + 16), ub);
+                tmem_ld_wait();
+                float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ua[j])); m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ub[j])); }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            }
+            kpart[grp * 128 + d] = mx;
+            // the ones row of the V operand (row 128 of every plane; rows 129..143 feed context columns nobody loads)
+            for (int pl = et; pl < (p.nb * n) >> 3; pl += n_epi) {
+                const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+                *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)pl * 2304u + 128u * 16u) = pack8(ones, p.fmt);
+            }
+            if (dbg && r == 0) dbg[3] = clock64();
+            esync();
+            for (int g = 0; g < gps; ++g) mx = fmaxf(mx, kpart[(s * gps + g) * 128 + d]);
+#pragma unroll 2
+            for (int c = 0; c < 64; c += 16) {
+                uint32_t ku[16], vu[16];
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_k + col0 + c), ku);
+                tmem_ld16_issue(tlane + (uint32_t)(p.col_v + col0 + c), vu);
+                tmem_ld_wait();
+                float kv[16], vv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { kv[j] = fast_exp(__uint_as_float(ku[j]) - mx); vv[j] = __uint_as_float(vu[j]); }
+                const uint32_t pl = (uint32_t)(col0 + c) >> 3;
+                uint8_t* pd = smem + p.p_off + pl * 2048u + (uint32_t)d * 16u;
+                uint8_t* vd = smem + p.v_off + pl * 2304u + (uint32_t)d * 16u;
+                *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
+                *reinterpret_cast<uint4*>(pd + 2048u) = pack8(kv + 8, p.fmt);
+                *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
+                *reinterpret_cast<uint4*>(vd + 2304u) = pack8(vv + 8, p.fmt);
+            }
+            if (dbg && r == 0) dbg[4] = clock64();
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_arrive(2, n_epi + 32);
+          } else {
             // ================= EPI 0: column softmax numerators of K, V to shared memory =================
             const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
             // two 16-channel chunks per iteration: both TMEM loads are in flight together and the two shuffle
@@ -455,6 +543,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             fence_proxy_async();
             tc_fence_before();
             named_bar_arrive(2, n_epi + 32);
+          }
             // ================= EPI 1: context normalisation -> B operand; softmax_d(q) -> A operand =================
             mbar_wait(bar_mma, ph & 1); ++ph;
             tc_fence_after();
