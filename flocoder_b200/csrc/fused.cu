@@ -811,6 +811,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                             const uint32_t ta = tlane + (uint32_t)(acc_col + t * C + cbeg);
                             if constexpr (CW == 16) tmem_ld16_issue(ta, av); else tmem_ld8_issue(ta, av);
                             tmem_ld_wait();
+                            if (dbg && et == 0) dbg[i * 8 + 6] = clock64();
                             float ps[NV];
 #pragma unroll
                             for (int g = 0; g < NG; ++g) {
@@ -828,20 +829,29 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
 #pragma unroll
                             for (int j = 0; j < CW; ++j) y[j] = __uint_as_float(av[j]);
                         }
+                        if (dbg && et == 0) dbg[i * 8 + 7] = clock64();
                         epi_sync();
+                        if (dbg && et == 0) dbg[80 + i] = clock64();
                         if (!has_work) return;
                         float sum[NV];
 #pragma unroll
                         for (int v = 0; v < NV; ++v) sum[v] = 0.f;
-                        for (int w = wlo; w < whi; ++w) {           // fixed order: identical in every thread, deterministic
-                            if constexpr (NV == 2) {
-                                const float2 a = *reinterpret_cast<const float2*>(wpart + w * 8);
-                                sum[0] += a.x; sum[1] += a.y;
-                            } else {
+                        // fixed order: identical in every thread, deterministic.  Unrolled over the largest trip count with a
+                        // predicate, so that all loads are in flight before the first add (a counted loop was a chain of eight
+                        // load -> add round trips on the critical path of every step)
 #pragma unroll
-                                for (int v4 = 0; v4 < NV / 4; ++v4) {
-                                    const float4 a = *reinterpret_cast<const float4*>(wpart + w * 8 + v4 * 4);
-                                    sum[v4 * 4] += a.x; sum[v4 * 4 + 1] += a.y; sum[v4 * 4 + 2] += a.z; sum[v4 * 4 + 3] += a.w;
+                        for (int k = 0; k < EPI_WARPS; ++k) {
+                            const int w = wlo + k;
+                            if (w < whi) {
+                                if constexpr (NV == 2) {
+                                    const float2 a = *reinterpret_cast<const float2*>(wpart + w * 8);
+                                    sum[0] += a.x; sum[1] += a.y;
+                                } else {
+#pragma unroll
+                                    for (int v4 = 0; v4 < NV / 4; ++v4) {
+                                        const float4 a = *reinterpret_cast<const float4*>(wpart + w * 8 + v4 * 4);
+                                        sum[v4 * 4] += a.x; sum[v4 * 4 + 1] += a.y; sum[v4 * 4 + 2] += a.z; sum[v4 * 4 + 3] += a.w;
+                                    }
                                 }
                             }
                         }

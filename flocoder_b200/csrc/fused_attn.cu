@@ -957,9 +957,11 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 float2 ms = make_float2(0.f, 1.f);
                 if (s < p.nb) {
                     if (n >= 32) {
-                        const int bps = n >> 5;                 // 32-row blocks per sample
+                        const int bps = n >> 5;                 // 32-row blocks per sample (at most 8: n <= 256)
                         float tx = 0.f, tq = 0.f;
-                        for (int k = 0; k < bps; ++k) { const float2 a = partial[s * bps + k]; tx += a.x; tq += a.y; }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)             // unrolled: the loads are in flight together (same order of additions)
+                            if (k < bps) { const float2 a = partial[s * bps + k]; tx += a.x; tq += a.y; }
                         const float icnt = fast_rcp((float)(C * n));
                         const float mean = tx * icnt;
                         ms = make_float2(mean, rsqrtf(fmaxf(tq * icnt - mean * mean, 0.f) + 1e-5f));

@@ -57,4 +57,5 @@ for i, name in enumerate(names):
             continue
         print(f"   step {s}: mma_start +{row[0]-start:7d} issue {row[1]-row[0] if row[1] else 0:6d} | epi_start +{row[2]-start:7d} "
               f"(after issue {row[2]-row[1] if row[1] else 0:6d}) pass1 {row[3]-row[2] if row[3] else 0:6d} reduce {row[4]-row[3] if row[4] else 0:6d} "
-              f"pass2 {row[5]-(row[4] if row[4] else row[2]):6d}")
+              f"pass2 {row[5]-(row[4] if row[4] else row[2]):6d}"
+              + (f" | fast head: tmem +{row[6]-row[3]} scatter +{row[7]-row[6]} barrier +{tl[80+s]-row[7]} finish +{row[4]-tl[80+s]}" if row[6] and tl[80 + s] else ""))
