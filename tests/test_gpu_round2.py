@@ -369,7 +369,8 @@ def test_three_channel_latents_midi_vqgan_3d_gray(compute_dtype, tol):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # the small-batch plan (quarter-filled k_attn_small tiles with four threads per (row, head); st.async hand-off of the N-split
-# stages) against the full-tile / fence-and-arrive forms of the same kernels: the arithmetic is the same in the same order
+# stages; transposed K / V projections in k_attn) against the full-tile / fence-and-arrive / row forms of the same kernels:
+# the arithmetic is the same in the same order
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B", [37, 256])
 def test_plan_switches_are_bit_identical(B, monkeypatch):
@@ -395,3 +396,4 @@ def test_plan_switches_are_bit_identical(B, monkeypatch):
     assert torch.equal(base, forward_with({"FLO_SMALL_DIV": "1"}))        # full k_attn_small tiles, one thread per (row, head)
     assert torch.equal(base, forward_with({"FLO_SMALL_DIV": "2"}))        # half tiles
     assert torch.equal(base, forward_with({"FLO_TX_HANDOFF": "0"}))       # stores -> fence -> barrier -> release-arrive hand-off
+    assert torch.equal(base, forward_with({"FLO_ATTN_NO_KTRANS": "1"}))   # K / V projected with pixels as lanes (shuffle softmax)
