@@ -832,37 +832,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                         if (dbg && et == 0) dbg[i * 8 + 7] = clock64();
                         epi_sync();
                         if (dbg && et == 0) dbg[80 + i] = clock64();
-                        if (!has_work) return;
-                        float sum[NV];
+                        // mean / rstd of every group ONCE (lane g of the first warp whose partial sums make up the group: warp 0, or
+                        // warps 0 and 4 when the two warp groups hold different channels), then a second barrier and one small load per
+                        // thread -- instead of sixteen loads, 64 adds and NG rsqrt sequences in each of the 256 threads.  Same order of
+                        // additions and the same expressions: bit-identical statistics.
+                        float2* const gstat = reinterpret_cast<float2*>(fastbuf + 96) + (wlo ? 4 : 0);
+                        if (has_work && warp == wlo && lane < NG) {
+                            float sx = 0.f, sq = 0.f;
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) sum[v] = 0.f;
-                        // fixed order: identical in every thread, deterministic.  Unrolled over the largest trip count with a
-                        // predicate, so that all loads are in flight before the first add (a counted loop was a chain of eight
-                        // load -> add round trips on the critical path of every step)
-#pragma unroll
-                        for (int k = 0; k < EPI_WARPS; ++k) {
-                            const int w = wlo + k;
-                            if (w < whi) {
-                                if constexpr (NV == 2) {
-                                    const float2 a = *reinterpret_cast<const float2*>(wpart + w * 8);
-                                    sum[0] += a.x; sum[1] += a.y;
-                                } else {
-#pragma unroll
-                                    for (int v4 = 0; v4 < NV / 4; ++v4) {
-                                        const float4 a = *reinterpret_cast<const float4*>(wpart + w * 8 + v4 * 4);
-                                        sum[v4 * 4] += a.x; sum[v4 * 4 + 1] += a.y; sum[v4 * 4 + 2] += a.z; sum[v4 * 4 + 3] += a.w;
-                                    }
-                                }
+                            for (int k = 0; k < EPI_WARPS; ++k) {
+                                const int w = wlo + k;
+                                if (w < whi) { const float2 a = *reinterpret_cast<const float2*>(wpart + w * 8 + 2 * lane); sx += a.x; sq += a.y; }
                             }
+                            const float mean = sx * icnt;
+                            const float var = fmaxf(sq * icnt - mean * mean, 0.f);
+                            const float rstd = rsqrtf(var + 1e-5f);
+                            gstat[lane] = make_float2(rstd, -mean * rstd);
                         }
+                        epi_sync();
+                        if (!has_work) return;
 #pragma unroll
                         for (int g = 0; g < NG; ++g) {
-                            const float mean = sum[2 * g] * icnt;
-                            const float var = fmaxf(sum[2 * g + 1] * icnt - mean * mean, 0.f);
-                            const float rstd = rsqrtf(var + 1e-5f);
-                            const float nmr = -mean * rstd;
+                            const float2 st = gstat[g];
 #pragma unroll
-                            for (int j = 0; j < CG; ++j) y[g * CG + j] = fmaf(y[g * CG + j], rstd, nmr);
+                            for (int j = 0; j < CG; ++j) y[g * CG + j] = fmaf(y[g * CG + j], st.x, st.y);
                         }
                     };
                     auto tail = [&](auto cw_tag) {
