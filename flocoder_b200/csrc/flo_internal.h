@@ -269,6 +269,8 @@ struct ChainParams {
     int g_max, coef_n, cpar_n;              // stats region layout: rowstat[rows*g_max] | coef[coef_n] (float2) | cpar[cpar_n] (float) |
                                             // gpar[C] (float2)
     int prod_lanes;                         // lanes of the producer warp that issue weight chunks (chunk cc -> lane cc % prod_lanes)
+    int wide;                               // 1: the grid leaves at most one CTA per SM: launch the instance without the register cap
+    int no_fast2;                           // 1: N-split stages keep the generic row-statistics GroupNorm epilogue (FLO_NO_FAST2=1)
     int tx_handoff;                         // N-split stages: 1 = the step hand-off rides on the output stores themselves (st.async +
                                             // mbarrier transaction bytes); 0 = stores, proxy fence, CTA barrier, release-arrive on every CTA
     int early_pdl;                          // 1: griddepcontrol.launch_dependents at kernel start (this grid leaves SMs idle: the next

@@ -293,8 +293,10 @@ __device__ __forceinline__ int warp_sum_scatter(float (&p)[NV], int lane) {
 constexpr int FINAL_MAX_CH = 4;     // latent channels the fused final epilogue handles (api.cu routes more to the layer-wise path)
 // FAST: every GroupNorm step of the stage takes the warp-shuffle path (one sample per CTA, one accumulator chunk per
 // thread: chosen by the planner); the generic row-statistics path is compiled out, and vice versa.
-template <int MT, bool SPLIT, int FMT, bool FAST>
-__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
+// WIDE: an instance without the two-CTAs-per-SM register cap, launched when the grid leaves at most one CTA per SM anyway; the
+// barrier-free 4x4 GroupNorm epilogue lives there (it spills under the 96-register cap and then loses to the generic one).
+template <int MT, bool SPLIT, int FMT, bool FAST, bool WIDE = false>
+__global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? FLO_CHAIN_MINB : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
                                                          const __grid_constant__ CUtensorMap tm3,
@@ -957,6 +959,150 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                 } else {
                 const int pm = (MT == 1 && G == 1 && !is_final) ? 2 : 1;   // partial columns per group in rowstat
                 const int GS = G * pm;
+                // N-split stages at 2x2 pixels: a sample's 16 padded rows are exactly one half-warp and the CTA's channels one group, so
+                // the statistics are four xor-shuffles away, the accumulator chunk stays in registers between the statistics and the
+                // normalisation, and the two warp groups (the two channel halves) meet behind ONE barrier -- no per-row partials in
+                // shared memory, no coefficient table, no second tensor-memory load.
+                bool fast2 = false;
+                if constexpr (SPLIT && MT == 1)
+                    fast2 = G == 1 && geo.PP == 16 && !is_final && (cend - cbeg == 8 || cend - cbeg == 16) && !p.no_fast2;
+                bool fast3 = false;
+                if constexpr (!SPLIT && MT == 1 && WIDE)
+                    fast3 = geo.H == 4 && geo.W == 4 && geo.nb <= 3 && !is_final && (cpg == 8 || cpg == 16) && ((cend - cbeg) & 15) == 0 &&
+                            cend > cbeg && !p.no_fast2;
+                if (fast2) {
+                    if (dbg && et == 0) dbg[i * 8 + 3] = clock64();
+                    auto body = [&](auto cw_tag) {
+                        constexpr int CW = decltype(cw_tag)::value;
+                        uint32_t av[CW];
+                        const uint32_t ta = tlane + (uint32_t)(acc_col + cbeg);
+                        if constexpr (CW == 16) tmem_ld16_issue(ta, av); else tmem_ld8_issue(ta, av);
+                        tmem_ld_wait();
+                        const bool valid = ri[0].valid;
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CW; j += 2) {
+                            const float xa = __uint_as_float(av[j]), xb = __uint_as_float(av[j + 1]);
+                            s0 += xa; q0 = fmaf(xa, xa, q0); s1 += xb; q1 = fmaf(xb, xb, q1);
+                        }
+                        float sx = valid ? s0 + s1 : 0.f, sq = valid ? q0 + q1 : 0.f;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+                        float2* const part = reinterpret_cast<float2*>(fastbuf);          // [2 warp groups][8 samples]
+                        const int sl = r >> 4;                                             // sample of this row inside the CTA
+                        if ((lane & 15) == 0) part[wg * 8 + sl] = make_float2(sx, sq);
+                        epi_sync();
+                        if (dbg && et == 0) dbg[i * 8 + 4] = clock64();
+                        uint32_t rv[CW];
+                        if (res_mode == 1) {
+                            const uint32_t tr = tlane + (uint32_t)(res_col + cbeg);
+                            if constexpr (CW == 16) tmem_ld16_issue(tr, rv); else tmem_ld8_issue(tr, rv);
+                            tmem_ld_wait();
+                        }
+                        if (!valid) return;
+                        const float2 pa = part[sl], pb = part[8 + sl];
+                        const float icnt = fast_rcp((float)(C * HW));
+                        const float mean = (pa.x + pb.x) * icnt;
+                        const float rstd = rsqrtf(fmaxf((pa.y + pb.y) * icnt - mean * mean, 0.f) + 1e-5f);
+                        float rr[CW];
+                        if (res_mode == 2) {
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)((c0 + cbeg) >> 3) * plane_bytes + (uint32_t)ri[0].pp * 16u;
+#pragma unroll
+                            for (int hb = 0; hb < CW / 8; ++hb) unpack8t<FMT>(*reinterpret_cast<const uint4*>(src + hb * plane_bytes), rr + hb * 8);
+                        } else if (res_mode == 1) {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) rr[j] = __uint_as_float(rv[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) rr[j] = 0.f;
+                        }
+                        // FiLM(GroupNorm(x)) = x a + b with a = rstd gamma (1 + scale), b = (beta - mean rstd gamma)(1 + scale) + shift
+                        const float4* gp = reinterpret_cast<const float4*>(gpar + cbeg);                    // (gamma, beta) x 2 channels
+                        const float4* cf = reinterpret_cast<const float4*>(coef + ri[0].s * C + cbeg);      // (1 + scale, shift) x 2 channels
+                        float v[CW];
+                        float sxa = 0.f, sqa = 0.f, sxb = 0.f, sqb = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CW; j += 2) {
+                            const float4 gb = gp[j >> 1], f = cf[j >> 1];
+                            float a0 = rstd * gb.x, b0 = gb.y - mean * a0, a1 = rstd * gb.z, b1 = gb.w - mean * a1;
+                            a0 *= f.x; b0 = fmaf(b0, f.x, f.y); a1 *= f.z; b1 = fmaf(b1, f.z, f.w);
+                            float ya = fmaf(__uint_as_float(av[j]), a0, b0);
+                            float yb = fmaf(__uint_as_float(av[j + 1]), a1, b1);
+                            ya = fast_silu_t<FMT>(ya); yb = fast_silu_t<FMT>(yb);
+                            ya += rr[j]; yb += rr[j + 1];
+                            v[j] = ya; v[j + 1] = yb;
+                            sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);
+                        }
+                        psx[0] += sxa + sxb; psq[0] += sqa + sqb;
+#pragma unroll
+                        for (int hb = 0; hb < CW / 8; ++hb) write8(ri[0], ((c0 + cbeg) >> 3) + hb, v + hb * 8);
+                    };
+                    if (cw8) body(IntTag<8>()); else body(IntTag<16>());
+                } else if (fast3) {
+                    // 4x4 pixels, up to three samples per CTA: the valid rows of sample s (padded positions 36 s + 7 ..) all lie in
+                    // warp s of each warp group, and a 16-channel chunk holds whole groups -- so a (sample, group) sum is one warp
+                    // butterfly away and every chunk is normalised out of registers with no barrier at all.
+                    if (dbg && et == 0) dbg[i * 8 + 3] = clock64();
+                    const bool valid = ri[0].valid;
+                    const float icnt = fast_rcp((float)(cpg * HW));
+                    for (int c = cbeg; c < cend; c += 16) {
+                        uint32_t av[16], rv[16];
+                        tmem_ld16_issue(tlane + (uint32_t)(acc_col + c), av);
+                        if (res_mode == 1) tmem_ld16_issue(tlane + (uint32_t)(res_col + c), rv);
+                        tmem_ld_wait();
+                        // partial sums of the chunk's groups: one group of 16 channels, or two of 8
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float xa = __uint_as_float(av[j]), xb = __uint_as_float(av[8 + j]);
+                            s0 += xa; q0 = fmaf(xa, xa, q0); s1 += xb; q1 = fmaf(xb, xb, q1);
+                        }
+                        if (!valid) { s0 = 0.f; q0 = 0.f; s1 = 0.f; q1 = 0.f; }
+                        if (cpg == 16) { s0 += s1; q0 += q1; }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                            if (cpg == 8) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+                        }
+                        if (!valid) continue;
+                        const float m0 = s0 * icnt, r0 = rsqrtf(fmaxf(q0 * icnt - m0 * m0, 0.f) + 1e-5f);
+                        float m1 = m0, r1 = r0;
+                        if (cpg == 8) { m1 = s1 * icnt; r1 = rsqrtf(fmaxf(q1 * icnt - m1 * m1, 0.f) + 1e-5f); }
+                        float rr[16];
+                        if (res_mode == 2) {
+                            const uint8_t* src = smem + res_slot_off + (uint32_t)(c >> 3) * plane_bytes + (uint32_t)ri[0].pp * 16u;
+#pragma unroll
+                            for (int hb = 0; hb < 2; ++hb) unpack8t<FMT>(*reinterpret_cast<const uint4*>(src + hb * plane_bytes), rr + hb * 8);
+                        } else if (res_mode == 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rr[j] = __uint_as_float(rv[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rr[j] = 0.f;
+                        }
+                        const float4* gp = reinterpret_cast<const float4*>(gpar + c);
+                        const float4* cf = reinterpret_cast<const float4*>(coef + ri[0].s * C + c);
+                        float v[16];
+                        float sxa = 0.f, sqa = 0.f, sxb = 0.f, sqb = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float mean = j < 8 ? m0 : m1, rstd = j < 8 ? r0 : r1;
+                            const float4 gb = gp[j >> 1], f = cf[j >> 1];
+                            float a0 = rstd * gb.x, b0 = gb.y - mean * a0, a1 = rstd * gb.z, b1 = gb.w - mean * a1;
+                            a0 *= f.x; b0 = fmaf(b0, f.x, f.y); a1 *= f.z; b1 = fmaf(b1, f.z, f.w);
+                            float ya = fmaf(__uint_as_float(av[j]), a0, b0);
+                            float yb = fmaf(__uint_as_float(av[j + 1]), a1, b1);
+                            ya = fast_silu_t<FMT>(ya); yb = fast_silu_t<FMT>(yb);
+                            ya += rr[j]; yb += rr[j + 1];
+                            v[j] = ya; v[j + 1] = yb;
+                            sxa += ya; sqa = fmaf(ya, ya, sqa); sxb += yb; sqb = fmaf(yb, yb, sqb);
+                        }
+                        psx[0] += sxa + sxb; psq[0] += sqa + sqb;
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) write8(ri[0], (c >> 3) + hb, v + hb * 8);
+                    }
+                    if (dbg && et == 0) dbg[i * 8 + 4] = clock64();
+                } else {
                 // pass 1: per-row (sum, sumsq) per group
                 {
                     float run_sx = 0.f, run_sq = 0.f;
@@ -1058,6 +1204,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2) ? FLO_CHAIN_MINB : 1)
                         for (int hb = 0; hb < CW / 8; ++hb) write8(ri[k], ((c0 + c) >> 3) + hb, v + hb * 8);
                     }
                 });
+                }
                 if (pn_g >= 0) {
                     // ---- fused PreNorm of the following attention block: GroupNorm(1, C) of the 16-bit result
                     const int pm2 = (MT == 1) ? 2 : 1;
@@ -1147,6 +1294,8 @@ cudaError_t fused_configure() {
     if (e == cudaSuccess) e = chain_attr<4, false, false>();
     if (e == cudaSuccess) e = chain_attr<1, false, true>();
     if (e == cudaSuccess) e = chain_attr<2, false, true>();
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     return attn_configure();
 }
@@ -1191,7 +1340,8 @@ int fused_max_active_clusters(int nsplit, int smem_bytes) {
 }
 
 template <int FMT>
-static const void* chain_fn(int mt, bool split, bool fast) {
+static const void* chain_fn(int mt, bool split, bool fast, bool wide) {
+    if (wide && !fast && !split && mt == 1) return (const void*)k_chain<1, false, FMT, false, true>;
     if (fast) {
         if (split || mt > 2) return nullptr;
         return mt == 1 ? (const void*)k_chain<1, false, FMT, true> : (const void*)k_chain<2, false, FMT, true>;
@@ -1206,7 +1356,7 @@ static const void* chain_fn(int mt, bool split, bool fast) {
 }
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
     if (p.nsplit > 1 && p.n_mtiles != 1) return cudaErrorInvalidValue;
-    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0) : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0);
+    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0) : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0);
     if (!fn) return cudaErrorInvalidValue;
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
     return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);

@@ -892,7 +892,19 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             esync();
             if (dbg && et == 0) dbg[28] = clock64();
             if (n >= 32) {
-                // nothing: the normalisation pass forms mean / rstd from `partial`
+                // one thread per sample adds the n / 32 block sums (fixed order) and publishes mean / rstd; a second barrier is cheaper
+                // than the same eight loads, sixteen adds, rcp and rsqrt in every thread on the tail of the kernel
+                if (et < p.nb) {
+                    const int bps = n >> 5;
+                    float tx = 0.f, tq = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < bps) { const float2 a = partial[et * bps + k]; tx += a.x; tq += a.y; }
+                    const float icnt = fast_rcp((float)(C * n));
+                    const float mean = tx * icnt;
+                    stat[et] = make_float2(mean, rsqrtf(fmaxf(tq * icnt - mean * mean, 0.f) + 1e-5f));
+                }
+                esync();
             } else {
             if (et < p.nb * parts) {
                 const int lgp = 31 - __clz(parts);
@@ -955,20 +967,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const int b = b0 + s;
                 float2 ms = make_float2(0.f, 1.f);
-                if (s < p.nb) {
-                    if (n >= 32) {
-                        const int bps = n >> 5;                 // 32-row blocks per sample (at most 8: n <= 256)
-                        float tx = 0.f, tq = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)             // unrolled: the loads are in flight together (same order of additions)
-                            if (k < bps) { const float2 a = partial[s * bps + k]; tx += a.x; tq += a.y; }
-                        const float icnt = fast_rcp((float)(C * n));
-                        const float mean = tx * icnt;
-                        ms = make_float2(mean, rsqrtf(fmaxf(tq * icnt - mean * mean, 0.f) + 1e-5f));
-                    } else {
-                        ms = stat[s];
-                    }
-                }
+                if (s < p.nb) ms = stat[s];
                 if (dbg && et == 0) dbg[30] = clock64();
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
                 // the residual rows of the NEXT channel chunk are requested before this chunk is processed
