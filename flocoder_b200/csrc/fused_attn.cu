@@ -172,10 +172,15 @@ __device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
 }
 
 // HC: heads per CTA (4; 2 = the head split), a template parameter so that the channel loops keep compile-time bounds
-template <int HC>
+// LEAN: the instance the default plan launches (linear attention, transposed K / V projections): `full` and `ktrans` are
+// compile-time there, so the mid-attention path, the row-form first epilogue and their helpers are not part of its code
+// (200 KB -> the kernels are latency chains that stall on instruction fetch as much as on memory)
+template <int HC, bool LEAN = false>
 __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const bool is_full = LEAN ? false : (p.full != 0);
+    const bool is_kt = LEAN ? true : (p.ktrans != 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     // Warp roles: [0, EW) epilogue (EW = 4, or 8 when a sample spans two M tiles: one tile per warp group, both groups
     // share the TMEM lane quadrants), EW = TMA producer, EW + 1 = MMA issuer.
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     // end of the batch, rows past the last sample of a partly filled M tile.  A CTA whose rows are all live skips the clear
     // (152 KB of shared-memory stores at the 16x16 level, on the critical path of every CTA that is not in the first wave):
     // every contraction runs over the rows of ONE sample, and what the unwritten planes feed are accumulator columns nobody loads.
-    const bool all_live = !p.full && HS == 1 && p.n_pad == p.n && ((p.nb * p.n) & 127) == 0 && b0 + p.nb <= p.B;
+    const bool all_live = !is_full && HS == 1 && p.n_pad == p.n && ((p.nb * p.n) & 127) == 0 && b0 + p.nb <= p.B;
     if (!all_live)
         for (int i = tid * 16; i < p.zero_bytes; i += n_thr * 16)
             *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0, 0, 0, 0);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && lane == 0) dbg[0] = clock64();
             // ---- phase 0: K and V convolutions (and Q for the mid attention)
             const uint32_t wb_off = hrank * (uint32_t)NCH * 16u;      // this CTA's channels inside every 128-channel weight tile
-            const bool tr = p.ktrans != 0;
+            const bool tr = is_kt != 0;
             // transposed projection D[channel lanes][pixel columns] = W (A operand: the K-major weight tile, 128 rows x 16 B per K half)
             // x x^ (B operand: the CTA's nb * n pixel rows of the input tile, planes of 8 channels)
             auto conv_T = [&](int col) {
@@ -281,12 +286,12 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_k, p.qkv_chunks, p.qkv_S);
             attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_v, p.qkv_chunks, p.qkv_S);
             }
-            if (p.full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_q, p.qkv_chunks, p.qkv_S);
+            if (is_full) attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.xh_off, xh_plane, NCH, 128, wb_off, p.col_q, p.qkv_chunks, p.qkv_S);
             if (dbg && lane == 0) dbg[1] = clock64();
             if (elect_one()) umma_commit(bar_mma);
             __syncwarp();
             int ph = 0;
-            if (!p.full) {
+            if (!is_full) {
                 // ---- phase 1: context per sample (both operands MN-major, K = pixels), then the Q convolution
                 named_bar_sync(2, n_epi + 32); ++ph;
                 tc_fence_after();
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             named_bar_sync(2, n_epi + 32); ++ph;
             tc_fence_after();
             if (dbg && lane == 0) dbg[24] = clock64();
-            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, p.full ? p.p_off : p.v_off, plane, C, C, 0u, p.col_proj,
+            attn_conv(p, smem_base, tmem_base, bar_full, bar_empty, rs, is_full ? p.p_off : p.v_off, plane, C, C, 0u, p.col_proj,
                       p.o_chunks, p.o_S);
             if (elect_one()) umma_commit(bar_mma);
             __syncwarp();
@@ -382,8 +387,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         float* par = reinterpret_cast<float*>(stat + 128);                  // [3][128]: bias, gamma, beta
         for (int c = et; c < C; c += n_epi) {
             par[c] = p.fblob[p.bo_off + c];
-            par[128 + c] = p.full ? 1.0f : p.fblob[p.gamma_off + c];
-            par[256 + c] = p.full ? 0.0f : p.fblob[p.beta_off + c];
+            par[128 + c] = is_full ? 1.0f : p.fblob[p.gamma_off + c];
+            par[256 + c] = is_full ? 0.0f : p.fblob[p.beta_off + c];
         }
         esync();
         griddep_wait();
@@ -391,8 +396,8 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         mbar_wait(bar_mma, ph & 1); ++ph;
         tc_fence_after();
         if (dbg && r == 0) dbg[2] = clock64();
-        if (!p.full) {
-          if (p.ktrans) {
+        if (!is_full) {
+          if (is_kt) {
             // ================= EPI 0, transposed: tensor-memory lane = channel, columns = the CTA's pixels =================
             // A warp group owns 64 pixel columns of one sample; the softmax over pixels is a loop per thread (no shuffles), the
             // groups of a sample exchange one maximum per channel through shared memory, and k~ / v go to the operand slots K-major
@@ -747,7 +752,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         // the residual rows of this thread's first tile are requested BEFORE waiting for the to_out MMAs: their L2 round trip
         // (~800 cycles) otherwise sits on the critical path between the statistics barrier and the stores
         uint4 pre_xa = make_uint4(0, 0, 0, 0), pre_xb = pre_xa;
-        if (!p.full && HS == 1 && t0 < p.n_mtiles && cpart == 0) {
+        if (!is_full && HS == 1 && t0 < p.n_mtiles && cpart == 0) {
             const int rd = t0 * 128 + r, s = rd >> lgn, px = rd & (n - 1);
             if (s < p.nb && b0 + s < p.B) {
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
@@ -854,7 +859,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
         } else {
-        if (!p.full) {
+        if (!is_full) {
             // (the C output channels are not split: with 16 epilogue warps the second channel group only keeps the barriers)
             for (int t = t0; t < p.n_mtiles && cpart == 0; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
@@ -929,7 +934,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         }
         const float* gamma = par + 128;
         const float* beta = par + 256;
-        if (p.full) {
+        if (is_full) {
             // 32 valid rows (TMEM quadrant 0): warp 0 moves the projection to shared memory, then every warp finishes a
             // quarter of the channels: + bias + x (unet.py:122, Residual)
             constexpr int QP = 132;
@@ -1542,6 +1547,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
 cudaError_t attn_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_attn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1557,7 +1563,8 @@ cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_ma
                                    : (p.full ? (const void*)k_attn_small<4, false> : (const void*)k_attn_small<4, true>);
         return launch_pdl(fn, grid, SMALL_THREADS, (size_t)p.smem_bytes, s, args, 1);
     }
-    return launch_pdl(p.hc == 2 ? (const void*)k_attn<2> : (const void*)k_attn<4>, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
+    const void* fn = p.hc == 2 ? (const void*)k_attn<2> : ((p.ktrans && !p.full) ? (const void*)k_attn<4, true> : (const void*)k_attn<4>);
+    return launch_pdl(fn, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
 }
 
 }  // namespace flo
