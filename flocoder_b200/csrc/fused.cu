@@ -295,7 +295,10 @@ constexpr int FINAL_MAX_CH = 4;     // latent channels the fused final epilogue 
 // thread: chosen by the planner); the generic row-statistics path is compiled out, and vice versa.
 // WIDE: an instance without the two-CTAs-per-SM register cap, launched when the grid leaves at most one CTA per SM anyway; the
 // barrier-free 4x4 GroupNorm epilogue lives there (it spills under the 96-register cap and then loses to the generic one).
-template <int MT, bool SPLIT, int FMT, bool FAST, bool WIDE = false>
+// ENDS: bit 0 = the stage may hold the init conv (first stage), bit 1 = the final conv + integrator update (last stage).  The FAST
+// instances are compiled per combination: the 96-register cap that keeps two CTAs on an SM made the all-in-one instance spill on
+// its hot path (280 bytes of spill loads), and the stages that hold neither ran 2.5 % faster end to end without that code.
+template <int MT, bool SPLIT, int FMT, bool FAST, bool WIDE = false, int ENDS = 3>
 __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? FLO_CHAIN_MINB : 1) k_chain(const __grid_constant__ CUtensorMap tm0,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2,
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? 
             const int epi = p.st[i].epi, Ctot = p.st[i].C, acc_col = p.st[i].acc_col, res_col = p.st[i].res_col;
             const int C = Ctot >> lgQ, c0 = (int)qrank * C;      // this CTA's channels [c0, c0 + C) of the step's Ctot
             const int res_mode = p.st[i].res_mode, res_slot_off = p.st[i].res_slot_off;
-            const int is_final = p.st[i].final, pn_g = p.st[i].pn_g;
+            const int is_final = (ENDS & 2) ? p.st[i].final : 0, pn_g = p.st[i].pn_g;
             const int out_slot_off = p.st[i].out_slot_off;
             uint4* const og = p.st[i].out_g >= 0 ? reinterpret_cast<uint4*>(p.gt[p.st[i].out_g]) : nullptr;
             // this thread's channels of the step: one tile -> the warp groups split the channels (the final epilogue needs all
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? 
             float2* const pnpar = reinterpret_cast<float2*>(fastbuf + 128) + (2 + (i & 1)) * p.max_c;    // PreNorm (gamma, beta)
 
             // small constants staged while the MMAs of this step run
-            if (epi == CE_INIT) {
+            if ((ENDS & 1) && epi == CE_INIT) {
                 const float* w = fblob + p.init_w_off;
                 const float* bias = fblob + p.init_b_off;
                 const int cin0 = p.cin0;
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? 
             // kernel start was measured to slow the running kernel (profiles/r01_pdl_gaps.txt)
             if (i == n_steps - 1) griddep_launch();
 
-            if (epi == CE_INIT) {
+            if ((ENDS & 1) && epi == CE_INIT) {
                 // ---- init_conv 1x1 from the NCHW fp32 integrator state (unet.py:295)
                 const float* xs = ctrl->xs;
                 const int cin0 = p.cin0;
@@ -1286,6 +1289,12 @@ static cudaError_t chain_attr() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<MT, SPLIT, 1, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
 }
+template <int MT, int ENDS>
+static cudaError_t fast_ends_attr() {
+    cudaError_t e = cudaFuncSetAttribute(k_chain<MT, false, 0, true, false, ENDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<MT, false, 1, true, false, ENDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
+}
 cudaError_t fused_configure() {
     cudaError_t e = chain_attr<1, false, false>();
     if (e == cudaSuccess) e = chain_attr<1, true, false>();
@@ -1294,6 +1303,12 @@ cudaError_t fused_configure() {
     if (e == cudaSuccess) e = chain_attr<4, false, false>();
     if (e == cudaSuccess) e = chain_attr<1, false, true>();
     if (e == cudaSuccess) e = chain_attr<2, false, true>();
+    if (e == cudaSuccess) e = fast_ends_attr<1, 0>();
+    if (e == cudaSuccess) e = fast_ends_attr<1, 1>();
+    if (e == cudaSuccess) e = fast_ends_attr<1, 2>();
+    if (e == cudaSuccess) e = fast_ends_attr<2, 0>();
+    if (e == cudaSuccess) e = fast_ends_attr<2, 1>();
+    if (e == cudaSuccess) e = fast_ends_attr<2, 2>();
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
@@ -1340,10 +1355,13 @@ int fused_max_active_clusters(int nsplit, int smem_bytes) {
 }
 
 template <int FMT>
-static const void* chain_fn(int mt, bool split, bool fast, bool wide) {
+static const void* chain_fn(int mt, bool split, bool fast, bool wide, int ends) {
     if (wide && !fast && !split && mt == 1) return (const void*)k_chain<1, false, FMT, false, true>;
     if (fast) {
         if (split || mt > 2) return nullptr;
+        if (ends == 0) return mt == 1 ? (const void*)k_chain<1, false, FMT, true, false, 0> : (const void*)k_chain<2, false, FMT, true, false, 0>;
+        if (ends == 1) return mt == 1 ? (const void*)k_chain<1, false, FMT, true, false, 1> : (const void*)k_chain<2, false, FMT, true, false, 1>;
+        if (ends == 2) return mt == 1 ? (const void*)k_chain<1, false, FMT, true, false, 2> : (const void*)k_chain<2, false, FMT, true, false, 2>;
         return mt == 1 ? (const void*)k_chain<1, false, FMT, true> : (const void*)k_chain<2, false, FMT, true>;
     }
     switch (mt) {
@@ -1356,7 +1374,10 @@ static const void* chain_fn(int mt, bool split, bool fast, bool wide) {
 }
 cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid, cudaStream_t s) {
     if (p.nsplit > 1 && p.n_mtiles != 1) return cudaErrorInvalidValue;
-    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0) : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0);
+    int ends = 0;
+    for (int i = 0; i < p.n_steps; ++i) ends |= (p.st[i].epi == CE_INIT ? 1 : 0) | (p.st[i].final != 0 ? 2 : 0);
+    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends)
+                           : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends);
     if (!fn) return cudaErrorInvalidValue;
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
     return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);
