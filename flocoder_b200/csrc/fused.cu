@@ -1303,6 +1303,10 @@ cudaError_t fused_configure() {
     if (e == cudaSuccess) e = chain_attr<4, false, false>();
     if (e == cudaSuccess) e = chain_attr<1, false, true>();
     if (e == cudaSuccess) e = chain_attr<2, false, true>();
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, true, 0, false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, true, 1, false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 0, false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain<1, false, 1, false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = fast_ends_attr<1, 0>();
     if (e == cudaSuccess) e = fast_ends_attr<1, 1>();
     if (e == cudaSuccess) e = fast_ends_attr<1, 2>();
@@ -1356,6 +1360,10 @@ int fused_max_active_clusters(int nsplit, int smem_bytes) {
 
 template <int FMT>
 static const void* chain_fn(int mt, bool split, bool fast, bool wide, int ends) {
+    if (ends == 0 && !fast && mt == 1) {
+        if (split) return (const void*)k_chain<1, true, FMT, false, false, 0>;
+        if (wide) return (const void*)k_chain<1, false, FMT, false, true, 0>;
+    }
     if (wide && !fast && !split && mt == 1) return (const void*)k_chain<1, false, FMT, false, true>;
     if (fast) {
         if (split || mt > 2) return nullptr;
