@@ -1058,7 +1058,9 @@ __device__ __forceinline__ int segred16(float (&v)[16], int lane) {
     return chan;
 }
 
-template <int NPX, bool LINEAR>
+// QT: the quarter-tile instance (32 live rows, small-batch plan) -- `quarter` is a compile-time constant there and the full-tile
+// forms of the first epilogue and of the attention core are not part of its code (and vice versa)
+template <int NPX, bool LINEAR, bool QT = false>
 __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_constant__ CUtensorMap tm_xh,
                                                                    const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1194,7 +1196,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
         // chunk's scratch rows live in the input tile, which is dead once the projections have completed).
         // quarter tile (32 live rows): twelve of the sixteen warps own no rows.  The four that do only MOVE k and v to the staging rows
         // and then turn to q; the column softmax of k runs out of shared memory on the others meanwhile (see below)
-        const bool quarter = live_rows == 32;
+        const bool quarter = QT;
         const bool qsm = quarter && LINEAR;
         if (wact) {
             const int cA = part * 32;
@@ -1552,6 +1554,10 @@ cudaError_t attn_configure() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
 }
 
@@ -1559,8 +1565,11 @@ cudaError_t launch_pdl(const void* fn, int grid, int block, size_t smem, cudaStr
 cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_map, int grid, cudaStream_t s) {
     void* args[2] = {(void*)&xh_map, (void*)&p};
     if (p.small) {
-        const void* fn = p.n == 16 ? (p.full ? (const void*)k_attn_small<16, false> : (const void*)k_attn_small<16, true>)
-                                   : (p.full ? (const void*)k_attn_small<4, false> : (const void*)k_attn_small<4, true>);
+        const bool qt = p.nb * p.n == 32;
+        const void* fn = p.n == 16 ? (p.full ? (qt ? (const void*)k_attn_small<16, false, true> : (const void*)k_attn_small<16, false>)
+                                             : (qt ? (const void*)k_attn_small<16, true, true> : (const void*)k_attn_small<16, true>))
+                                   : (p.full ? (qt ? (const void*)k_attn_small<4, false, true> : (const void*)k_attn_small<4, false>)
+                                             : (qt ? (const void*)k_attn_small<4, true, true> : (const void*)k_attn_small<4, true>));
         return launch_pdl(fn, grid, SMALL_THREADS, (size_t)p.smem_bytes, s, args, 1);
     }
     const void* fn = p.hc == 2 ? (const void*)k_attn<2> : ((p.ktrans && !p.full) ? (const void*)k_attn<4, true> : (const void*)k_attn<4>);
