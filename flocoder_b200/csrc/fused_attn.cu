@@ -175,7 +175,8 @@ __device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
 // LEAN: the instance the default plan launches (linear attention, transposed K / V projections): `full` and `ktrans` are
 // compile-time there, so the mid-attention path, the row-form first epilogue and their helpers are not part of its code
 // (200 KB -> the kernels are latency chains that stall on instruction fetch as much as on memory)
-template <int HC, bool LEAN = false>
+// NT: M tiles per CTA as a compile-time constant (1: the 8x8 level with 8 epilogue warps, 2: 16x16 with 16; 0: run time)
+template <int HC, bool LEAN = false, int NT = 0>
 __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     // Warp roles: [0, EW) epilogue (EW = 4, or 8 when a sample spans two M tiles: one tile per warp group, both groups
     // share the TMEM lane quadrants), EW = TMA producer, EW + 1 = MMA issuer.
-    const int EW = p.epi_warps, n_epi = EW * 32, n_thr = (int)blockDim.x;
+    const int EW = NT == 2 ? 16 : (NT == 1 ? 8 : p.epi_warps), n_epi = EW * 32, n_thr = (int)blockDim.x;
+    const int n_mtiles_k = NT ? NT : p.n_mtiles;
+    const bool n_ge32 = (LEAN && NT) ? true : (p.n >= 32);
     const int w_prod = EW, w_mma = EW + 1;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_base + p.bar_off;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         // the softmax epilogues are chains of TMEM loads, shuffles and MUFU ops, and four warps per scheduler hide what two cannot
         // One M tile per CTA (8x8 level, two samples) with EW = 8: both groups work on tile 0 and split the channels the same way
         // (four warps per SM left every scheduler idle most of the time: 6 k-cycle softmax epilogues on 16 k exponentials).
-        const bool one_tile_split = EW == 8 && p.n_mtiles == 1;
+        const bool one_tile_split = EW == 8 && n_mtiles_k == 1;
         const int half = (EW >= 8 && !one_tile_split) ? (grp & 1) : 0;
         const int t0 = half, tstep = (EW >= 8 && !one_tile_split) ? 2 : 1;
         const int cpart = EW == 16 ? (grp >> 1) : (one_tile_split ? grp : 0), ncp = (EW == 16 || one_tile_split) ? 2 : 1;
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         float* kmax = reinterpret_cast<float*>(smem + p.kmax_off);          // [nb][128]
         float* kpart = kmax + p.nb * 128;                                   // [n_mtiles*4][128]
         float2* rowstat = reinterpret_cast<float2*>(smem + p.stats_off);    // [n_mtiles*128]
-        float2* partial = rowstat + p.n_mtiles * 128;
+        float2* partial = rowstat + n_mtiles_k * 128;
         float2* stat = partial + 256;
         int ph = 0;
         // to_out bias and GroupNorm affine into shared memory while the first MMAs run (they are read per channel chunk
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             const int seg = n < 32 ? n : 32;                 // lanes per sample inside one warp
             // two 16-channel chunks per iteration: both TMEM loads are in flight together and the two shuffle
             // reductions are independent, so their latencies overlap
-            for (int t = t0; t < p.n_mtiles; t += tstep) {
+            for (int t = t0; t < n_mtiles_k; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 for (int c32 = ch_lo; c32 < ch_hi; c32 += 32) {
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             }
             if (dbg && r == 0) dbg[3] = clock64();
             esync();
-            if (n >= 32) {
+            if (n_ge32) {
                 const int wps = n >> 5;                      // warp-rows per sample
                 for (int idx = et; idx < p.nb * 128; idx += n_epi) {
                     const int s = idx >> 7, c = idx & 127;
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
                 esync();
             }
-            for (int t = t0; t < p.n_mtiles; t += tstep) {
+            for (int t = t0; t < n_mtiles_k; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     }
                 }
             }
-            for (int t = t0; t < p.n_mtiles; t += tstep) {
+            for (int t = t0; t < n_mtiles_k; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const uint32_t row_off = (uint32_t)(s * n_pad + px) * 16u;
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         // the residual rows of this thread's first tile are requested BEFORE waiting for the to_out MMAs: their L2 round trip
         // (~800 cycles) otherwise sits on the critical path between the statistics barrier and the stores
         uint4 pre_xa = make_uint4(0, 0, 0, 0), pre_xb = pre_xa;
-        if (!is_full && HS == 1 && t0 < p.n_mtiles && cpart == 0) {
+        if (!is_full && HS == 1 && t0 < n_mtiles_k && cpart == 0) {
             const int rd = t0 * 128 + r, s = rd >> lgn, px = rd & (n - 1);
             if (s < p.nb && b0 + s < p.B) {
                 const uint4* xsrc = reinterpret_cast<const uint4*>(p.x2);
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
         } else {
         if (!is_full) {
             // (the C output channels are not split: with 16 epilogue warps the second channel group only keeps the barriers)
-            for (int t = t0; t < p.n_mtiles && cpart == 0; t += tstep) {
+            for (int t = t0; t < n_mtiles_k && cpart == 0; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn;
                 const bool valid = s < p.nb && b0 + s < p.B;
                 float sx = 0.f, sq = 0.f;
@@ -880,7 +883,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     }
                 }
                 sx += sx2; sq += sq2;
-                if (n >= 32) {
+                if (n_ge32) {
                     // a warp's 32 rows lie in one sample: reduce with shuffles, one partial per 32-row block, ONE barrier;
                     // every thread then adds its sample's n/32 block sums itself (fixed order: deterministic)
                     if (!valid) { sx = 0.f; sq = 0.f; }
@@ -896,7 +899,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             if (dbg && et == 0) dbg[27] = clock64();
             esync();
             if (dbg && et == 0) dbg[28] = clock64();
-            if (n >= 32) {
+            if (n_ge32) {
                 // one thread per sample adds the n / 32 block sums (fixed order) and publishes mean / rstd; a second barrier is cheaper
                 // than the same eight loads, sixteen adds, rcp and rsqrt in every thread on the tail of the kernel
                 if (et < p.nb) {
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 }
             }
         } else {
-            for (int t = t0; t < p.n_mtiles && cpart == 0; t += tstep) {
+            for (int t = t0; t < n_mtiles_k && cpart == 0; t += tstep) {
                 const int rd = t * 128 + r, s = rd >> lgn, px = rd & (n - 1);
                 const bool valid = s < p.nb && b0 + s < p.B;
                 const int b = b0 + s;
@@ -1550,6 +1553,8 @@ cudaError_t attn_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_attn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1573,6 +1578,10 @@ cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_ma
         return launch_pdl(fn, grid, SMALL_THREADS, (size_t)p.smem_bytes, s, args, 1);
     }
     const void* fn = p.hc == 2 ? (const void*)k_attn<2> : ((p.ktrans && !p.full) ? (const void*)k_attn<4, true> : (const void*)k_attn<4>);
+    if (p.hc == 4 && p.ktrans && !p.full && p.n >= 64) {
+        if (p.n_mtiles == 2 && p.epi_warps == 16) fn = (const void*)k_attn<4, true, 2>;
+        if (p.n_mtiles == 1 && p.epi_warps == 8) fn = (const void*)k_attn<4, true, 1>;
+    }
     return launch_pdl(fn, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
 }
 
