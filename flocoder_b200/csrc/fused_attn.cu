@@ -78,14 +78,14 @@ __device__ __forceinline__ void attn_conv(const AttnFusedParams& p, uint32_t sme
     }
 }
 
-__device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, int px, int c16, const float* v) {
+__device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, int px, int c16, const float* v, int fmt) {
     const int ncb = p.C >> 3;
     const int lgW = 31 - __clz(p.W);
     const int h = px >> lgW, w = px & (p.W - 1);
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const int cb = (c16 >> 3) + hb;
-        const uint4 u = pack8(v + hb * 8, p.fmt);
+        const uint4 u = pack8(v + hb * 8, fmt);
         if (p.out) reinterpret_cast<uint4*>(p.out)[(size_t)(cb * p.B + b) * p.n + px] = u;
         if (p.out_un) {
             const int plane = ((h & 1) * 2 + (w & 1)) * ncb + cb;
@@ -107,9 +107,9 @@ __device__ __forceinline__ void attn_write_out(const AttnFusedParams& p, int b, 
 // blocks of the two source pixels whose copies land at output columns w and w + W: the W lanes of a row then write W * 16
 // CONTIGUOUS bytes per store (whole 32-byte sectors) instead of four half-filled sectors per lane -- the scattered form ran at
 // one sector per cycle and cost 9.5k cycles for the C = 128 output of the 2x2 level (profiles/r02_attn_small_timeline.txt).
-__device__ __forceinline__ void attn_write_out_w(const AttnFusedParams& p, int b, int px, int c16, const float* v, bool valid) {
+__device__ __forceinline__ void attn_write_out_w(const AttnFusedParams& p, int b, int px, int c16, const float* v, bool valid, int fmt) {
     if (!p.out_up || p.W < 2) {
-        if (valid) attn_write_out(p, b, px, c16, v);
+        if (valid) attn_write_out(p, b, px, c16, v, fmt);
         return;
     }
     const int ncb = p.C >> 3;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void attn_write_out_w(const AttnFusedParams& p, int b
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
         const int cb = (c16 >> 3) + hb;
-        const uint4 u = pack8(v + hb * 8, p.fmt);
+        const uint4 u = pack8(v + hb * 8, fmt);
         uint4 a, c;
         a.x = __shfl_sync(0xffffffffu, u.x, src0); a.y = __shfl_sync(0xffffffffu, u.y, src0);
         a.z = __shfl_sync(0xffffffffu, u.z, src0); a.w = __shfl_sync(0xffffffffu, u.w, src0);
@@ -176,10 +176,12 @@ __device__ __forceinline__ int colmax16(float (&v)[16], int lane) {
 // compile-time there, so the mid-attention path, the row-form first epilogue and their helpers are not part of its code
 // (200 KB -> the kernels are latency chains that stall on instruction fetch as much as on memory)
 // NT: M tiles per CTA as a compile-time constant (1: the 8x8 level with 8 epilogue warps, 2: 16x16 with 16; 0: run time)
-template <int HC, bool LEAN = false, int NT = 0>
+// FMTK: the 16-bit operand format as a compile-time constant (0 fp16, 1 bf16; -1: run time)
+template <int HC, bool LEAN = false, int NT = 0, int FMTK = -1>
 __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant__ CUtensorMap tm_xh,
                                                         const __grid_constant__ AttnFusedParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int fmt_k = FMTK >= 0 ? FMTK : p.fmt;
     const bool is_full = LEAN ? false : (p.full != 0);
     const bool is_kt = LEAN ? true : (p.ktrans != 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             // transposed projection D[channel lanes][pixel columns] = W (A operand: the K-major weight tile, 128 rows x 16 B per K half)
             // x x^ (B operand: the CTA's nb * n pixel rows of the input tile, planes of 8 channels)
             auto conv_T = [&](int col) {
-                const uint32_t idesc = make_idesc16(128, p.nb * n, p.fmt, 0, 0);
+                const uint32_t idesc = make_idesc16(128, p.nb * n, fmt_k, 0, 0);
                 for (int ci = 0; ci < p.qkv_chunks; ++ci) {
                     const int slot = rs.cc & (ATTN_RING - 1);
                     mbar_wait(bar_full + 8 * slot, (rs.cc / ATTN_RING) & 1);
@@ -301,14 +303,14 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 if (dbg && lane == 0) dbg[8] = clock64();
                 // M = 128 channel rows are always read (with two heads per CTA rows 64..127 are whatever follows the P slot:
                 // their accumulator lanes are never loaded), N = this CTA's (h, e) channels + the ones block
-                const uint32_t idesc_ctx = make_idesc16(128, NCH + 16, p.fmt, 1, 1);
+                const uint32_t idesc_ctx = make_idesc16(128, NCH + 16, fmt_k, 1, 1);
                 {
                     const int nb = p.nb, col_ctx = p.col_ctx;
                     const uint32_t p_off = p.p_off, v_off = p.v_off;
                     if (tr) {
                         // k~ [128 channel rows][pixels] and v [144 rows: channels, then the ones row][pixels], both K-major: planes of
                         // eight pixels, 2048 / 2304 bytes each
-                        const uint32_t idesc_t = make_idesc16(128, NCH + 16, p.fmt, 0, 0);
+                        const uint32_t idesc_t = make_idesc16(128, NCH + 16, fmt_k, 0, 0);
                         if (elect_one())
                             for (int s = 0; s < nb; ++s)
                                 for (int ks = 0; ks < n / 16; ++ks) {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 named_bar_sync(2, n_epi + 32); ++ph;
                 tc_fence_after();
                 if (dbg && lane == 0) dbg[16] = clock64();
-                const uint32_t idesc_out = make_idesc16(128, 32, p.fmt, 0, 0);
+                const uint32_t idesc_out = make_idesc16(128, 32, fmt_k, 0, 0);
                 {
                     const int nb = p.nb, col_out = p.col_out;
                     const uint32_t p_off = p.p_off, ct_off = p.ct_off;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
             // the ones row of the V operand (row 128 of every plane; rows 129..143 feed context columns nobody loads)
             for (int pl = et; pl < (p.nb * n) >> 3; pl += n_epi) {
                 const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-                *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)pl * 2304u + 128u * 16u) = pack8(ones, p.fmt);
+                *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)pl * 2304u + 128u * 16u) = pack8(ones, fmt_k);
             }
             if (dbg && r == 0) dbg[3] = clock64();
             esync();
@@ -440,10 +442,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 const uint32_t pl = (uint32_t)(col0 + c) >> 3;
                 uint8_t* pd = smem + p.p_off + pl * 2048u + (uint32_t)d * 16u;
                 uint8_t* vd = smem + p.v_off + pl * 2304u + (uint32_t)d * 16u;
-                *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
-                *reinterpret_cast<uint4*>(pd + 2048u) = pack8(kv + 8, p.fmt);
-                *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
-                *reinterpret_cast<uint4*>(vd + 2304u) = pack8(vv + 8, p.fmt);
+                *reinterpret_cast<uint4*>(pd) = pack8(kv, fmt_k);
+                *reinterpret_cast<uint4*>(pd + 2048u) = pack8(kv + 8, fmt_k);
+                *reinterpret_cast<uint4*>(vd) = pack8(vv, fmt_k);
+                *reinterpret_cast<uint4*>(vd + 2304u) = pack8(vv + 8, fmt_k);
             }
             if (dbg && r == 0) dbg[4] = clock64();
             fence_proxy_async();
@@ -537,14 +539,14 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     }
                     uint8_t* pd = smem + p.p_off + (uint32_t)(c16 >> 3) * plane + row_off;
                     uint8_t* vd = smem + p.v_off + (uint32_t)(c16 >> 3) * plane + row_off;
-                    *reinterpret_cast<uint4*>(pd) = pack8(kv, p.fmt);
-                    *reinterpret_cast<uint4*>(pd + plane) = pack8(kv + 8, p.fmt);
-                    *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
-                    *reinterpret_cast<uint4*>(vd + plane) = pack8(vv + 8, p.fmt);
+                    *reinterpret_cast<uint4*>(pd) = pack8(kv, fmt_k);
+                    *reinterpret_cast<uint4*>(pd + plane) = pack8(kv + 8, fmt_k);
+                    *reinterpret_cast<uint4*>(vd) = pack8(vv, fmt_k);
+                    *reinterpret_cast<uint4*>(vd + plane) = pack8(vv + 8, fmt_k);
                 }
                 if (valid && cpart == 0) {
                     const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-                    *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)(NCH >> 3) * plane + row_off) = pack8(ones, p.fmt);
+                    *reinterpret_cast<uint4*>(smem + p.v_off + (uint32_t)(NCH >> 3) * plane + row_off) = pack8(ones, fmt_k);
                 }
             }
             if (dbg && r == 0) dbg[4] = clock64();
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     for (int e = 0; e < 32; ++e) {
                         if (e < e_lo || e >= e_hi) continue;
                         const float val = (e < 16 ? c0[e] : c1[e - 16]) * inv;
-                        const uint32_t u = pack2(val, 0.f, p.fmt);
+                        const uint32_t u = pack2(val, 0.f, fmt_k);
                         *reinterpret_cast<uint16_t*>(base + (uint32_t)(e >> 3) * 128u + (uint32_t)(e & 7) * 16u) = (uint16_t)(u & 0xFFFFu);
                     }
                 }
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                         for (int j = 0; j < 32; ++j) q[j] *= inv;
                         uint8_t* qd = smem + p.p_off + (uint32_t)(4 * (h2 + k)) * plane + row_off;
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, p.fmt);
+                        for (int cb = 0; cb < 4; ++cb) *reinterpret_cast<uint4*>(qd + (uint32_t)cb * plane) = pack8(q + cb * 8, fmt_k);
                     }
                 }
             }
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                         for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(ua[j]); v[16 + j] = __uint_as_float(ub[j]); }
                         uint8_t* od = smem + p.v_off + (uint32_t)(c32 >> 3) * plane + row_off;
 #pragma unroll
-                        for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(od + (uint32_t)k8 * plane) = pack8(v + 8 * k8, p.fmt);
+                        for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(od + (uint32_t)k8 * plane) = pack8(v + 8 * k8, fmt_k);
                     }
                 }
             fence_proxy_async();
@@ -675,10 +677,10 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const uint32_t kvrow = (uint32_t)((lane & (n - 1)) * p.nb + (lane >> lgn));
                     uint8_t* kd = kbuf + kvrow * KP + (uint32_t)c16 * 2u;
                     uint8_t* vd = vbuf + kvrow * KP + (uint32_t)c16 * 2u;
-                    *reinterpret_cast<uint4*>(kd) = pack8(kv, p.fmt);
-                    *reinterpret_cast<uint4*>(kd + 16) = pack8(kv + 8, p.fmt);
-                    *reinterpret_cast<uint4*>(vd) = pack8(vv, p.fmt);
-                    *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, p.fmt);
+                    *reinterpret_cast<uint4*>(kd) = pack8(kv, fmt_k);
+                    *reinterpret_cast<uint4*>(kd + 16) = pack8(kv + 8, fmt_k);
+                    *reinterpret_cast<uint4*>(vd) = pack8(vv, fmt_k);
+                    *reinterpret_cast<uint4*>(vd + 16) = pack8(vv + 8, fmt_k);
                     float4* qd = reinterpret_cast<float4*>(qbuf + lane * QP + c16);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) qd[k4] = make_float4(qv[4 * k4], qv[4 * k4 + 1], qv[4 * k4 + 2], qv[4 * k4 + 3]);
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) {
                             float kk[8];
-                            unpack8(*reinterpret_cast<const uint4*>(kr + cb * 16), kk, p.fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(kr + cb * 16), kk, fmt_k);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) a = fmaf(q[cb * 8 + e], kk[e], a);
                         }
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
 #pragma unroll
                         for (int cb = 0; cb < 4; ++cb) {
                             float vv[8];
-                            unpack8(*reinterpret_cast<const uint4*>(vr + cb * 16), vv, p.fmt);
+                            unpack8(*reinterpret_cast<const uint4*>(vr + cb * 16), vv, fmt_k);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) o[cb * 8 + e] = fmaf(a, vv[e], o[cb * 8 + e]);
                         }
@@ -744,7 +746,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                 // 'b h (x y) d -> b (h d) x y' (unet.py:121): channel = h*32 + d, as the A operand of the to_out conv
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb)
-                    *reinterpret_cast<uint4*>(smem + p.p_off + (uint32_t)(4 * h + cb) * plane + (uint32_t)row * 16u) = pack8(o + cb * 8, p.fmt);
+                    *reinterpret_cast<uint4*>(smem + p.p_off + (uint32_t)(4 * h + cb) * plane + (uint32_t)row * 16u) = pack8(o + cb * 8, fmt_k);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const float4* xb = reinterpret_cast<const float4*>(xbuf + r * C + c16);
 #pragma unroll
                     for (int cb = 0; cb < 8; ++cb)
-                        if (cb == (c16 >> 3)) { unpack8(xres[cb], x2, p.fmt); unpack8(xres[cb + (cb < 7 ? 1 : 0)], x2 + 8, p.fmt); }
+                        if (cb == (c16 >> 3)) { unpack8(xres[cb], x2, fmt_k); unpack8(xres[cb + (cb < 7 ? 1 : 0)], x2 + 8, fmt_k); }
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const float4 o = xb[k4];
@@ -858,7 +860,7 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                             v[j] = y + x2[j];
                         }
                     }
-                    attn_write_out(p, b0, px, c16, v);
+                    attn_write_out(p, b0, px, c16, v, fmt_k);
                 }
             }
         } else {
@@ -962,11 +964,11 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     const float4* ys = reinterpret_cast<const float4*>(ybuf + row * QP + c16);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) { const float4 t4 = ys[k4]; v[4 * k4] = t4.x; v[4 * k4 + 1] = t4.y; v[4 * k4 + 2] = t4.z; v[4 * k4 + 3] = t4.w; }
-                    unpack8(xa, x2, p.fmt);
-                    unpack8(xb, x2 + 8, p.fmt);
+                    unpack8(xa, x2, fmt_k);
+                    unpack8(xb, x2 + 8, fmt_k);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = v[j] + bias[c16 + j] + x2[j];
-                    attn_write_out(p, b, px, c16, v);
+                    attn_write_out(p, b, px, c16, v, fmt_k);
                 }
             }
         } else {
@@ -990,15 +992,15 @@ __global__ void __launch_bounds__(ATTN_MAX_THREADS) k_attn(const __grid_constant
                     float v[16], x2[16];
                     tmem_ld16(tlane + (uint32_t)(p.col_proj + t * C + c16), v);
                     if (valid) {
-                        unpack8(xa, x2, p.fmt);
-                        unpack8(xb, x2 + 8, p.fmt);
+                        unpack8(xa, x2, fmt_k);
+                        unpack8(xb, x2 + 8, fmt_k);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float y = (v[j] + bias[c16 + j] - ms.x) * ms.y * gamma[c16 + j] + beta[c16 + j];
                             v[j] = y + x2[j];
                         }
                     }
-                    attn_write_out_w(p, b, px, c16, v, valid);
+                    attn_write_out_w(p, b, px, c16, v, valid, fmt_k);
                     xa = na; xb = nb4;
                 }
             }
@@ -1537,7 +1539,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_attn_small(const __grid_co
                 if (LINEAR) y = (y - mean) * rstd * gamma[c16 + j] + beta[c16 + j];
                 v[k][j] = y + x2[j];
             }
-            attn_write_out_w(p, b, px, c16, v[k], valid);
+            attn_write_out_w(p, b, px, c16, v[k], valid, p.fmt);
         }
         }
         if (dbg && et == 0) dbg[28] = clock64();
@@ -1553,8 +1555,10 @@ cudaError_t attn_configure() {
     cudaError_t e = cudaFuncSetAttribute(k_attn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn<4, true, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attn_small<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1579,8 +1583,8 @@ cudaError_t launch_attn_fused(const AttnFusedParams& p, const CUtensorMap& xh_ma
     }
     const void* fn = p.hc == 2 ? (const void*)k_attn<2> : ((p.ktrans && !p.full) ? (const void*)k_attn<4, true> : (const void*)k_attn<4>);
     if (p.hc == 4 && p.ktrans && !p.full && p.n >= 64) {
-        if (p.n_mtiles == 2 && p.epi_warps == 16) fn = (const void*)k_attn<4, true, 2>;
-        if (p.n_mtiles == 1 && p.epi_warps == 8) fn = (const void*)k_attn<4, true, 1>;
+        if (p.n_mtiles == 2 && p.epi_warps == 16) fn = p.fmt ? (const void*)k_attn<4, true, 2, 1> : (const void*)k_attn<4, true, 2, 0>;
+        if (p.n_mtiles == 1 && p.epi_warps == 8) fn = p.fmt ? (const void*)k_attn<4, true, 1, 1> : (const void*)k_attn<4, true, 1, 0>;
     }
     return launch_pdl(fn, grid * p.hsplit, (p.epi_warps + 2) * 32, (size_t)p.smem_bytes, s, args, p.hsplit);
 }
