@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (MT <= 2 && !SPLIT && !WIDE) ? 
     const uint32_t tmem_slot = bar_epi + 8;
     const uint32_t bar_x = tmem_slot + 8;
     const uint32_t bar_epi2 = bar_x + 8;         // transaction hand-off: steps alternate between bar_epi and bar_epi2
-    const bool txh = SPLIT && p.tx_handoff != 0;
+    const bool txh = SPLIT && (ENDS == 0 ? true : p.tx_handoff != 0);      // (the lean N-split instance is only launched with it)
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 16 * MAX_WSTAGES + 24);
     const Geo geo = make_geo(p);
     // N-split: the Q CTAs of a cluster own the same samples and 1/Q of every step's output channels
@@ -1359,9 +1359,9 @@ int fused_max_active_clusters(int nsplit, int smem_bytes) {
 }
 
 template <int FMT>
-static const void* chain_fn(int mt, bool split, bool fast, bool wide, int ends) {
+static const void* chain_fn(int mt, bool split, bool fast, bool wide, int ends, bool txh) {
     if (ends == 0 && !fast && mt == 1) {
-        if (split) return (const void*)k_chain<1, true, FMT, false, false, 0>;
+        if (split && txh) return (const void*)k_chain<1, true, FMT, false, false, 0>;
         if (wide) return (const void*)k_chain<1, false, FMT, false, true, 0>;
     }
     if (wide && !fast && !split && mt == 1) return (const void*)k_chain<1, false, FMT, false, true>;
@@ -1384,8 +1384,8 @@ cudaError_t launch_chain(const ChainParams& p, const CUtensorMap* maps, int grid
     if (p.nsplit > 1 && p.n_mtiles != 1) return cudaErrorInvalidValue;
     int ends = 0;
     for (int i = 0; i < p.n_steps; ++i) ends |= (p.st[i].epi == CE_INIT ? 1 : 0) | (p.st[i].final != 0 ? 2 : 0);
-    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends)
-                           : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends);
+    const void* fn = p.fmt ? chain_fn<1>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends, p.tx_handoff != 0)
+                           : chain_fn<0>(p.n_mtiles, p.nsplit > 1, p.fast != 0, p.wide != 0, ends, p.tx_handoff != 0);
     if (!fn) return cudaErrorInvalidValue;
     void* args[5] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&maps[3], (void*)&p};
     return launch_pdl(fn, grid * p.nsplit, FUSED_THREADS, (size_t)p.smem_bytes, s, args, p.nsplit);
