@@ -1362,7 +1362,7 @@ template <int FMT>
 static const void* chain_fn(int mt, bool split, bool fast, bool wide, int ends, bool txh) {
     if (ends == 0 && !fast && mt == 1) {
         if (split && txh) return (const void*)k_chain<1, true, FMT, false, false, 0>;
-        if (wide) return (const void*)k_chain<1, false, FMT, false, true, 0>;
+        if (!split && wide) return (const void*)k_chain<1, false, FMT, false, true, 0>;
     }
     if (wide && !fast && !split && mt == 1) return (const void*)k_chain<1, false, FMT, false, true>;
     if (fast) {
