@@ -8,9 +8,10 @@
 //           * the conv bias folded into the GEMM (one extra K slice: a constant "ones" A tile x a B tile holding the
 //             bias split into a 16-bit high part and a 16-bit remainder, so it is exact to ~2^-17),
 //           * the ResnetBlock 1x1 res_conv accumulated into a second TMEM region (never leaves TMEM),
-//           * GroupNorm statistics reduced with warp shuffles, then GroupNorm affine and FiLM collapsed per step into
-//             ONE (scale, offset) pair per (sample, channel) in shared memory, so the normalise pass is one FMA +
-//             SiLU per element,
+//           * GroupNorm statistics reduced with warp shuffles on register-resident accumulator chunks wherever the row
+//             geometry allows it (one sample per CTA: FAST; 2x2 N-split stages: a sample = one half-warp; 4x4 stages: a
+//             sample's valid rows = one warp) -- otherwise per-row partial sums and ONE (scale, offset) pair per (sample,
+//             channel) in shared memory, so that the normalise pass is one FMA + SiLU per element,
 //           * the PreNorm of the following attention block fused into the last epilogue,
 //           * init_conv (unet.py:295) as the first epilogue of the first stage and final_conv + the RK4 / Euler
 //             / CFG stage update (unet.py:372, sampling.py:43-48,69-74) as the last epilogue of the last stage.
@@ -21,10 +22,13 @@
 // CTA a warp group owns whole tiles (tile t -> group t & 1), with one M tile the groups split the output channels
 // (group g -> channels [g C/2, (g+1) C/2)), so a thread normalises 8..16 accumulator values per step instead of 32:
 // the epilogue is a latency chain (TMEM load -> FMA -> MUFU -> pack -> store), and its length, not the instruction
-// count, is what a step costs.  The kernel is templated on the M tiles per CTA, the N-split and the 16-bit operand
-// format, so tile loops, row bookkeeping and pack/unpack code are static.
-// Steps alternate MMA(i) -> EPI(i) -> MMA(i+1) ... through two mbarriers (bar_mma: tcgen05.commit, bar_epi: 256
-// arrivals); overlap of one sample group's epilogue with another's MMAs comes from the co-resident CTA.
+// count, is what a step costs.  The kernel is templated on everything that is uniform per launch -- M tiles per CTA,
+// N-split, 16-bit operand format, FAST epilogue, the two-CTAs-per-SM register cap (WIDE lifts it for single-wave
+// launches), init / final code (ENDS) -- and a stage launches the instance that matches it: tile loops, row bookkeeping
+// and pack/unpack code are static, and no launch pays registers or spills for code it never runs.
+// Steps alternate MMA(i) -> EPI(i) -> MMA(i+1) ...: bar_mma (tcgen05.commit) one way; back, inside one CTA a named
+// barrier, across a cluster the output stores themselves (st.async completing transaction bytes on the consumers'
+// mbarriers).  Overlap of one sample group's epilogue with another's MMAs comes from the co-resident CTA.
 #include <cuda_fp16.h>
 
 #include <cstring>
