@@ -100,3 +100,24 @@ def test_create_without_gpu_fails_loudly():
     with pytest.raises(RuntimeError):
         _lib.Engine(dim=16, channels=4, dim_mults=(1, 2, 4, 8), groups=4, n_classes=0, height=16, width=16,
                     compute_dtype="fp32", device="cpu", state_dict=m.state_dict())
+
+
+def test_fused_plan_decisions_round2():
+    """Host-only planner checks (no GPU): (1) a stage that allocates all 512 tensor-memory columns must not fit twice on an SM
+    (a second co-resident CTA would sit in tcgen05.alloc until the first exits: downs.1.2 ran as two waves before the planner
+    asked for more than half an SM); (2) the small-batch plan gives the 4x4 / 2x2 attention blocks quarter-filled tiles."""
+    import re
+    cfg = _lib.make_cfg(dim=16, channels=4, dim_mults=[1, 2, 4, 8], groups=4, n_classes=0, height=16, width=16,
+                        compute_dtype="bf16", device_index=0)
+    lines = [l for l in _lib.describe_plan(cfg, 256).splitlines() if l.startswith("stage")]
+    attn = [l for l in lines if " attn " in l]
+    assert len(attn) == 9 and len(lines) == 19
+    sm_bytes = 233472                                     # shared memory per SM; every CTA also reserves 1 KB
+    for l in attn:
+        smem, tmem = int(re.search(r"smem=(\d+)", l).group(1)), int(re.search(r"tmem=(\d+)", l).group(1))
+        if tmem > 256:
+            assert 2 * (smem + 1024) > sm_bytes, l
+    by_name = {l.split()[3]: l for l in attn}
+    assert "nb=2 " in by_name["downs.2.2"] and "ctas=128" in by_name["downs.2.2"]      # 4x4: 32 live rows per CTA
+    assert "nb=8 " in by_name["downs.3.2"] and "ctas=32" in by_name["downs.3.2"]       # 2x2
+    assert "nb=8 " in by_name["mid_attn"] and "full=1" in by_name["mid_attn"]
